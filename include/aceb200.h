@@ -1,0 +1,189 @@
+/*
+ * aceb200.h -- C ABI of the B200-native ACE evaluation hot path.
+ *
+ * This is the drop-in boundary under ACE.jl's evaluation methods.  ACE.jl has
+ * no FFI of its own; its extension seam is multiple dispatch on the `evaluator` field of
+ * `LinearACEModel` (src/linearmodel.jl:36-40, 107-111, 133-134) and on the basis types.  Each entry
+ * point below names the reference method(s) it replaces.  Host code (Julia `ccall`, or the ctypes
+ * mirror in ace_jl_b200/) fills `aceb200_desc` from the live basis/model objects once; all tables
+ * are copied to the GPU at `aceb200_model_create`.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative ACEB200_E* code; the message is available
+ *     from aceb200_last_error() (thread-local).  Nothing aborts.
+ *   - all index tables are 1-based exactly as the Julia objects hold them (converted once, on
+ *     upload); integers are int32 unless stated.
+ *   - complex numbers are interleaved (re, im) doubles.
+ *   - the caller owns every buffer and keeps it alive for the duration of the call; no pointer is
+ *     retained after a call returns (tables are copied at create).
+ *   - a model handle is immutable except through aceb200_set_params(); evaluation calls on one
+ *     handle may be issued from several host threads (they serialise on the handle's workspace).
+ *   - there is NO CPU fallback: without a CUDA device every call fails with ACEB200_ECUDA.
+ */
+#ifndef ACEB200_H
+#define ACEB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACEB200_ABI_VERSION 1
+
+/* error codes */
+#define ACEB200_OK            0
+#define ACEB200_EDESC        -1   /* malformed descriptor / batch                         */
+#define ACEB200_EUNSUPPORTED -2   /* transform / component / size outside the supported set */
+#define ACEB200_ECUDA        -3   /* CUDA runtime error (including "no device")            */
+#define ACEB200_ENOMEM       -4   /* out of device or host memory                          */
+#define ACEB200_EEMPTY       -5   /* an environment with zero neighbours where the reference
+                                     asserts length(cfg) > 0 (src/product_1pbasis.jl:124)     */
+#define ACEB200_ECATEGORY    -6   /* species code outside 1..n_cat (src/discrete1pbasis.jl:39) */
+
+/* distance transforms: the closed set of src/transforms/distancetransforms.jl:16-25 */
+#define ACEB200_TRANS_ID     0    /* t = r                                  par: -                */
+#define ACEB200_TRANS_POLY   1    /* t = ((1+r0)/(1+r))^p                   par: p, r0            */
+#define ACEB200_TRANS_MORSE  2    /* t = exp(-lambda (r/r0 - 1))            par: lambda, r0       */
+#define ACEB200_TRANS_AGNESI 3    /* t = 1/(1 + a (r/r0)^p)                 par: r0, p, a         */
+
+/* one-particle basis component kinds, in the order of Product1pBasis.bases (src/product_1pbasis.jl:5-8) */
+#define ACEB200_COMP_RN   0       /* Rn1pBasis   (src/b1pcomponents/Rn.jl:17-29)   */
+#define ACEB200_COMP_YLM  1       /* Ylm1pBasis  (src/b1pcomponents/Ylm.jl:18-26)  */
+#define ACEB200_COMP_CAT  2       /* Categorical1pBasis (src/discrete1pbasis.jl:58) */
+#define ACEB200_MAX_COMP  4
+
+/* memory space of batch inputs and of the outputs of a call */
+#define ACEB200_HOST   0
+#define ACEB200_DEVICE 1
+
+typedef struct aceb200_model aceb200_model;
+
+/* Everything a LinearACEModel / SymmetricBasis holds that evaluation needs. */
+typedef struct aceb200_desc {
+    int32_t abi_version;        /* = ACEB200_ABI_VERSION */
+    int32_t struct_bytes;       /* = sizeof(aceb200_desc) */
+
+    /* radial basis: OrthPolyBasis (src/polynomials/orthpolys.jl:82-92) of the transformed distance */
+    int32_t n_rad;              /* length(J) = N                                  */
+    int32_t pl, pr;             /* envelope powers                                */
+    double  tl, tr;             /* envelope roots (transformed variable)          */
+    const double *rad_A;        /* [n_rad] recursion coefficients                 */
+    const double *rad_B;        /* [n_rad]                                        */
+    const double *rad_C;        /* [n_rad]                                        */
+    int32_t trans_kind;         /* ACEB200_TRANS_*, parsed from Lambda.exstr (src/transforms/lambdas.jl:9-12) */
+    int32_t _pad0;
+    double  trans_par[4];
+
+    /* angular basis: SHBasis(maxL) (src/polynomials/sphericalharmonics.jl:285-291) */
+    int32_t maxL;
+    /* categorical basis: number of categories Q, 0 if there is no Categorical1pBasis */
+    int32_t n_cat;
+
+    /* Product1pBasis (src/product_1pbasis.jl:5-8) */
+    int32_t n_comp;                         /* NB                                          */
+    int32_t comp_kind[ACEB200_MAX_COMP];    /* kind of bases[i]                            */
+    int32_t nA;                             /* length(basis1p)                             */
+    const int32_t *indices;                 /* [nA][n_comp] = Vector{NTuple{NB,Int}}, 1-based */
+
+    /* PIBasisSpec (src/pibasis.jl:10-13) */
+    int32_t nAA;
+    int32_t maxord;                         /* size(iAA2iA, 2)                             */
+    const int32_t *orders;                  /* [nAA]                                       */
+    const int32_t *iAA2iA;                  /* column-major nAA x maxord (Julia Matrix), 1-based, 0 = padding */
+    int32_t pireal;                         /* PIBasis.real === real (src/pibasis.jl:148)  */
+    int32_t symreal;                        /* SymmetricBasis.real === real (src/symmbasis.jl:37) */
+
+    /* A2Bmap::SparseMatrixCSC{PROP,Int} (src/symmbasis.jl:33-38), nB x nAA */
+    int32_t nB;
+    int32_t ncomp;                          /* complex components per entry: 1, 3 or 9     */
+    int64_t nnz;
+    const int32_t *colptr;                  /* [nAA+1], 1-based                            */
+    const int32_t *rowval;                  /* [nnz],   1-based                            */
+    const double  *nzval;                   /* [nnz][ncomp] complex                        */
+
+    /* LinearACEModel.c (src/linearmodel.jl:36-40): Vector{T} or Vector{SVector{nprop,T}} */
+    int32_t nprop;
+    int32_t _pad1;
+    const double *c;                        /* [nB][nprop] real; may be NULL (zeros)       */
+} aceb200_desc;
+
+/* A ragged batch of atomic environments.  R has exactly the memory of
+ * Vector{PositionState{Float64}} (src/states.jl:396: isbits, 24-byte stride) for the
+ * concatenated configurations. */
+typedef struct aceb200_batch {
+    int64_t nenv;
+    const int64_t *offsets;     /* [nenv+1], offsets[0] = 0; environment e owns neighbours offsets[e]..offsets[e+1]-1 */
+    const double  *R;           /* [offsets[nenv]][3]                                                              */
+    const int32_t *species;     /* [offsets[nenv]] 1-based category index (val2i, src/discrete1pbasis.jl:33), or NULL */
+    int32_t space;              /* ACEB200_HOST or ACEB200_DEVICE: where offsets/R/species AND the outputs live     */
+    int32_t _pad;
+} aceb200_batch;
+
+/* ---- lifecycle -------------------------------------------------------------------------- */
+
+/* number of CUDA devices visible; <= 0 means the library cannot run */
+int aceb200_device_count(void);
+/* device used by models created afterwards from this host thread (default 0) */
+int aceb200_set_device(int device);
+/* copy `n` bytes of the calling thread's last error message */
+int aceb200_last_error(char *buf, int n);
+
+/* Replaces the construction of a ProductEvaluator (src/evaluator.jl:30-31) plus the read-only use of
+ * basis1p / pibasis.spec / A2Bmap by every evaluate method.  Uploads all tables, computes c~. */
+int aceb200_model_create(const aceb200_desc *desc, aceb200_model **out);
+int aceb200_model_destroy(aceb200_model *m);
+/* set_params!(m, c) -> _get_eff_coeffs! (src/linearmodel.jl:67-71, src/evaluator.jl:48-66); c is [nB][nprop] host */
+int aceb200_set_params(aceb200_model *m, const double *c, int64_t n);
+/* read back c~ = A2Bmap^T c as [nAA][nprop][ncomp] complex (ProductEvaluator.coeffs, src/evaluator.jl:11) */
+int aceb200_get_eff_coeffs(aceb200_model *m, double *ctilde);
+/* run subsequent calls on this CUDA stream (a cudaStream_t); NULL = the legacy default stream */
+int aceb200_set_stream(aceb200_model *m, void *cuda_stream);
+/* number of kernels this handle has launched so far (monotone counter, for audits) */
+int64_t aceb200_launch_count(const aceb200_model *m);
+
+/* ---- basis values ------------------------------------------------------------------------ */
+
+/* evaluate(basis1p::Product1pBasis, cfg) (src/product_1pbasis.jl:123-134): A [nenv][nA] complex */
+int aceb200_eval_A(aceb200_model *m, const aceb200_batch *b, double *A);
+/* evaluate(pibasis::PIBasis, cfg) (src/pibasis.jl:258-294): AA [nenv][nAA], real if pireal else complex */
+int aceb200_eval_AA(aceb200_model *m, const aceb200_batch *b, double *AA);
+/* evaluate(basis::SymmetricBasis, cfg) (src/symmbasis.jl:297-316): B [nenv][nB][ncomp], real if symreal else complex */
+int aceb200_eval_B(aceb200_model *m, const aceb200_batch *b, double *B);
+
+/* ---- basis Jacobians (evaluate_d / evaluate_ed) -------------------------------------------- */
+/* Per environment these are Julia Matrix{DState}(nbasis x J), column-major: [neighbour][basis index][...]. */
+
+/* evaluate_ed(basis1p, cfg) (src/product_1pbasis.jl:234-250): A as above (may be NULL),
+ * dA [sum J][nA][3] complex */
+int aceb200_eval_dA(aceb200_model *m, const aceb200_batch *b, double *A, double *dA);
+/* evaluate_ed(pibasis, cfg) (src/pibasis.jl:303-332, 402-432): dAA [sum J][nAA][3], real if pireal else complex */
+int aceb200_eval_dAA(aceb200_model *m, const aceb200_batch *b, double *AA, double *dAA);
+/* evaluate_ed(basis, cfg) (src/symmbasis.jl:322-336): dB [sum J][nB][3][ncomp] (component fastest,
+ * the memory of coco_o_daa's result, src/properties.jl:53-59), real if symreal else complex */
+int aceb200_eval_dB(aceb200_model *m, const aceb200_batch *b, double *B, double *dB);
+
+/* ---- linear model ------------------------------------------------------------------------- */
+
+/* evaluate(m::LinearACEModel, cfg) via ProductEvaluator (src/evaluator.jl:121-147):
+ * E [nenv][nprop][ncomp], real if symreal else complex */
+int aceb200_energy(aceb200_model *m, const aceb200_batch *b, double *E);
+/* evaluate + grad_config (src/evaluator.jl:150-200): G [sum J][nprop][3][ncomp] (component fastest),
+ * real if symreal else complex; E may be NULL */
+int aceb200_energy_forces(aceb200_model *m, const aceb200_batch *b, double *E, double *G);
+/* grad_params(m, cfg) (src/linearmodel.jl:114-123) is eval_B; grad_params_config (:127) is eval_dB. */
+
+/* ---- introspection (sizes the host needs to allocate outputs) ------------------------------ */
+typedef struct aceb200_sizes {
+    int32_t nA, nAA, nB, ncomp, nprop, maxord, pireal, symreal;
+} aceb200_sizes;
+int aceb200_model_sizes(const aceb200_model *m, aceb200_sizes *out);
+
+/* Device-side timing of the last evaluation call on this handle, in milliseconds: CUDA events
+ * recorded on the handle's stream around the kernel launches only (no copies). */
+int aceb200_last_kernel_ms(const aceb200_model *m, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACEB200_H */
