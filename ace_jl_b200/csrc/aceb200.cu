@@ -1,0 +1,730 @@
+// aceb200.cu -- the C ABI of include/aceb200.h on top of the kernels in ace_kernels.cuh.
+//
+// Host-side responsibilities: validate and flatten the descriptor (ace_tables.h), upload tables,
+// keep c~ and the tree weights in sync with set_params, split a batch into chunks that fit the
+// workspace, move host batches to the device and results back, launch.  There is no CPU evaluation
+// path in this file: every entry point needs a CUDA device.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "ace_platform.cuh"
+#include "ace_kernels.cuh"
+#include "ace_tables.h"
+
+using namespace aceb200;
+
+// ----------------------------------------------------------------------------------------------
+// errors
+// ----------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static thread_local int g_device = 0;
+
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t err__ = (call);                                                               \
+        if (err__ != cudaSuccess)                                                                 \
+            throw ModelError(err__ == cudaErrorMemoryAllocation ? ACEB200_ENOMEM : ACEB200_ECUDA, \
+                             std::string(#call) + ": " + cudaGetErrorString(err__));              \
+    } while (0)
+
+// ----------------------------------------------------------------------------------------------
+// device buffers
+// ----------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    void reserve(size_t n)
+    {
+        if (n <= bytes) return;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        CU(cudaMalloc(&p, n));
+        bytes = n;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+template <class T>
+static T* upload(std::vector<DevBuf>& pool, const std::vector<T>& v)
+{
+    pool.emplace_back();
+    DevBuf& b = pool.back();
+    b.reserve(std::max<size_t>(v.size(), 1) * sizeof(T));
+    if (!v.empty()) CU(cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return b.as<T>();
+}
+
+// ----------------------------------------------------------------------------------------------
+// the model handle
+// ----------------------------------------------------------------------------------------------
+struct aceb200_model {
+    int device = 0;
+    HostTables T;
+    RadialParams rp;
+    AlpParams ap;
+    std::vector<cplx> ctilde;       // [nAA][P]
+    bool cw = false;                // complex tree weights
+    int PB = 1, Ppad = 1, NMAX = 8;
+    // device tables
+    std::vector<DevBuf> pool;
+    ColumnsDev C;
+    const int *d_slot_pos = nullptr, *d_slot_neg = nullptr, *d_code = nullptr;
+    const int *d_orders = nullptr, *d_spec = nullptr;
+    const int *d_csr_ptr = nullptr, *d_csr_col = nullptr;
+    const c2* d_csr_val = nullptr;
+    TreeDev tree[kMaxOrdDev + 1];
+    DevBuf d_w0, d_w1;
+    DevBuf d_lw[kMaxOrdDev + 1];
+    // per-call workspace (guarded by mu)
+    std::mutex mu;
+    DevBuf ws_Ac, ws_Dt, ws_envidx, ws_E, ws_G, ws_A, ws_AA, ws_dA, ws_dAA, ws_out, ws_err;
+    DevBuf in_off, in_R, in_sp;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_ms = 0.0;
+    long long launches = 0;
+    int sm_count = 148;
+    int smem_optin = 227 * 1024;
+};
+
+static int pick_nmax(int n)
+{
+    const int opts[] = {4, 8, 12, 16, 20, 24, 32};
+    for (int o : opts) if (n <= o) return o;
+    return 32;
+}
+
+static int pick_pb(int P)
+{
+    if (P == 1) return 1;
+    if (P <= 2) return 2;
+    if (P == 3 || P == 9) return 3;
+    return 4;
+}
+
+static void fill_params(aceb200_model* m, const aceb200_desc& d)
+{
+    RadialParams& rp = m->rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.N = d.n_rad; rp.pl = d.pl; rp.pr = d.pr; rp.tkind = d.trans_kind; rp.tl = d.tl; rp.tr = d.tr;
+    for (int i = 0; i < 4; ++i) rp.tpar[i] = d.trans_par[i];
+    for (int i = 0; i < d.n_rad; ++i) { rp.A[i] = d.rad_A[i]; rp.B[i] = d.rad_B[i]; rp.C[i] = d.rad_C[i]; }
+    AlpParams& ap = m->ap;
+    memset(&ap, 0, sizeof(ap));
+    ap.L = m->T.Lused;
+    // src/polynomials/sphericalharmonics.jl:146-159
+    for (int l = 2; l <= ap.L; ++l)
+        for (int mm = 0; mm <= l - 2; ++mm) {
+            double ls = (double)l * l, lm1s = (double)(l - 1) * (l - 1), ms = (double)mm * mm;
+            ap.A[index_p(l, mm)] = sqrt((4 * ls - 1.0) / (ls - ms));
+            ap.B[index_p(l, mm)] = -sqrt((lm1s - ms) / (4 * lm1s - 1.0));
+        }
+    ap.diagc[0] = 0.0;
+    ap.diagc[1] = sqrt(1.5);                                   // :180
+    for (int mm = 2; mm <= kMaxL + 1; ++mm) ap.diagc[mm] = sqrt(1.0 + 0.5 / mm);   // :192
+    for (int mm = 0; mm <= kMaxL + 1; ++mm) ap.offc[mm] = sqrt(2.0 * mm + 3.0);    // :179, :191
+}
+
+// c~ and the weights that depend on it: order-0/1 weights and the leaf weights of every tree
+static void upload_weights(aceb200_model* m, const double* c)
+{
+    HostTables& T = m->T;
+    eff_coeffs(T, c, m->ctilde);
+    bool cw = false;
+    for (const cplx& z : m->ctilde) if (z.imag() != 0.0) { cw = true; break; }
+    if (cw && T.pireal)
+        throw ModelError(ACEB200_EUNSUPPORTED, "complex effective coefficients with a real AA basis (pireal) are not supported");
+    m->cw = cw;
+    const int P = T.P, Ppad = m->Ppad, cs = cw ? 2 : 1;
+    auto put = [&](std::vector<double>& w, size_t row, int aa, double mult) {
+        for (int p = 0; p < P; ++p) {
+            cplx z = m->ctilde[(size_t)aa * P + p] * mult;
+            w[(row * Ppad + p) * cs] = z.real();
+            if (cw) w[(row * Ppad + p) * cs + 1] = z.imag();
+        }
+    };
+    std::vector<double> w0((size_t)Ppad * cs, 0.0), w1((size_t)T.nA * Ppad * cs, 0.0);
+    if (T.has_const) put(w0, 0, 0, 1.0);
+    for (int a = 0; a < T.nA; ++a) if (T.aa1_of_target[a] >= 0) put(w1, a, T.aa1_of_target[a], 1.0);
+    m->d_w0.reserve(w0.size() * sizeof(double));
+    m->d_w1.reserve(w1.size() * sizeof(double));
+    CU(cudaMemcpy(m->d_w0.p, w0.data(), w0.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(m->d_w1.p, w1.data(), w1.size() * sizeof(double), cudaMemcpyHostToDevice));
+    for (int nu = 2; nu <= T.maxord; ++nu) {
+        const Tree& tr = T.trees[nu];
+        std::vector<double> lw(std::max<size_t>(tr.lidx.size(), 1) * Ppad * cs, 0.0);
+        for (size_t i = 0; i < tr.lidx.size(); ++i) put(lw, i, tr.laa[i], (double)tr.lmult[i]);
+        m->d_lw[nu].reserve(lw.size() * sizeof(double));
+        CU(cudaMemcpy(m->d_lw[nu].p, lw.data(), lw.size() * sizeof(double), cudaMemcpyHostToDevice));
+        m->tree[nu].lw = m->d_lw[nu].as<double>();
+    }
+}
+
+static void upload_tables(aceb200_model* m)
+{
+    HostTables& T = m->T;
+    std::vector<int32_t> cq, cl, cm, cc, cb, ci;
+    for (const Column& c : T.cols) { cq.push_back(c.q); cl.push_back(c.l); cm.push_back(c.m); cc.push_back(c.cnt); cb.push_back(c.base); ci.push_back(c.ip); }
+    ColumnsDev& C = m->C;
+    C.ncols = T.ncols; C.nS = T.nS; C.nPused = (T.Lused + 1) * (T.Lused + 2) / 2; C.nQ = T.nQ;
+    C.q = upload(m->pool, cq); C.l = upload(m->pool, cl); C.m = upload(m->pool, cm);
+    C.cnt = upload(m->pool, cc); C.base = upload(m->pool, cb); C.ip = upload(m->pool, ci);
+    C.colmap = upload(m->pool, T.colmap);
+    m->d_slot_pos = upload(m->pool, T.slot_pos);
+    m->d_slot_neg = upload(m->pool, T.slot_neg);
+    m->d_code = upload(m->pool, T.iA_code);
+    m->d_orders = upload(m->pool, T.orders);
+    m->d_spec = upload(m->pool, T.spec);
+    m->d_csr_ptr = upload(m->pool, T.csr_ptr);
+    m->d_csr_col = upload(m->pool, T.csr_col);
+    std::vector<c2> val(T.csr_val.size());
+    for (size_t k = 0; k < val.size(); ++k) val[k] = c2{T.csr_val[k].real(), T.csr_val[k].imag()};
+    m->d_csr_val = upload(m->pool, val);
+    for (int nu = 2; nu <= T.maxord; ++nu) {
+        const Tree& tr = T.trees[nu];
+        TreeDev& D = m->tree[nu];
+        memset(&D, 0, sizeof(D));
+        D.ptr0 = upload(m->pool, tr.ptr0);
+        for (int k = 0; k < nu - 2; ++k) { D.nidx[k] = upload(m->pool, tr.nidx[k]); D.nptr[k] = upload(m->pool, tr.nptr[k]); }
+        D.lidx = upload(m->pool, tr.lidx);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// batch handling
+// ----------------------------------------------------------------------------------------------
+struct Chunk { long long e0, e1, j0, j1; };
+
+struct BatchView {
+    const aceb200_batch* b;
+    std::vector<long long> host_off;    // chunk boundary offsets when the batch is on the device; all offsets when on the host
+    long long nenv, nJ;
+};
+
+// environments per chunk: bounded by a workspace budget per environment
+static long long chunk_envs(long long nenv, size_t bytes_per_env, size_t budget)
+{
+    long long n = (long long)(budget / std::max<size_t>(bytes_per_env, 1));
+    n = std::max<long long>(32, (n / 32) * 32);
+    return std::min<long long>(n, ((nenv + 31) / 32) * 32);
+}
+
+__global__ void k_gather_offsets(const long long* off, long long nenv, long long step, long long nb, long long* out)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > nb) return;
+    long long e = i * step;
+    if (e > nenv) e = nenv;
+    out[i] = off[e];
+}
+
+// Per-call state: where the inputs of a chunk live on the device.
+struct Staged {
+    const long long* off;   // device, points at the chunk's first offset
+    const double* R;        // device
+    const int* species;     // device or null
+    long long jbase;        // absolute neighbour index of R[0]
+};
+
+static void validate_batch(const aceb200_batch* b)
+{
+    if (!b) throw ModelError(ACEB200_EDESC, "null batch");
+    if (b->nenv < 0) throw ModelError(ACEB200_EDESC, "negative nenv");
+    if (b->nenv > 0 && (!b->offsets || !b->R)) throw ModelError(ACEB200_EDESC, "null offsets / R");
+    if (b->space != ACEB200_HOST && b->space != ACEB200_DEVICE) throw ModelError(ACEB200_EDESC, "batch.space must be HOST or DEVICE");
+}
+
+// boundary offsets for chunks of `step` environments
+static std::vector<long long> boundary_offsets(aceb200_model* m, const aceb200_batch* b, long long step)
+{
+    long long nb = (b->nenv + step - 1) / step;
+    std::vector<long long> out(nb + 1);
+    if (b->space == ACEB200_HOST) {
+        for (long long i = 0; i <= nb; ++i) out[i] = b->offsets[std::min(i * step, (long long)b->nenv)];
+    } else {
+        m->ws_out.reserve((nb + 1) * sizeof(long long));
+        auto kfn = k_gather_offsets;
+        ACE_LAUNCH(kfn, dim3((unsigned)((nb + 1 + 127) / 128)), dim3(128), 0, m->stream, reinterpret_cast<const long long*>(b->offsets), (long long)b->nenv, step, nb, m->ws_out.as<long long>());
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out.data(), m->ws_out.p, (nb + 1) * sizeof(long long), cudaMemcpyDeviceToHost, m->stream));
+        CU(cudaStreamSynchronize(m->stream));
+    }
+    for (long long i = 0; i < nb; ++i)
+        if (out[i + 1] < out[i]) throw ModelError(ACEB200_EDESC, "offsets must be non-decreasing");
+    return out;
+}
+
+static Staged stage_chunk(aceb200_model* m, const aceb200_batch* b, const Chunk& c)
+{
+    Staged s;
+    long long ne = c.e1 - c.e0, nj = c.j1 - c.j0;
+    if (b->space == ACEB200_DEVICE) {
+        s.off = reinterpret_cast<const long long*>(b->offsets) + c.e0;
+        s.R = b->R + 3 * c.j0;
+        s.species = b->species ? b->species + c.j0 : nullptr;
+        s.jbase = c.j0;
+        return s;
+    }
+    m->in_off.reserve((ne + 1) * sizeof(long long));
+    m->in_R.reserve(std::max<long long>(nj, 1) * 3 * sizeof(double));
+    CU(cudaMemcpyAsync(m->in_off.p, b->offsets + c.e0, (ne + 1) * sizeof(long long), cudaMemcpyHostToDevice, m->stream));
+    if (nj > 0) CU(cudaMemcpyAsync(m->in_R.p, b->R + 3 * c.j0, nj * 3 * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    s.off = m->in_off.as<long long>();
+    s.R = m->in_R.as<double>();
+    s.species = nullptr;
+    if (b->species) {
+        m->in_sp.reserve(std::max<long long>(nj, 1) * sizeof(int));
+        if (nj > 0) CU(cudaMemcpyAsync(m->in_sp.p, b->species + c.j0, nj * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+        s.species = m->in_sp.as<int>();
+    }
+    s.jbase = c.j0;
+    return s;
+}
+
+static BatchDev batch_dev(const Staged& s, const Chunk& c)
+{
+    BatchDev B;
+    B.nenv = c.e1 - c.e0; B.off = s.off; B.R = s.R; B.species = s.species; B.jbase = s.jbase;
+    return B;
+}
+
+// ----------------------------------------------------------------------------------------------
+// kernel launch helpers
+// ----------------------------------------------------------------------------------------------
+template <int NMAX>
+static void launch_pool_t(aceb200_model* m, const PoolParams& p, dim3 grid, size_t smem)
+{
+    auto kfn = k_pool<NMAX>;
+    CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ACE_LAUNCH(kfn, grid, dim3(kPoolThreads), smem, m->stream, p);
+}
+
+static void launch_pool(aceb200_model* m, const BatchDev& B, long long ldA, int* envidx)
+{
+    HostTables& T = m->T;
+    PoolParams p;
+    p.rp = m->rp; p.ap = m->ap; p.C = m->C; p.B = B;
+    p.Ac = m->ws_Ac.as<c2>(); p.ldA = ldA; p.envidx = envidx; p.errflag = m->ws_err.as<int>();
+    p.colpass_size = std::min(T.ncols, kPoolThreads);
+    p.TE = std::max(1, kPoolThreads / p.colpass_size);
+    int nP = (T.Lused + 1) * (T.Lused + 2) / 2;
+    p.SK = (m->rp.N + 2 * nP) | 1;
+    size_t smem = (size_t)kPoolThreads * p.SK * sizeof(double) + kPoolThreads * sizeof(int);
+    dim3 grid((unsigned)((B.nenv + p.TE - 1) / p.TE), (unsigned)((T.ncols + p.colpass_size - 1) / p.colpass_size));
+    switch (m->NMAX) {
+    case 4: launch_pool_t<4>(m, p, grid, smem); break;
+    case 8: launch_pool_t<8>(m, p, grid, smem); break;
+    case 12: launch_pool_t<12>(m, p, grid, smem); break;
+    case 16: launch_pool_t<16>(m, p, grid, smem); break;
+    case 20: launch_pool_t<20>(m, p, grid, smem); break;
+    case 24: launch_pool_t<24>(m, p, grid, smem); break;
+    default: launch_pool_t<32>(m, p, grid, smem); break;
+    }
+    CU(cudaGetLastError());
+    m->launches++;
+}
+
+template <int PB, bool CW>
+static void launch_adjoint_t(aceb200_model* m, const AdjointParams& p, int grid, size_t smem)
+{
+    auto kfn = k_adjoint<PB, CW>;
+    CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ACE_LAUNCH(kfn, dim3(grid), dim3(32), smem, m->stream, p);
+}
+
+static void launch_adjoint(aceb200_model* m, long long nenv, long long ldA, bool want_D)
+{
+    HostTables& T = m->T;
+    AdjointParams p;
+    memset(&p, 0, sizeof(p));
+    p.nS = T.nS; p.nA = T.nA; p.maxord = T.maxord; p.P = T.P; p.Ppad = m->Ppad; p.has_const = T.has_const; p.want_D = want_D ? 1 : 0;
+    p.slot_pos = m->d_slot_pos; p.slot_neg = m->d_slot_neg; p.code = m->d_code;
+    p.w1 = m->d_w1.as<double>(); p.w0 = m->d_w0.as<double>();
+    for (int nu = 2; nu <= T.maxord; ++nu) p.tree[nu] = m->tree[nu];
+    p.Ac = m->ws_Ac.as<c2>(); p.ldA = ldA; p.Dt = m->ws_Dt.as<c2>(); p.E = m->ws_E.as<double>(); p.nenv = nenv;
+    size_t smem = (size_t)T.nS * 32 * sizeof(c2);
+    if (smem > (size_t)m->smem_optin)
+        throw ModelError(ACEB200_EUNSUPPORTED, "one-particle basis too large for the shared-memory tile of k_adjoint");
+    long long ntiles = (nenv + 31) / 32;
+    int per_sm = std::max<int>(1, std::min<int>(32, (int)((size_t)m->smem_optin / (smem + 1024))));
+    int grid = (int)std::min<long long>(ntiles, (long long)m->sm_count * per_sm);
+    const bool cw = m->cw;
+#define ACE_ADJ(PBV) { if (cw) launch_adjoint_t<PBV, true>(m, p, grid, smem); else launch_adjoint_t<PBV, false>(m, p, grid, smem); }
+    switch (m->PB) {
+    case 1: ACE_ADJ(1) break;
+    case 2: ACE_ADJ(2) break;
+    case 3: ACE_ADJ(3) break;
+    default: ACE_ADJ(4) break;
+    }
+#undef ACE_ADJ
+    CU(cudaGetLastError());
+    m->launches++;
+}
+
+template <int NMAX, int PB>
+static void launch_forces_t(aceb200_model* m, const ForceParams& p)
+{
+    auto kfn = k_forces<NMAX, PB>;
+    ACE_LAUNCH(kfn, dim3((unsigned)((p.nJ + kForceThreads - 1) / kForceThreads)), dim3(kForceThreads), 0, m->stream, p);
+}
+
+static void launch_forces(aceb200_model* m, const BatchDev& B, long long nJ, long long ldA, double* G)
+{
+    if (nJ == 0) return;
+    ForceParams p;
+    p.rp = m->rp; p.ap = m->ap; p.C = m->C; p.B = B; p.envidx = m->ws_envidx.as<int>();
+    p.Dt = m->ws_Dt.as<c2>(); p.ldA = ldA; p.P = m->T.P; p.nprop = m->T.nprop; p.ncomp = m->T.ncomp; p.G = G; p.nJ = nJ;
+    const int pb = m->PB == 1 ? 1 : (m->PB == 3 ? 3 : 2);
+#define ACE_F(NM) { if (pb == 1) launch_forces_t<NM, 1>(m, p); else if (pb == 3) launch_forces_t<NM, 3>(m, p); else launch_forces_t<NM, 2>(m, p); }
+    switch (m->NMAX) {
+    case 4: ACE_F(4) break;
+    case 8: ACE_F(8) break;
+    case 12: ACE_F(12) break;
+    case 16: ACE_F(16) break;
+    case 20: ACE_F(20) break;
+    case 24: ACE_F(24) break;
+    default: ACE_F(32) break;
+    }
+#undef ACE_F
+    CU(cudaGetLastError());
+    m->launches++;
+}
+
+template <int NMAX>
+static void launch_dA_t(aceb200_model* m, const dAParams& p)
+{
+    auto kfn = k_dA<NMAX>;
+    ACE_LAUNCH(kfn, dim3((unsigned)((p.nJ + 127) / 128)), dim3(128), 0, m->stream, p);
+}
+
+static void launch_dA(aceb200_model* m, const BatchDev& B, long long nJ, c2* dA)
+{
+    if (nJ == 0) return;
+    dAParams p;
+    p.rp = m->rp; p.ap = m->ap; p.C = m->C; p.B = B; p.slot_pos = m->d_slot_pos; p.slot_neg = m->d_slot_neg;
+    p.nA = m->T.nA; p.dA = dA; p.nJ = nJ;
+    switch (m->NMAX) {
+    case 4: launch_dA_t<4>(m, p); break;
+    case 8: launch_dA_t<8>(m, p); break;
+    case 12: launch_dA_t<12>(m, p); break;
+    case 16: launch_dA_t<16>(m, p); break;
+    case 20: launch_dA_t<20>(m, p); break;
+    case 24: launch_dA_t<24>(m, p); break;
+    default: launch_dA_t<32>(m, p); break;
+    }
+    CU(cudaGetLastError());
+    m->launches++;
+}
+
+static unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+static void check_errflag(aceb200_model* m)
+{
+    int flag = 0;
+    CU(cudaMemcpyAsync(&flag, m->ws_err.p, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    if (flag == 5) throw ModelError(ACEB200_EEMPTY, "Product1pBasis can only be evaluated with non-empty configurations");
+    if (flag == 6) throw ModelError(ACEB200_ECATEGORY, "species code not found in the category list");
+}
+
+// Copy `bytes` of a result to the user's buffer (host or device space).
+static void deliver(aceb200_model* m, const aceb200_batch* b, void* user, const void* dev, size_t bytes)
+{
+    if (!user || bytes == 0 || user == dev) return;
+    CU(cudaMemcpyAsync(user, dev, bytes, b->space == ACEB200_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, m->stream));
+}
+
+// ----------------------------------------------------------------------------------------------
+// the evaluation driver
+// ----------------------------------------------------------------------------------------------
+enum Want { W_A = 1, W_AA = 2, W_B = 4, W_dA = 8, W_dAA = 16, W_dB = 32, W_E = 64, W_G = 128 };
+
+struct Outputs {
+    double *A = nullptr, *AA = nullptr, *B = nullptr, *dA = nullptr, *dAA = nullptr, *dB = nullptr, *E = nullptr, *G = nullptr;
+};
+
+static void run(aceb200_model* m, const aceb200_batch* b, int want, const Outputs& o)
+{
+    validate_batch(b);
+    HostTables& T = m->T;
+    if ((want & (W_E | W_G)) && !T.symreal)
+        throw ModelError(ACEB200_EUNSUPPORTED, "energy / forces need a real symmetric basis (SymmetricBasis.real === real)");
+    if (b->nenv == 0) return;
+    CU(cudaSetDevice(m->device));
+    std::lock_guard<std::mutex> lock(m->mu);
+    const int P = T.P, nA = T.nA, nAA = T.nAA, nB = T.nB, ncomp = T.ncomp;
+    const int ca = T.pireal ? 1 : 2, cs = T.symreal ? 1 : 2;
+    const bool need_full_A = want & (W_A | W_AA | W_B | W_dA | W_dAA | W_dB);
+    const bool need_AA = want & (W_AA | W_B | W_dAA | W_dB);
+    const bool need_dA = want & (W_dA | W_dAA | W_dB);
+    const bool need_dAA = want & (W_dAA | W_dB);
+
+    // workspace bytes per environment (J-dependent parts use the batch average, bounded below)
+    std::vector<long long> ends = boundary_offsets(m, b, b->nenv);   // total neighbour count
+    const long long nJ_tot = ends[1] - ends[0];
+    const double Jav = std::max(1.0, (double)nJ_tot / (double)b->nenv);
+    size_t per_env = (size_t)T.nS * 16 + 64;
+    if (want & W_G) per_env += (size_t)T.nS * P * 16 + (size_t)(Jav * (4 + 24.0 * P));
+    if (want & (W_E | W_G)) per_env += (size_t)P * 8;
+    if (need_full_A) per_env += (size_t)nA * 16;
+    if (need_AA) per_env += (size_t)nAA * 8 * ca;
+    if (want & W_B) per_env += (size_t)nB * ncomp * 8 * cs;
+    if (need_dA) per_env += (size_t)(Jav * nA * 48.0);
+    if (need_dAA) per_env += (size_t)(Jav * nAA * 24.0 * ca);
+    if (want & W_dB) per_env += (size_t)(Jav * nB * 24.0 * ncomp * cs);
+    if (b->space == ACEB200_HOST) per_env += (size_t)(Jav * 28.0) + 8;
+    const long long step = chunk_envs(b->nenv, per_env, (size_t)3 << 30);
+    std::vector<long long> bo = boundary_offsets(m, b, step);
+
+    m->ws_err.reserve(sizeof(int));
+    CU(cudaMemsetAsync(m->ws_err.p, 0, sizeof(int), m->stream));
+    double kernel_ms = 0.0;
+    const long long nchunks = (b->nenv + step - 1) / step;
+    for (long long ic = 0; ic < nchunks; ++ic) {
+        Chunk c;
+        c.e0 = ic * step; c.e1 = std::min<long long>(b->nenv, c.e0 + step); c.j0 = bo[ic]; c.j1 = bo[ic + 1];
+        const long long ne = c.e1 - c.e0, nj = c.j1 - c.j0;
+        const long long ldA = ((ne + 31) / 32) * 32;
+        Staged st = stage_chunk(m, b, c);
+        BatchDev B = batch_dev(st, c);
+        m->ws_Ac.reserve((size_t)T.nS * ldA * sizeof(c2));
+        if (want & W_G) {
+            m->ws_Dt.reserve((size_t)T.nS * P * ldA * sizeof(c2));
+            m->ws_envidx.reserve(std::max<long long>(nj, 1) * sizeof(int));
+        }
+        CU(cudaEventRecord(m->ev0, m->stream));
+        launch_pool(m, B, ldA, (want & W_G) ? m->ws_envidx.as<int>() : nullptr);
+
+        if (want & (W_E | W_G)) {
+            m->ws_E.reserve((size_t)ne * P * sizeof(double));
+            double* Gdev = nullptr;
+            launch_adjoint(m, ne, ldA, (want & W_G) != 0);
+            if (want & W_G) {
+                const size_t gper = (size_t)P * 3;
+                if (b->space == ACEB200_DEVICE) Gdev = o.G + (size_t)c.j0 * gper;
+                else { m->ws_G.reserve(std::max<long long>(nj, 1) * gper * sizeof(double)); Gdev = m->ws_G.as<double>(); }
+                launch_forces(m, B, nj, ldA, Gdev);
+            }
+            CU(cudaEventRecord(m->ev1, m->stream));
+            if (o.E) deliver(m, b, o.E + (size_t)c.e0 * P, m->ws_E.p, (size_t)ne * P * sizeof(double));
+            if ((want & W_G) && b->space == ACEB200_HOST)
+                deliver(m, b, o.G + (size_t)c.j0 * P * 3, Gdev, (size_t)nj * P * 3 * sizeof(double));
+        } else {
+            // basis values / Jacobians
+            c2* dA_dev = nullptr; double* AA_dev = nullptr; double* dAA_dev = nullptr;
+            m->ws_A.reserve((size_t)ne * nA * sizeof(c2));
+            { auto kfn = k_expand_A;
+              ACE_LAUNCH(kfn, dim3(blocks_for(ne * nA, 256)), dim3(256), 0, m->stream, ne, nA, m->d_code, m->ws_Ac.as<c2>(), ldA, m->ws_A.as<c2>());
+              CU(cudaGetLastError()); m->launches++; }
+            if (need_AA) {
+                m->ws_AA.reserve((size_t)ne * nAA * 8 * ca);
+                AA_dev = m->ws_AA.as<double>();
+                auto kfn = k_AA;
+                ACE_LAUNCH(kfn, dim3(blocks_for(ne * nAA, 256)), dim3(256), 0, m->stream, ne, nA, nAA, std::max(1, T.maxord), m->d_orders, m->d_spec,
+                           (const c2*)m->ws_A.as<c2>(), T.pireal, AA_dev);
+                CU(cudaGetLastError()); m->launches++;
+            }
+            double* B_dev = nullptr;
+            if (want & W_B) {
+                m->ws_out.reserve((size_t)ne * nB * ncomp * 8 * cs);
+                B_dev = m->ws_out.as<double>();
+                auto kfn = k_B;
+                ACE_LAUNCH(kfn, dim3(blocks_for(ne * nB * ncomp, 256)), dim3(256), 0, m->stream, ne, nB, nAA, ncomp, m->d_csr_ptr, m->d_csr_col, m->d_csr_val,
+                           (const double*)AA_dev, T.pireal, T.symreal, B_dev);
+                CU(cudaGetLastError()); m->launches++;
+            }
+            if (need_dA) {
+                m->ws_dA.reserve(std::max<long long>(nj, 1) * nA * 3 * sizeof(c2));
+                dA_dev = m->ws_dA.as<c2>();
+                launch_dA(m, B, nj, dA_dev);
+            }
+            if (need_dAA) {
+                m->ws_dAA.reserve(std::max<long long>(nj, 1) * nAA * 24 * ca);
+                dAA_dev = m->ws_dAA.as<double>();
+                auto kfn = k_dAA;
+                ACE_LAUNCH(kfn, dim3(blocks_for(ne * nAA, 128)), dim3(128), 0, m->stream, ne, st.off, nA, nAA, std::max(1, T.maxord), m->d_orders, m->d_spec,
+                           (const c2*)m->ws_A.as<c2>(), (const c2*)dA_dev, T.pireal, dAA_dev);
+                CU(cudaGetLastError()); m->launches++;
+            }
+            double* dB_dev = nullptr;
+            if ((want & W_dB) && nj > 0) {
+                m->ws_G.reserve((size_t)nj * nB * 24 * ncomp * cs);
+                dB_dev = m->ws_G.as<double>();
+                auto kfn = k_dB;
+                ACE_LAUNCH(kfn, dim3(blocks_for(nj * nB * 3, 128)), dim3(128), 0, m->stream, nj, nB, nAA, ncomp, m->d_csr_ptr, m->d_csr_col, m->d_csr_val,
+                           (const double*)dAA_dev, T.pireal, T.symreal, dB_dev);
+                CU(cudaGetLastError()); m->launches++;
+            }
+            CU(cudaEventRecord(m->ev1, m->stream));
+            if (o.A) deliver(m, b, o.A + (size_t)c.e0 * nA * 2, m->ws_A.p, (size_t)ne * nA * sizeof(c2));
+            if (o.AA) deliver(m, b, o.AA + (size_t)c.e0 * nAA * ca, AA_dev, (size_t)ne * nAA * 8 * ca);
+            if (o.B) deliver(m, b, o.B + (size_t)c.e0 * nB * ncomp * cs, B_dev, (size_t)ne * nB * ncomp * 8 * cs);
+            if (o.dA) deliver(m, b, o.dA + (size_t)c.j0 * nA * 6, dA_dev, (size_t)nj * nA * 3 * sizeof(c2));
+            if (o.dAA) deliver(m, b, o.dAA + (size_t)c.j0 * nAA * 3 * ca, dAA_dev, (size_t)nj * nAA * 24 * ca);
+            if (o.dB) deliver(m, b, o.dB + (size_t)c.j0 * nB * 3 * ncomp * cs, dB_dev, (size_t)nj * nB * 24 * ncomp * cs);
+        }
+        CU(cudaStreamSynchronize(m->stream));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+        kernel_ms += ms;
+    }
+    m->last_ms = kernel_ms;
+    check_errflag(m);
+}
+
+// ----------------------------------------------------------------------------------------------
+// extern "C"
+// ----------------------------------------------------------------------------------------------
+#define API_BEGIN try {
+#define API_END                                                                  \
+    } catch (const ModelError& e) { return fail(e.code, e.what()); }             \
+    catch (const std::bad_alloc&) { return fail(ACEB200_ENOMEM, "host out of memory"); } \
+    catch (const std::exception& e) { return fail(ACEB200_EDESC, e.what()); }    \
+    return ACEB200_OK;
+
+extern "C" {
+
+int aceb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int aceb200_set_device(int device)
+{
+    API_BEGIN
+    int n = aceb200_device_count();
+    if (device < 0 || device >= n) throw ModelError(ACEB200_ECUDA, "no such CUDA device");
+    g_device = device;
+    API_END
+}
+
+int aceb200_last_error(char* buf, int n)
+{
+    if (!buf || n <= 0) return ACEB200_EDESC;
+    snprintf(buf, (size_t)n, "%s", g_err.c_str());
+    return ACEB200_OK;
+}
+
+int aceb200_model_create(const aceb200_desc* desc, aceb200_model** out)
+{
+    aceb200_model* m = nullptr;
+    try {
+        if (!desc || !out) throw ModelError(ACEB200_EDESC, "null argument");
+        *out = nullptr;
+        if (aceb200_device_count() <= 0) throw ModelError(ACEB200_ECUDA, "no CUDA device available: ace_b200 has no CPU path");
+        m = new aceb200_model();
+        m->device = g_device;
+        CU(cudaSetDevice(m->device));
+        build_tables(*desc, m->T);
+        fill_params(m, *desc);
+        m->NMAX = pick_nmax(desc->n_rad);
+        m->PB = pick_pb(m->T.P);
+        m->Ppad = ((m->T.P + m->PB - 1) / m->PB) * m->PB;
+        CU(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, m->device));
+        CU(cudaDeviceGetAttribute(&m->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
+        CU(cudaEventCreate(&m->ev0));
+        CU(cudaEventCreate(&m->ev1));
+        upload_tables(m);
+        upload_weights(m, desc->c);
+        *out = m;
+    } catch (const ModelError& e) { delete m; return fail(e.code, e.what()); }
+    catch (const std::bad_alloc&) { delete m; return fail(ACEB200_ENOMEM, "host out of memory"); }
+    catch (const std::exception& e) { delete m; return fail(ACEB200_EDESC, e.what()); }
+    return ACEB200_OK;
+}
+
+int aceb200_model_destroy(aceb200_model* m)
+{
+    if (!m) return ACEB200_OK;
+    cudaSetDevice(m->device);
+    for (DevBuf& b : m->pool) b.release();
+    DevBuf* bufs[] = {&m->d_w0, &m->d_w1, &m->ws_Ac, &m->ws_Dt, &m->ws_envidx, &m->ws_E, &m->ws_G, &m->ws_A, &m->ws_AA,
+                      &m->ws_dA, &m->ws_dAA, &m->ws_out, &m->ws_err, &m->in_off, &m->in_R, &m->in_sp};
+    for (DevBuf* b : bufs) b->release();
+    for (int nu = 0; nu <= kMaxOrdDev; ++nu) m->d_lw[nu].release();
+    if (m->ev0) cudaEventDestroy(m->ev0);
+    if (m->ev1) cudaEventDestroy(m->ev1);
+    delete m;
+    return ACEB200_OK;
+}
+
+int aceb200_set_params(aceb200_model* m, const double* c, int64_t n)
+{
+    API_BEGIN
+    if (!m || !c) throw ModelError(ACEB200_EDESC, "null argument");
+    if (n != (int64_t)m->T.nB * m->T.nprop) throw ModelError(ACEB200_EDESC, "set_params: expected nB*nprop coefficients");
+    CU(cudaSetDevice(m->device));
+    std::lock_guard<std::mutex> lock(m->mu);
+    upload_weights(m, c);
+    API_END
+}
+
+int aceb200_get_eff_coeffs(aceb200_model* m, double* ctilde)
+{
+    API_BEGIN
+    if (!m || !ctilde) throw ModelError(ACEB200_EDESC, "null argument");
+    memcpy(ctilde, m->ctilde.data(), m->ctilde.size() * sizeof(cplx));
+    API_END
+}
+
+int aceb200_set_stream(aceb200_model* m, void* cuda_stream)
+{
+    if (!m) return fail(ACEB200_EDESC, "null model");
+    m->stream = (cudaStream_t)cuda_stream;
+    return ACEB200_OK;
+}
+
+int64_t aceb200_launch_count(const aceb200_model* m) { return m ? m->launches : 0; }
+
+int aceb200_model_sizes(const aceb200_model* m, aceb200_sizes* out)
+{
+    if (!m || !out) return fail(ACEB200_EDESC, "null argument");
+    out->nA = m->T.nA; out->nAA = m->T.nAA; out->nB = m->T.nB; out->ncomp = m->T.ncomp; out->nprop = m->T.nprop;
+    out->maxord = m->T.maxord; out->pireal = m->T.pireal; out->symreal = m->T.symreal;
+    return ACEB200_OK;
+}
+
+int aceb200_last_kernel_ms(const aceb200_model* m, double* ms)
+{
+    if (!m || !ms) return fail(ACEB200_EDESC, "null argument");
+    *ms = m->last_ms;
+    return ACEB200_OK;
+}
+
+#define NEED(m, b) if (!(m) || !(b)) throw ModelError(ACEB200_EDESC, "null argument")
+
+int aceb200_eval_A(aceb200_model* m, const aceb200_batch* b, double* A)
+{ API_BEGIN NEED(m, b); Outputs o; o.A = A; run(m, b, W_A, o); API_END }
+
+int aceb200_eval_AA(aceb200_model* m, const aceb200_batch* b, double* AA)
+{ API_BEGIN NEED(m, b); Outputs o; o.AA = AA; run(m, b, W_AA, o); API_END }
+
+int aceb200_eval_B(aceb200_model* m, const aceb200_batch* b, double* B)
+{ API_BEGIN NEED(m, b); Outputs o; o.B = B; run(m, b, W_B, o); API_END }
+
+int aceb200_eval_dA(aceb200_model* m, const aceb200_batch* b, double* A, double* dA)
+{ API_BEGIN NEED(m, b); Outputs o; o.A = A; o.dA = dA; run(m, b, W_dA | (A ? W_A : 0), o); API_END }
+
+int aceb200_eval_dAA(aceb200_model* m, const aceb200_batch* b, double* AA, double* dAA)
+{ API_BEGIN NEED(m, b); Outputs o; o.AA = AA; o.dAA = dAA; run(m, b, W_dAA | (AA ? W_AA : 0), o); API_END }
+
+int aceb200_eval_dB(aceb200_model* m, const aceb200_batch* b, double* B, double* dB)
+{ API_BEGIN NEED(m, b); Outputs o; o.B = B; o.dB = dB; run(m, b, W_dB | (B ? W_B : 0), o); API_END }
+
+int aceb200_energy(aceb200_model* m, const aceb200_batch* b, double* E)
+{ API_BEGIN NEED(m, b); Outputs o; o.E = E; run(m, b, W_E, o); API_END }
+
+int aceb200_energy_forces(aceb200_model* m, const aceb200_batch* b, double* E, double* G)
+{ API_BEGIN NEED(m, b); if (!G) throw ModelError(ACEB200_EDESC, "null G"); Outputs o; o.E = E; o.G = G; run(m, b, W_E | W_G, o); API_END }
+
+}  // extern "C"
