@@ -147,6 +147,11 @@ class Handle:
         L.check(self.lib.aceb200_last_kernel_ms(self.ptr, C.byref(v)))
         return v.value
 
+    def last_stage_ms(self):
+        v = (C.c_double * 3)()
+        L.check(self.lib.aceb200_last_stage_ms(self.ptr, v))
+        return {"pool": v[0], "adjoint": v[1], "forces": v[2]}
+
     def set_params(self, c: np.ndarray):
         c = np.ascontiguousarray(c, dtype=np.float64)
         L.check(self.lib.aceb200_set_params(self.ptr, c.ctypes.data_as(L.c_double_p), c.size))
@@ -208,6 +213,12 @@ class Handle:
             G = b.empty((b.nJ, self.s.nprop, 3, self.s.ncomp), not self.s.symreal)
         self._call("aceb200_energy_forces", b, E, G)
         return E, G
+
+
+def measure_fp64_tflops() -> float:
+    v = C.c_double()
+    L.check(L.load().aceb200_measure_fp64(C.byref(v)))
+    return v.value
 
 
 # ------------------------------------------------------------------------------------------------

@@ -5,6 +5,7 @@
 // workspace, move host batches to the device and results back, launch.  There is no CPU evaluation
 // path in this file: every entry point needs a CUDA device.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -88,8 +89,9 @@ struct aceb200_model {
     DevBuf ws_Ac, ws_Dt, ws_envidx, ws_E, ws_G, ws_A, ws_AA, ws_dA, ws_dAA, ws_out, ws_err;
     DevBuf in_off, in_R, in_sp;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
     double last_ms = 0.0;
+    double stage_ms[3] = {0.0, 0.0, 0.0};   // pool, adjoint, forces of the last energy(_forces) call
     long long launches = 0;
     int sm_count = 148;
     int smem_optin = 227 * 1024;
@@ -481,12 +483,17 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
     if (need_dAA) per_env += (size_t)(Jav * nAA * 24.0 * ca);
     if (want & W_dB) per_env += (size_t)(Jav * nB * 24.0 * ncomp * cs);
     if (b->space == ACEB200_HOST) per_env += (size_t)(Jav * 28.0) + 8;
-    const long long step = chunk_envs(b->nenv, per_env, (size_t)3 << 30);
+    long long step = chunk_envs(b->nenv, per_env, (size_t)3 << 30);
+    if (const char* ov = getenv("ACEB200_CHUNK_ENVS")) {   // test hook: force the multi-chunk path on small batches
+        long long v = atoll(ov);
+        if (v >= 32) step = std::min<long long>(step, (v / 32) * 32);
+    }
     std::vector<long long> bo = boundary_offsets(m, b, step);
 
     m->ws_err.reserve(sizeof(int));
     CU(cudaMemsetAsync(m->ws_err.p, 0, sizeof(int), m->stream));
     double kernel_ms = 0.0;
+    double stage_ms[3] = {0.0, 0.0, 0.0};
     const long long nchunks = (b->nenv + step - 1) / step;
     for (long long ic = 0; ic < nchunks; ++ic) {
         Chunk c;
@@ -506,7 +513,9 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
         if (want & (W_E | W_G)) {
             m->ws_E.reserve((size_t)ne * P * sizeof(double));
             double* Gdev = nullptr;
+            CU(cudaEventRecord(m->evA, m->stream));
             launch_adjoint(m, ne, ldA, (want & W_G) != 0);
+            CU(cudaEventRecord(m->evB, m->stream));
             if (want & W_G) {
                 const size_t gper = (size_t)P * 3;
                 if (b->space == ACEB200_DEVICE) Gdev = o.G + (size_t)c.j0 * gper;
@@ -575,9 +584,31 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
         kernel_ms += ms;
+        if (want & (W_E | W_G)) {
+            float a = 0.f, bb = 0.f, cc = 0.f;
+            CU(cudaEventElapsedTime(&a, m->ev0, m->evA));
+            CU(cudaEventElapsedTime(&bb, m->evA, m->evB));
+            CU(cudaEventElapsedTime(&cc, m->evB, m->ev1));
+            stage_ms[0] += a; stage_ms[1] += bb; stage_ms[2] += cc;
+        }
     }
     m->last_ms = kernel_ms;
+    for (int i = 0; i < 3; ++i) m->stage_ms[i] = stage_ms[i];
     check_errflag(m);
+}
+
+// FP64 FMA throughput probe: 8 independent dependent-FMA chains per thread.  The roofline
+// denominator of this path is the FP64 pipe, which MEASURED_PEAKS.json does not hold.
+__global__ void k_fp64_peak(int iters, double* sink)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double x = 1.0000001, y = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = a0 * x + y; a1 = a1 * x + y; a2 = a2 * x + y; a3 = a3 * x + y;
+        a4 = a4 * x + y; a5 = a5 * x + y; a6 = a6 * x + y; a7 = a7 * x + y;
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) sink[threadIdx.x] = s;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -634,6 +665,8 @@ int aceb200_model_create(const aceb200_desc* desc, aceb200_model** out)
         CU(cudaDeviceGetAttribute(&m->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
         CU(cudaEventCreate(&m->ev0));
         CU(cudaEventCreate(&m->ev1));
+        CU(cudaEventCreate(&m->evA));
+        CU(cudaEventCreate(&m->evB));
         upload_tables(m);
         upload_weights(m, desc->c);
         *out = m;
@@ -654,6 +687,8 @@ int aceb200_model_destroy(aceb200_model* m)
     for (int nu = 0; nu <= kMaxOrdDev; ++nu) m->d_lw[nu].release();
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
+    if (m->evA) cudaEventDestroy(m->evA);
+    if (m->evB) cudaEventDestroy(m->evB);
     delete m;
     return ACEB200_OK;
 }
@@ -699,6 +734,43 @@ int aceb200_last_kernel_ms(const aceb200_model* m, double* ms)
     if (!m || !ms) return fail(ACEB200_EDESC, "null argument");
     *ms = m->last_ms;
     return ACEB200_OK;
+}
+
+int aceb200_last_stage_ms(const aceb200_model* m, double* ms3)
+{
+    if (!m || !ms3) return fail(ACEB200_EDESC, "null argument");
+    for (int i = 0; i < 3; ++i) ms3[i] = m->stage_ms[i];
+    return ACEB200_OK;
+}
+
+int aceb200_measure_fp64(double* tflops)
+{
+    API_BEGIN
+    if (!tflops) throw ModelError(ACEB200_EDESC, "null argument");
+    if (aceb200_device_count() <= 0) throw ModelError(ACEB200_ECUDA, "no CUDA device");
+    CU(cudaSetDevice(g_device));
+    int sms = 148;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g_device));
+    double* sink = nullptr;
+    CU(cudaMalloc((void**)&sink, 1024 * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    const int iters = 1 << 15, threads = 256, blocks = sms * 8;
+    auto kfn = k_fp64_peak;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(cudaEventRecord(e0, nullptr));
+        ACE_LAUNCH(kfn, dim3(blocks), dim3(threads), 0, (cudaStream_t) nullptr, iters, sink);
+        CU(cudaEventRecord(e1, nullptr));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        double fl = (double)blocks * threads * (double)iters * 8.0 * 2.0;
+        if (ms > 0.f) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    *tflops = best;
+    API_END
 }
 
 #define NEED(m, b) if (!(m) || !(b)) throw ModelError(ACEB200_EDESC, "null argument")

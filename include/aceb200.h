@@ -183,6 +183,14 @@ int aceb200_model_sizes(const aceb200_model *m, aceb200_sizes *out);
  * recorded on the handle's stream around the kernel launches only (no copies). */
 int aceb200_last_kernel_ms(const aceb200_model *m, double *ms);
 
+/* per-kernel split of the last aceb200_energy / aceb200_energy_forces call: ms3 = {pool, adjoint, forces} */
+int aceb200_last_stage_ms(const aceb200_model *m, double *ms3);
+
+/* Measured FP64 FMA throughput of the current device in TFLOP/s (a register-resident FMA probe).
+ * The FP64 pipe is the roofline that bounds this path and the driver's
+ * MEASURED_PEAKS.json does not record it. */
+int aceb200_measure_fp64(double *tflops);
+
 #ifdef __cplusplus
 }
 #endif

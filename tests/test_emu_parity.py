@@ -1,0 +1,62 @@
+"""Kernel index logic on the CPU: the CUDA sources compiled against tests/emu/cuda_emu.h (one std::thread
+per CUDA thread) must reproduce the oracle.  This is NOT a product path: the emulated library lives in
+tests/emu/, is built by tests/emu/build_emu.sh and is loaded only here."""
+import ctypes
+import os
+import subprocess
+
+import pytest
+
+from ace_jl_b200 import _lib
+from conftest import ROOT, make_basis
+from parity_common import compare_all
+
+EMU_SO = os.path.join(ROOT, "tests", "emu", "libaceb200_emu.so")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    srcs = [os.path.join(ROOT, "ace_jl_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "ace_jl_b200", "csrc"))
+            if f.endswith((".cu", ".cuh", ".h"))] + [os.path.join(ROOT, "tests", "emu", "cuda_emu.h")]
+    if not os.path.exists(EMU_SO) or os.path.getmtime(EMU_SO) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.check_call([os.path.join(ROOT, "tests", "emu", "build_emu.sh")])
+    lib = ctypes.CDLL(EMU_SO)
+    for name, res, args in _lib.SYMBOLS:
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    saved = _lib._lib
+    _lib._lib = lib
+    yield lib
+    _lib._lib = saved
+
+
+@pytest.mark.parametrize("kind,nprop,Js", [
+    ("inv_simple_3_6", 1, [3, 10, 1, 35, 7, 2, 140]),     # ragged, one tile boundary crossing (J > 128)
+    ("inv_sparse_4_8", 4, [5, 12, 33]),                   # order 4, multi-property
+    ("euclvec_3_5", 1, [3, 10, 1, 35]),                   # complex effective coefficients, 3 components
+    ("euclmat_2_5", 2, [3, 10]),                          # 9 components x 2 properties
+    ("species_3_5", 2, [5, 12, 33, 130]),                 # categorical component
+    ("inv_morse_2_6", 1, [6, 20]),
+    ("inv_agnesi_2_6", 1, [6, 20]),
+])
+def test_emulated_kernels_match_oracle(emu, kind, nprop, Js):
+    compare_all(make_basis(kind), nprop, Js)
+
+
+def test_emulated_errors(emu):
+    import numpy as np
+    import ace_jl_b200 as ace
+    basis = make_basis("inv_simple_3_6")
+    model = ace.LinearACEModel(basis, np.zeros(len(basis)))
+    h = model.evaluator.handle
+    R = np.array([[0.5, 0.5, 0.5], [1.0, 0.2, 0.1]])
+    with pytest.raises(_lib.AceB200Error) as ei:            # an empty environment (product_1pbasis.jl:124)
+        h.energy(ace.B200Batch(R, [0, 2, 2]))
+    assert ei.value.code == -5
+    sp_basis = make_basis("species_3_5")
+    hs = ace.LinearACEModel(sp_basis, np.zeros(len(sp_basis))).evaluator.handle
+    with pytest.raises(_lib.AceB200Error) as ei:            # unknown category (discrete1pbasis.jl:39)
+        hs.energy(ace.B200Batch(R, [0, 2], np.array([1, 9], dtype=np.int32)))
+    assert ei.value.code == -6
+    with pytest.raises(_lib.AceB200Error):
+        model.evaluate([])
