@@ -232,7 +232,7 @@ def _trivial_symm(basis) -> SymmetricBasis:
         pib = PIBasis(basis, spec, isreal=False)
     else:
         pib = basis
-    A2B = SparseCSC(0, len(pib), np.ones(len(pib) + 1, dtype=np.int32), [], np.zeros((0, 1)))
+    A2B = SparseCSC(0, len(pib), np.ones(len(pib) + 1, dtype=np.int32), [], np.zeros((0, 1)), 1)
     from .properties import Invariant
     from .symmetrygroups import NoSym
     return SymmetricBasis.from_parts(Invariant(), pib, A2B, NoSym(), False)

@@ -58,11 +58,13 @@ struct ColumnsDev {
     const int* colmap;      // [nQ][nPused]
 };
 
-struct TreeDev {
-    const int* ptr0;        // [nA+1]
-    const int* nidx[kMaxOrdDev]; const int* nptr[kMaxOrdDev];
-    const int* lidx;        // leaves: A-code
-    const double* lw;       // leaves: weights [leaf][Ppad] (real) or [leaf][Ppad][2] (complex)
+// Adjoint list of one correlation order: records of `stride` bytes, sorted by target.
+//   record = 4 x uint16 A-codes of the other factors (unused ones 0), then the weights:
+//            Ppad doubles (real weights) or Ppad (re, im) pairs (complex weights)
+struct ListDev {
+    const int* ptr;               // [nA+1]
+    const unsigned char* rec;
+    int stride;
 };
 
 struct BatchDev {
@@ -83,7 +85,6 @@ struct PoolParams {
     BatchDev B;
     c2* Ac;                 // [nS][ldA]
     long long ldA;
-    int* envidx;            // [neighbours of the chunk] -> chunk-local environment index (may be null)
     int* errflag;           // set to ACEB200_EEMPTY / ACEB200_ECATEGORY on bad input
     int TE;                 // environments per CTA
     int SK;                 // staging row stride in doubles (odd)
@@ -134,11 +135,6 @@ __global__ void __launch_bounds__(kPoolThreads) k_pool(const PoolParams p)
                 if (q < 0 || q >= p.C.nQ) { atomicMax(p.errflag, 6); q = 0; }   // ECATEGORY
             }
             sq[tid] = q;
-            if (p.envidx && blockIdx.y == 0) {
-                int e = 0;
-                while (e + 1 < ne && p.B.off[e0 + e + 1] <= j) ++e;
-                p.envidx[j - p.B.off[0]] = (int)(e0 + e);
-            }
             const Spher sp = cart2spher(x, y, z);
             double Rn[NMAX];
             radial_e<NMAX>(p.rp, sp.r, Rn);
@@ -184,65 +180,69 @@ struct AdjointParams {
     const int* code;                             // [nA] A-code of each target
     const double* w1;                            // [nA][Ppad](x2): order-1 weights (0 if no such AA)
     const double* w0;                            // [Ppad](x2): the constant
-    TreeDev tree[kMaxOrdDev + 1];                // index nu = 2..maxord
+    ListDev list[kMaxOrdDev + 1];                // index nu = 2..maxord
     const c2* Ac; long long ldA;                 // [nS][ldA]
     c2* Dt;                                      // [nS][P][ldA]
     double* E;                                   // [nenv][P] (real part)
     long long nenv;
 };
 
-// leaves: out[p] += w[leaf][p] * A[leaf idx]
-template <int PB, bool CW>
-__device__ __forceinline__ void leaves_eval(const TreeDev& T, int i0, int i1, const c2* As, int lane, int pb, int Ppad, c2 (&out)[PB])
+__device__ __forceinline__ c2 fetch_A(const c2* As, int lane, unsigned code)
 {
-    for (int i = i0; i < i1; ++i) {
-        const int code = __ldg(T.lidx + i);
-        const c2 a = decode_A(As[(code >> 2) * 32 + lane], code);
-        const double* w = T.lw + ((size_t)i * Ppad + pb) * (CW ? 2 : 1);
+    return decode_A(As[(code >> 2) * 32 + lane], (int)code);
+}
+
+// out[p] += sum over the leaves of target a:  w[leaf][p] * prod_{k < NU-1} A[code_k]
+// The loop body has no loop-carried dependence except the accumulators, the record addresses do not
+// depend on data, and control flow is warp-uniform: unrolling lets the table loads and the shared-memory
+// gathers of several leaves be in flight together.
+template <int NU, int PB, bool CW>
+__device__ __forceinline__ void list_eval(const ListDev& T, int a, const c2* As, int lane, int pb, c2 (&out)[PB])
+{
+    const int i0 = __ldg(T.ptr + a), i1 = __ldg(T.ptr + a + 1);
+    const unsigned char* r = T.rec + (size_t)i0 * T.stride;
+    const int stride = T.stride;
+#pragma unroll 4
+    for (int i = i0; i < i1; ++i, r += stride) {
+        c2 prod;
+        if (PB == 1 && !CW) {
+            // 16-byte record: one 128-bit uniform load brings the codes and the weight
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(r));
+            prod = fetch_A(As, lane, q.x & 0xffffu);
+            if (NU >= 3) prod = cmul(prod, fetch_A(As, lane, q.x >> 16));
+            if (NU >= 4) prod = cmul(prod, fetch_A(As, lane, q.y & 0xffffu));
+            if (NU >= 5) prod = cmul(prod, fetch_A(As, lane, q.y >> 16));
+            const double w = __hiloint2double((int)q.w, (int)q.z);
+            out[0].x += w * prod.x;
+            out[0].y += w * prod.y;
+        } else {
+            const uint2 q = __ldg(reinterpret_cast<const uint2*>(r));
+            prod = fetch_A(As, lane, q.x & 0xffffu);
+            if (NU >= 3) prod = cmul(prod, fetch_A(As, lane, q.x >> 16));
+            if (NU >= 4) prod = cmul(prod, fetch_A(As, lane, q.y & 0xffffu));
+            if (NU >= 5) prod = cmul(prod, fetch_A(As, lane, q.y >> 16));
+            const double* w = reinterpret_cast<const double*>(r + 8) + (size_t)pb * (CW ? 2 : 1);
 #pragma unroll
-        for (int p = 0; p < PB; ++p) {
-            if (CW) {
-                const double wr = __ldg(w + 2 * p), wi = __ldg(w + 2 * p + 1);
-                out[p].x += wr * a.x - wi * a.y;
-                out[p].y += wr * a.y + wi * a.x;
-            } else {
-                const double wr = __ldg(w + p);
-                out[p].x += wr * a.x;
-                out[p].y += wr * a.y;
+            for (int p = 0; p < PB; ++p) {
+                if (CW) {
+                    const double wr = __ldg(w + 2 * p), wi = __ldg(w + 2 * p + 1);
+                    out[p].x += wr * prod.x - wi * prod.y;
+                    out[p].y += wr * prod.y + wi * prod.x;
+                } else {
+                    const double wr = __ldg(w + p);
+                    out[p].x += wr * prod.x;
+                    out[p].y += wr * prod.y;
+                }
             }
         }
     }
 }
 
-// interior level LEVEL of a tree of depth DEPTH: out[p] += A[node] * (children sum)
-template <int DEPTH, int LEVEL, int PB, bool CW>
-struct TreeWalk {
-    static __device__ __forceinline__ void run(const TreeDev& T, int i0, int i1, const c2* As, int lane, int pb, int Ppad, c2 (&out)[PB])
-    {
-        if (LEVEL == DEPTH - 1) { leaves_eval<PB, CW>(T, i0, i1, As, lane, pb, Ppad, out); return; }
-        for (int i = i0; i < i1; ++i) {
-            const int code = __ldg(T.nidx[LEVEL] + i);
-            const c2 a = decode_A(As[(code >> 2) * 32 + lane], code);
-            c2 sub[PB];
-#pragma unroll
-            for (int p = 0; p < PB; ++p) sub[p] = c2{0.0, 0.0};
-            TreeWalk<DEPTH, (LEVEL + 1 < DEPTH ? LEVEL + 1 : LEVEL), PB, CW>::run(
-                T, __ldg(T.nptr[LEVEL] + i), __ldg(T.nptr[LEVEL] + i + 1), As, lane, pb, Ppad, sub);
-#pragma unroll
-            for (int p = 0; p < PB; ++p) {
-                out[p].x += a.x * sub[p].x - a.y * sub[p].y;
-                out[p].y += a.x * sub[p].y + a.y * sub[p].x;
-            }
-        }
-    }
-};
-
-// sum over orders nu = 2..maxord of dE/dA_a; also accumulates the energy  Re(A_a S_nu) / nu
+// sum over orders of dE/dA_a; also accumulates the energy  Re(A_a S_nu) / nu  (Euler: sum_a A_a dF_nu/dA_a = nu F_nu)
 template <int PB, bool CW>
 __device__ __forceinline__ void target_eval(const AdjointParams& p, int a, const c2* As, int lane, int pb, c2 (&S)[PB], double (&E)[PB])
 {
-    const int code = __ldg(p.code + a);
-    const c2 Aa = decode_A(As[(code >> 2) * 32 + lane], code);
+    const c2 Aa = fetch_A(As, lane, (unsigned)__ldg(p.code + a));
     // order 1: dE/dA_a = c~ ; energy Re(A_a c~)
     {
         const double* w = p.w1 + ((size_t)a * p.Ppad + pb) * (CW ? 2 : 1);
@@ -256,19 +256,15 @@ __device__ __forceinline__ void target_eval(const AdjointParams& p, int a, const
     }
 #define ACE_ORDER(NU)                                                                              \
     if (p.maxord >= NU) {                                                                          \
-        const TreeDev& T = p.tree[NU];                                                             \
-        const int i0 = __ldg(T.ptr0 + a), i1 = __ldg(T.ptr0 + a + 1);                              \
-        if (i1 > i0) {                                                                             \
-            c2 s[PB];                                                                              \
-            _Pragma("unroll") for (int q = 0; q < PB; ++q) s[q] = c2{0.0, 0.0};                    \
-            TreeWalk<NU - 1, 0, PB, CW>::run(T, i0, i1, As, lane, pb, p.Ppad, s);                  \
-            _Pragma("unroll") for (int q = 0; q < PB; ++q) {                                       \
-                S[q].x += s[q].x; S[q].y += s[q].y;                                                \
-                E[q] += (Aa.x * s[q].x - Aa.y * s[q].y) * (1.0 / NU);                              \
-            }                                                                                      \
+        c2 s[PB];                                                                                  \
+        _Pragma("unroll") for (int q = 0; q < PB; ++q) s[q] = c2{0.0, 0.0};                        \
+        list_eval<NU, PB, CW>(p.list[NU], a, As, lane, pb, s);                                     \
+        _Pragma("unroll") for (int q = 0; q < PB; ++q) {                                           \
+            S[q].x += s[q].x; S[q].y += s[q].y;                                                    \
+            E[q] += (Aa.x * s[q].x - Aa.y * s[q].y) * (1.0 / NU);                                  \
         }                                                                                          \
     }
-    ACE_ORDER(2) ACE_ORDER(3) ACE_ORDER(4) ACE_ORDER(5) ACE_ORDER(6)
+    ACE_ORDER(2) ACE_ORDER(3) ACE_ORDER(4) ACE_ORDER(5)
 #undef ACE_ORDER
 }
 
@@ -322,6 +318,105 @@ __global__ void __launch_bounds__(32) k_adjoint(const AdjointParams p)
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_adjoint_stream: the single-channel, real-weight fast path (energies + forces of an invariant model)
+// ------------------------------------------------------------------------------------------------
+// The adjoint lists of all targets and orders are flattened by the host into ONE stream of 16-byte
+// records, in exactly the order the kernel consumes them, grouped in blocks of 4 leaves of the same
+// (target, order):
+//     record = { u16 c0, u16 c1, u16 c2, u16 ctl, f64 w }        leaf value = w * A[c0] * A[c1] (* A[c2])
+// unused factors point at an extra slot that holds 1.  The ctl fields of a block's 4 records carry its
+// header: ctl0 = flags | order, ctl1 = A-code of the target, ctl2 = target index.
+// Because the stream is read strictly sequentially and identically by every lane, the warp fetches it
+// cooperatively -- 32 records (512 contiguous bytes) per coalesced load, two chunks ahead of use -- into a
+// small shared-memory ring, and reads records back as broadcasts.  Table latency is thereby hidden and
+// the leaf loop is branch-free; control (end of order segment / target / slot) is a warp-uniform branch
+// taken once per few dozen leaves.
+constexpr unsigned kSegEnd = 8, kTgtEnd = 16, kTgtNeg = 32, kTgtOdd = 64, kSlotEnd = 128;
+
+struct StreamParams {
+    int nS, has_const, want_D, nchunks;      // nchunks: stream length in chunks of 8 blocks = 32 records
+    const uint4* stream;
+    const double* w1;                        // [nA] order-1 weights
+    double w0;
+    const c2* Ac; long long ldA;
+    c2* Dt;                                  // [nS][ldA]
+    double* E;                               // [nenv]
+    long long nenv;
+};
+
+template <int NF>
+__global__ void __launch_bounds__(32) k_adjoint_stream(const StreamParams p)
+{
+    ACE_DYN_SMEM(c2, As);                                       // [nS + 1][32]; slot nS holds 1
+    uint4* ring = reinterpret_cast<uint4*>(As + (size_t)(p.nS + 1) * 32);   // [3][32]
+    const int lane = threadIdx.x;
+    const long long ntiles = (p.nenv + 31) / 32;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long e = tile * 32 + lane;
+        for (int s = 0; s < p.nS; ++s) As[s * 32 + lane] = p.Ac[(size_t)s * p.ldA + e];
+        As[p.nS * 32 + lane] = c2{1.0, 0.0};
+        ring[lane] = __ldg(p.stream + lane);
+        if (p.nchunks > 1) ring[32 + lane] = __ldg(p.stream + 32 + lane);
+        __syncwarp();
+        double E = p.has_const ? p.w0 : 0.0;
+        c2 D = c2{0.0, 0.0}, S = c2{0.0, 0.0}, acc0 = c2{0.0, 0.0}, acc1 = c2{0.0, 0.0};
+        int slot = 0;
+        for (int ch = 0; ch < p.nchunks; ++ch) {
+            const bool havepre = ch + 2 < p.nchunks;
+            uint4 pre = uint4{0u, 0u, 0u, 0u};
+            if (havepre) pre = __ldg(p.stream + (size_t)(ch + 2) * 32 + lane);
+            const uint4* rb = ring + (ch % 3) * 32;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                uint4 q[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) q[k] = rb[4 * b + k];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    c2 prod = cmul(fetch_A(As, lane, q[k].x & 0xffffu), fetch_A(As, lane, q[k].x >> 16));
+                    if (NF >= 3) prod = cmul(prod, fetch_A(As, lane, q[k].y & 0xffffu));
+                    const double w = __hiloint2double((int)q[k].w, (int)q[k].z);
+                    if (k & 1) { acc1.x += w * prod.x; acc1.y += w * prod.y; }
+                    else { acc0.x += w * prod.x; acc0.y += w * prod.y; }
+                }
+                const unsigned flags = q[0].y >> 16;
+                if (flags & 0xf8u) {
+                    const c2 Aa = fetch_A(As, lane, q[1].y >> 16);
+                    if (flags & kSegEnd) {
+                        const c2 sg = c2{acc0.x + acc1.x, acc0.y + acc1.y};
+                        acc0 = c2{0.0, 0.0}; acc1 = c2{0.0, 0.0};
+                        const unsigned nu = flags & 7u;
+                        const double inv = nu == 2 ? 0.5 : (nu == 3 ? (1.0 / 3.0) : 0.25);
+                        S.x += sg.x; S.y += sg.y;
+                        E += (Aa.x * sg.x - Aa.y * sg.y) * inv;    // Euler: sum_a A_a dF_nu/dA_a = nu F_nu
+                    }
+                    if (flags & kTgtEnd) {
+                        const double w = __ldg(p.w1 + (q[2].y >> 16));
+                        S.x += w;
+                        E += Aa.x * w;
+                        if (flags & kTgtNeg) {
+                            // Re(D- grad(phi_-m)) = Re((-1)^m conj(D-) grad(phi_m)): fold onto the m > 0 slot
+                            const double sgn = (flags & kTgtOdd) ? -1.0 : 1.0;
+                            D.x += sgn * S.x; D.y -= sgn * S.y;
+                        } else { D.x += S.x; D.y += S.y; }
+                        S = c2{0.0, 0.0};
+                    }
+                    if (flags & kSlotEnd) {
+                        if (p.want_D && e < p.nenv) p.Dt[(size_t)slot * p.ldA + e] = D;
+                        D = c2{0.0, 0.0};
+                        ++slot;
+                    }
+                }
+            }
+            if (havepre) ring[((ch + 2) % 3) * 32 + lane] = pre;
+            __syncwarp();
+        }
+        if (e < p.nenv) p.E[e] = E;
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_forces: one thread per neighbour
 // ------------------------------------------------------------------------------------------------
 struct ForceParams {
@@ -329,73 +424,88 @@ struct ForceParams {
     AlpParams ap;
     ColumnsDev C;
     BatchDev B;
-    const int* envidx;       // [neighbours of the chunk]
     const c2* Dt; long long ldA;
     int P, nprop, ncomp;
+    int TE;                  // environments per CTA
     double* G;               // [neighbour][nprop][3][ncomp], chunk-relative
-    long long nJ;            // neighbours in this chunk
 };
 
 constexpr int kForceThreads = 128;
 
+// A CTA owns TE consecutive environments: it stages their folded adjoints D~ in shared memory
+// ([slot][channel][local env]), then runs one thread per neighbour of those environments.
 template <int NMAX, int PB>
 __global__ void __launch_bounds__(kForceThreads) k_forces(const ForceParams p)
 {
-    const long long jl = (long long)blockIdx.x * kForceThreads + threadIdx.x;   // chunk-local neighbour
-    if (jl >= p.nJ) return;
-    const long long jabs = p.B.off[0] + jl;
-    const double* r = p.B.R + 3 * (jabs - p.B.jbase);
-    const double x = r[0], y = r[1], z = r[2];
-    int q = 0;
-    if (p.B.species) { q = p.B.species[jabs - p.B.jbase] - 1; if (q < 0 || q >= p.C.nQ) q = 0; }
-    const long long e = p.envidx[jl];
-    const Spher sp = cart2spher(x, y, z);
-    double Rn[NMAX], dRn[NMAX];
-    radial_ed<NMAX>(p.rp, sp.r, Rn, dRn);
-    const int* cmap = p.C.colmap + (size_t)q * p.C.nPused;
+    ACE_DYN_SMEM(c2, Ds);   // [nS][PB][TE]
+    const int tid = threadIdx.x;
+    const int TE = p.TE;
+    const long long e0 = (long long)blockIdx.x * TE;
+    if (e0 >= p.B.nenv) return;
+    const int ne = (int)((p.B.nenv - e0) < TE ? (p.B.nenv - e0) : TE);
+    const long long jbeg = p.B.off[e0], jend = p.B.off[e0 + ne];
+    const int nS = p.C.nS;
 
     for (int pb = 0; pb < p.P; pb += PB) {
-        double S0[PB], S1[PB], S2[PB];
+        __syncthreads();
+        for (int idx = tid; idx < nS * PB * ne; idx += kForceThreads) {
+            const int el = idx % ne, sc = idx / ne, c = sc % PB, s = sc / PB;
+            Ds[(size_t)sc * TE + el] = (pb + c < p.P) ? p.Dt[((size_t)s * p.P + pb + c) * p.ldA + e0 + el] : c2{0.0, 0.0};
+        }
+        __syncthreads();
+        for (long long jabs = jbeg + tid; jabs < jend; jabs += kForceThreads) {
+            int el = 0;
+            while (el + 1 < ne && p.B.off[e0 + el + 1] <= jabs) ++el;
+            const double* r = p.B.R + 3 * (jabs - p.B.jbase);
+            const double x = r[0], y = r[1], z = r[2];
+            int q = 0;
+            if (p.B.species) { q = p.B.species[jabs - p.B.jbase] - 1; if (q < 0 || q >= p.C.nQ) q = 0; }
+            const Spher sp = cart2spher(x, y, z);
+            double Rn[NMAX], dRn[NMAX];
+            radial_ed<NMAX>(p.rp, sp.r, Rn, dRn);
+            const int* cmap = p.C.colmap + (size_t)q * p.C.nPused;
+            double S0[PB], S1[PB], S2[PB];
 #pragma unroll
-        for (int c = 0; c < PB; ++c) { S0[c] = 0.0; S1[c] = 0.0; S2[c] = 0.0; }
-        for_each_lm_ed(p.ap, sp, [&](int l, int m, double Pt, double dP, double epr, double epi) {
-            const int col = __ldg(cmap + index_p(l, m));
-            if (col < 0) return;
-            const int cnt = __ldg(p.C.cnt + col), base = __ldg(p.C.base + col);
-            const double f0 = (m == 0) ? Pt : Pt * sp.sth;    // |Y| factor:  Y = ep * f0
-            const double f1 = (double)m * Pt;
+            for (int c = 0; c < PB; ++c) { S0[c] = 0.0; S1[c] = 0.0; S2[c] = 0.0; }
+            for_each_lm_ed(p.ap, sp, [&](int l, int m, double Pt, double dP, double epr, double epi) {
+                const int col = __ldg(cmap + index_p(l, m));
+                if (col < 0) return;
+                const int cnt = __ldg(p.C.cnt + col), base = __ldg(p.C.base + col);
+                const double f0 = (m == 0) ? Pt : Pt * sp.sth;    // |Y| factor:  Y = ep * f0
+                const double f1 = (double)m * Pt;
+#pragma unroll
+                for (int c = 0; c < PB; ++c) {
+                    double ur = 0.0, ui = 0.0, vr = 0.0, vi = 0.0;
+                    const c2* D = Ds + ((size_t)base * PB + c) * TE + el;
+#pragma unroll
+                    for (int n = 0; n < NMAX; ++n) {
+                        if (n < cnt) {
+                            const c2 d = D[(size_t)n * PB * TE];
+                            ur += d.x * Rn[n]; ui += d.y * Rn[n];
+                            vr += d.x * dRn[n]; vi += d.y * dRn[n];
+                        }
+                    }
+                    // z = u * ep ;  Re(v * ep)
+                    const double zr = ur * epr - ui * epi, zi = ur * epi + ui * epr;
+                    const double ve = vr * epr - vi * epi;
+                    S0[c] += f0 * ve;          // radial:   rhat * Re(v Y)
+                    S1[c] += f1 * zi;          // azimuth:  m Pt Im(u ep)
+                    S2[c] += dP * zr;          // polar:    dP Re(u ep)
+                }
+            });
+            // g = rhat S0 + (1/r) [ sphi S1 + cphi cth S2,  -cphi S1 + sphi cth S2,  -sth S2 ]
+            const double rx = x * sp.rinv, ry = y * sp.rinv, rz = z * sp.rinv;
+            const long long jl = jabs - p.B.off[0];
 #pragma unroll
             for (int c = 0; c < PB; ++c) {
                 if (pb + c >= p.P) break;
-                double ur = 0.0, ui = 0.0, vr = 0.0, vi = 0.0;
-                const c2* D = p.Dt + ((size_t)base * p.P + pb + c) * p.ldA + e;
-#pragma unroll
-                for (int n = 0; n < NMAX; ++n) {
-                    if (n < cnt) {
-                        const c2 d = D[(size_t)n * p.P * p.ldA];
-                        ur += d.x * Rn[n]; ui += d.y * Rn[n];
-                        vr += d.x * dRn[n]; vi += d.y * dRn[n];
-                    }
-                }
-                // z = u * ep ;  Re(v * ep)
-                const double zr = ur * epr - ui * epi, zi = ur * epi + ui * epr;
-                const double ve = vr * epr - vi * epi;
-                S0[c] += f0 * ve;          // radial:   rhat * Re(v Y)
-                S1[c] += f1 * zi;          // azimuth:  m Pt Im(u ep)
-                S2[c] += dP * zr;          // polar:    dP Re(u ep)
+                const double gx = rx * S0[c] + sp.rinv * (sp.sphi * S1[c] + sp.cphi * sp.cth * S2[c]);
+                const double gy = ry * S0[c] + sp.rinv * (-sp.cphi * S1[c] + sp.sphi * sp.cth * S2[c]);
+                const double gz = rz * S0[c] - sp.rinv * sp.sth * S2[c];
+                const int ch = pb + c, prop = ch / p.ncomp, comp = ch % p.ncomp;
+                double* g = p.G + (((size_t)jl * p.nprop + prop) * 3) * p.ncomp + comp;
+                g[0] = gx; g[p.ncomp] = gy; g[2 * p.ncomp] = gz;
             }
-        });
-        // g = rhat S0 + (1/r) [ sphi S1 + cphi cth S2,  -cphi S1 + sphi cth S2,  -sth S2 ]
-        const double rx = x * sp.rinv, ry = y * sp.rinv, rz = z * sp.rinv;
-#pragma unroll
-        for (int c = 0; c < PB; ++c) {
-            if (pb + c >= p.P) break;
-            const double gx = rx * S0[c] + sp.rinv * (sp.sphi * S1[c] + sp.cphi * sp.cth * S2[c]);
-            const double gy = ry * S0[c] + sp.rinv * (-sp.cphi * S1[c] + sp.sphi * sp.cth * S2[c]);
-            const double gz = rz * S0[c] - sp.rinv * sp.sth * S2[c];
-            const int ch = pb + c, prop = ch / p.ncomp, comp = ch % p.ncomp;
-            double* g = p.G + (((size_t)jl * p.nprop + prop) * 3) * p.ncomp + comp;
-            g[0] = gx; g[p.ncomp] = gy; g[2 * p.ncomp] = gz;
         }
     }
 }

@@ -10,10 +10,10 @@
 //     radial index n is a dense prefix 0..cnt-1.  Functions with m < 0 are never stored: the pooled
 //     A_{n l -m} equals (-1)^m conj(A_{n l m}) because Y_l^{-m} = (-1)^m conj(Y_l^m)
 //     (src/polynomials/sphericalharmonics.jl:394-398), so one complex "slot" serves both.
-//   * adjoint trees: for every one-particle function a ("target") and every correlation order nu, the
-//     nested sum  dE/dA_a |_nu = sum_b A_b ( sum_c A_c ( ... sum_z w A_z ) )  over the AA functions that
-//     contain a, with weights w = multiplicity * c~ (the stage-2 loop of src/evaluator.jl:180-185
-//     regrouped by target, which makes it a gather with no atomics).
+//   * adjoint lists: for every one-particle function a ("target") and every correlation order nu, the flat
+//     list of the AA functions that contain a:  dE/dA_a |_nu = sum_leaves w * prod_{others} A_other,
+//     with weights w = multiplicity * c~ (the stage-2 loop of src/evaluator.jl:180-185 regrouped by
+//     target, which turns its scatter-add into a gather with no atomics).
 //   * CSR copy of A2Bmap for the row-parallel B = A2B * AA product (src/symmbasis.jl:248-264).
 #pragma once
 
@@ -38,19 +38,19 @@ struct ModelError : std::runtime_error {
     ModelError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
 };
 
-constexpr int kMaxOrd = 6;   // correlation orders supported by the adjoint trees
+constexpr int kMaxOrd = 5;   // correlation orders supported by the adjoint lists (4 other factors per leaf)
 
 struct Column { int q, l, m, cnt, base, ip; };
 
-// One adjoint tree per correlation order nu >= 2.  depth = nu - 1 levels of "other" factors.
-//   ptr0[a]..ptr0[a+1]              children of target a at level 0
-//   level k < depth-1: nidx[k][i] = A-code of node i, nptr[k][i]..nptr[k][i+1] = its children at level k+1
-//   last level (leaves): lidx[i] = A-code, laa[i] = AA index (0-based), lmult[i] = multiplicity
+// One adjoint list per correlation order nu >= 2, sorted by target:
+//   ptr[a]..ptr[a+1]   leaves of target a
+//   codes[4*i + k]     A-code of the k-th other factor of leaf i (k < nu-1)
+//   laa[i], lmult[i]   AA index (0-based) and multiplicity: weight = lmult * c~[laa]
 struct Tree {
     int nu = 0;
-    std::vector<int32_t> ptr0;
-    std::vector<int32_t> nidx[kMaxOrd], nptr[kMaxOrd];
-    std::vector<int32_t> lidx, laa, lmult;
+    std::vector<int32_t> ptr;
+    std::vector<uint16_t> codes;
+    std::vector<int32_t> laa, lmult;
 };
 
 struct HostTables {
@@ -95,7 +95,7 @@ inline void build_tables(const aceb200_desc& d, HostTables& T)
     if (d.nA < 1 || d.nAA < 1 || d.nB < 0 || d.nnz < 0) throw ModelError(ACEB200_EDESC, "empty basis");
     if (!(d.ncomp == 1 || d.ncomp == 3 || d.ncomp == 9)) throw ModelError(ACEB200_EUNSUPPORTED, "ncomp must be 1, 3 or 9");
     if (d.nprop < 1) throw ModelError(ACEB200_EDESC, "nprop < 1");
-    if (d.maxord > kMaxOrd) throw ModelError(ACEB200_EUNSUPPORTED, "correlation order > 6");
+    if (d.maxord > kMaxOrd) throw ModelError(ACEB200_EUNSUPPORTED, "correlation order > 5");
     if (!d.rad_A || !d.rad_B || !d.rad_C || !d.indices || !d.orders || (d.maxord > 0 && !d.iAA2iA) || !d.colptr || (d.nnz > 0 && (!d.rowval || !d.nzval)))
         throw ModelError(ACEB200_EDESC, "null table pointer");
     int ib_rn = -1, ib_ylm = -1, ib_cat = -1;
@@ -227,36 +227,20 @@ inline void build_tables(const aceb200_desc& d, HostTables& T)
             }
         }
     }
+    if (T.nS * 4 + 3 > 65535) throw ModelError(ACEB200_EUNSUPPORTED, "too many one-particle slots for 16-bit A-codes");
     for (int nu = 2; nu <= T.maxord; ++nu) {
         Tree& tr = T.trees[nu];
         tr.nu = nu;
-        int depth = nu - 1;
-        tr.ptr0.assign(T.nA + 1, 0);
-        std::vector<int32_t> cnt0(T.nA, 0);
-        // std::map iterates keys (target, factor at level 0, ..., leaf factor) in lexicographic order,
-        // i.e. a depth-first walk of the tree; a node at level k is new when the key prefix
-        // key[0..k+1] differs from the previous key's.
-        std::vector<int32_t> prev;
+        tr.ptr.assign(T.nA + 1, 0);
+        // std::map iterates the keys (target, others...) in lexicographic order: leaves come out sorted by target
         for (auto& kv : entries[nu]) {
             const std::vector<int32_t>& key = kv.first;
-            int dif = 0;
-            if (!prev.empty()) { while (dif < nu && key[dif] == prev[dif]) ++dif; }
-            for (int k = 0; k < depth - 1; ++k) {
-                if (dif <= k + 1) {
-                    tr.nidx[k].push_back(T.iA_code[key[k + 1]]);
-                    tr.nptr[k].push_back(k + 1 < depth - 1 ? (int32_t)tr.nidx[k + 1].size() : (int32_t)tr.lidx.size());
-                    if (k == 0) cnt0[key[0]]++;
-                }
-            }
-            tr.lidx.push_back(T.iA_code[key[depth]]);
+            for (int k = 0; k < 4; ++k) tr.codes.push_back(k < nu - 1 ? (uint16_t)T.iA_code[key[k + 1]] : (uint16_t)0);
             tr.laa.push_back(kv.second.first);
             tr.lmult.push_back(kv.second.second);
-            if (depth == 1) cnt0[key[0]]++;
-            prev = key;
+            tr.ptr[key[0] + 1]++;
         }
-        for (int a = 0; a < T.nA; ++a) tr.ptr0[a + 1] = tr.ptr0[a] + cnt0[a];
-        for (int k = 0; k < depth - 1; ++k)
-            tr.nptr[k].push_back(k + 1 < depth - 1 ? (int32_t)tr.nidx[k + 1].size() : (int32_t)tr.lidx.size());
+        for (int a = 0; a < T.nA; ++a) tr.ptr[a + 1] += tr.ptr[a];
     }
 }
 

@@ -81,12 +81,14 @@ struct aceb200_model {
     const int *d_orders = nullptr, *d_spec = nullptr;
     const int *d_csr_ptr = nullptr, *d_csr_col = nullptr;
     const c2* d_csr_val = nullptr;
-    TreeDev tree[kMaxOrdDev + 1];
+    ListDev list[kMaxOrdDev + 1];
     DevBuf d_w0, d_w1;
     DevBuf d_lw[kMaxOrdDev + 1];
+    DevBuf d_stream;                // k_adjoint_stream records (single channel, real weights)
+    int stream_chunks = 0, stream_nf = 0;   // 0 chunks: use the generic k_adjoint
     // per-call workspace (guarded by mu)
     std::mutex mu;
-    DevBuf ws_Ac, ws_Dt, ws_envidx, ws_E, ws_G, ws_A, ws_AA, ws_dA, ws_dAA, ws_out, ws_err;
+    DevBuf ws_Ac, ws_Dt, ws_E, ws_G, ws_A, ws_AA, ws_dA, ws_dAA, ws_out, ws_err;
     DevBuf in_off, in_R, in_sp;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
@@ -135,6 +137,8 @@ static void fill_params(aceb200_model* m, const aceb200_desc& d)
     for (int mm = 0; mm <= kMaxL + 1; ++mm) ap.offc[mm] = sqrt(2.0 * mm + 3.0);    // :179, :191
 }
 
+static void upload_stream(aceb200_model* m);
+
 // c~ and the weights that depend on it: order-0/1 weights and the leaf weights of every tree
 static void upload_weights(aceb200_model* m, const double* c)
 {
@@ -162,12 +166,85 @@ static void upload_weights(aceb200_model* m, const double* c)
     CU(cudaMemcpy(m->d_w1.p, w1.data(), w1.size() * sizeof(double), cudaMemcpyHostToDevice));
     for (int nu = 2; nu <= T.maxord; ++nu) {
         const Tree& tr = T.trees[nu];
-        std::vector<double> lw(std::max<size_t>(tr.lidx.size(), 1) * Ppad * cs, 0.0);
-        for (size_t i = 0; i < tr.lidx.size(); ++i) put(lw, i, tr.laa[i], (double)tr.lmult[i]);
-        m->d_lw[nu].reserve(lw.size() * sizeof(double));
-        CU(cudaMemcpy(m->d_lw[nu].p, lw.data(), lw.size() * sizeof(double), cudaMemcpyHostToDevice));
-        m->tree[nu].lw = m->d_lw[nu].as<double>();
+        const size_t nleaf = tr.laa.size();
+        const int stride = 8 + 8 * Ppad * cs;
+        std::vector<unsigned char> rec(std::max<size_t>(nleaf, 1) * stride, 0);
+        std::vector<double> w((size_t)Ppad * cs);
+        for (size_t i = 0; i < nleaf; ++i) {
+            std::fill(w.begin(), w.end(), 0.0);
+            put(w, 0, tr.laa[i], (double)tr.lmult[i]);
+            memcpy(&rec[i * stride], &tr.codes[4 * i], 8);
+            memcpy(&rec[i * stride + 8], w.data(), w.size() * sizeof(double));
+        }
+        m->d_lw[nu].reserve(rec.size());
+        CU(cudaMemcpy(m->d_lw[nu].p, rec.data(), rec.size(), cudaMemcpyHostToDevice));
+        m->list[nu].rec = m->d_lw[nu].as<unsigned char>();
+        m->list[nu].stride = stride;
     }
+    upload_stream(m);
+}
+
+// Flatten the adjoint lists into the record stream k_adjoint_stream consumes (see ace_kernels.cuh).
+static void upload_stream(aceb200_model* m)
+{
+    HostTables& T = m->T;
+    m->stream_chunks = 0;
+    if (T.P != 1 || m->cw || T.maxord < 2 || T.maxord > 4 || !T.symreal) return;
+    const int NF = T.maxord <= 3 ? 2 : 3;
+    const uint16_t ONE = (uint16_t)(T.nS * 4);
+    std::vector<uint32_t> words;   // 4 per record
+    auto emit_block = [&](const uint16_t (*codes)[3], const double* w, int nleaf, unsigned flags, unsigned tcode, unsigned tidx) {
+        for (int k = 0; k < 4; ++k) {
+            uint16_t c0 = ONE, c1 = ONE, c2v = ONE;
+            double wk = 0.0;
+            if (k < nleaf) { c0 = codes[k][0]; c1 = codes[k][1]; c2v = codes[k][2]; wk = w[k]; }
+            unsigned ctl = k == 0 ? flags : (k == 1 ? tcode : (k == 2 ? tidx : 0u));
+            uint64_t wb; memcpy(&wb, &wk, 8);
+            words.push_back((uint32_t)c0 | ((uint32_t)c1 << 16));
+            words.push_back((uint32_t)c2v | (ctl << 16));
+            words.push_back((uint32_t)(wb & 0xffffffffu));
+            words.push_back((uint32_t)(wb >> 32));
+        }
+    };
+    for (int s = 0; s < T.nS; ++s) {
+        int tg[2] = {T.slot_pos[s], T.slot_neg[s]};
+        int ntg = 0, last = -1;
+        for (int k = 0; k < 2; ++k) if (tg[k] >= 0) { ++ntg; last = k; }
+        if (ntg == 0) { emit_block(nullptr, nullptr, 0, kSlotEnd, ONE, 0); continue; }
+        for (int k = 0; k < 2; ++k) {
+            const int a = tg[k];
+            if (a < 0) continue;
+            unsigned tflags = kTgtEnd | (k == last ? kSlotEnd : 0u);
+            if (T.iA_code[a] & 1) tflags |= kTgtNeg;
+            if (T.iA_code[a] & 2) tflags |= kTgtOdd;
+            const unsigned tcode = (unsigned)T.iA_code[a];
+            int lastnu = 0;
+            for (int nu = 2; nu <= T.maxord; ++nu) if (T.trees[nu].ptr[a + 1] > T.trees[nu].ptr[a]) lastnu = nu;
+            if (lastnu == 0) { emit_block(nullptr, nullptr, 0, tflags | 2u, tcode, (unsigned)a); continue; }
+            for (int nu = 2; nu <= T.maxord; ++nu) {
+                const Tree& tr = T.trees[nu];
+                const int i0 = tr.ptr[a], i1 = tr.ptr[a + 1];
+                for (int i = i0; i < i1; i += 4) {
+                    uint16_t codes[4][3];
+                    double w[4];
+                    const int n = std::min(4, i1 - i);
+                    for (int j = 0; j < n; ++j) {
+                        for (int f = 0; f < 3; ++f) codes[j][f] = (f < nu - 1) ? tr.codes[4 * (size_t)(i + j) + f] : ONE;
+                        w[j] = (m->ctilde[(size_t)tr.laa[i + j]] * (double)tr.lmult[i + j]).real();
+                    }
+                    unsigned flags = (unsigned)nu;
+                    if (i + 4 >= i1) { flags |= kSegEnd; if (nu == lastnu) flags |= tflags; }
+                    emit_block(codes, w, n, flags, tcode, (unsigned)a);
+                }
+            }
+        }
+    }
+    // pad to whole chunks of 8 blocks with inert blocks
+    while ((words.size() / 16) % 8 != 0) emit_block(nullptr, nullptr, 0, 0u, ONE, 0);
+    m->d_stream.reserve(words.size() * sizeof(uint32_t));
+    CU(cudaMemcpy(m->d_stream.p, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    m->stream_chunks = (int)(words.size() / 16 / 8);
+    m->stream_nf = NF;
 }
 
 static void upload_tables(aceb200_model* m)
@@ -190,14 +267,8 @@ static void upload_tables(aceb200_model* m)
     std::vector<c2> val(T.csr_val.size());
     for (size_t k = 0; k < val.size(); ++k) val[k] = c2{T.csr_val[k].real(), T.csr_val[k].imag()};
     m->d_csr_val = upload(m->pool, val);
-    for (int nu = 2; nu <= T.maxord; ++nu) {
-        const Tree& tr = T.trees[nu];
-        TreeDev& D = m->tree[nu];
-        memset(&D, 0, sizeof(D));
-        D.ptr0 = upload(m->pool, tr.ptr0);
-        for (int k = 0; k < nu - 2; ++k) { D.nidx[k] = upload(m->pool, tr.nidx[k]); D.nptr[k] = upload(m->pool, tr.nptr[k]); }
-        D.lidx = upload(m->pool, tr.lidx);
-    }
+    for (int nu = 0; nu <= kMaxOrdDev; ++nu) memset(&m->list[nu], 0, sizeof(ListDev));
+    for (int nu = 2; nu <= T.maxord; ++nu) m->list[nu].ptr = upload(m->pool, T.trees[nu].ptr);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -309,12 +380,12 @@ static void launch_pool_t(aceb200_model* m, const PoolParams& p, dim3 grid, size
     ACE_LAUNCH(kfn, grid, dim3(kPoolThreads), smem, m->stream, p);
 }
 
-static void launch_pool(aceb200_model* m, const BatchDev& B, long long ldA, int* envidx)
+static void launch_pool(aceb200_model* m, const BatchDev& B, long long ldA)
 {
     HostTables& T = m->T;
     PoolParams p;
     p.rp = m->rp; p.ap = m->ap; p.C = m->C; p.B = B;
-    p.Ac = m->ws_Ac.as<c2>(); p.ldA = ldA; p.envidx = envidx; p.errflag = m->ws_err.as<int>();
+    p.Ac = m->ws_Ac.as<c2>(); p.ldA = ldA; p.errflag = m->ws_err.as<int>();
     p.colpass_size = std::min(T.ncols, kPoolThreads);
     p.TE = std::max(1, kPoolThreads / p.colpass_size);
     int nP = (T.Lused + 1) * (T.Lused + 2) / 2;
@@ -342,15 +413,40 @@ static void launch_adjoint_t(aceb200_model* m, const AdjointParams& p, int grid,
     ACE_LAUNCH(kfn, dim3(grid), dim3(32), smem, m->stream, p);
 }
 
+template <int NF>
+static void launch_stream_t(aceb200_model* m, const StreamParams& p, int grid, size_t smem)
+{
+    auto kfn = k_adjoint_stream<NF>;
+    CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ACE_LAUNCH(kfn, dim3(grid), dim3(32), smem, m->stream, p);
+}
+
 static void launch_adjoint(aceb200_model* m, long long nenv, long long ldA, bool want_D)
 {
     HostTables& T = m->T;
+    if (m->stream_chunks > 0 && !getenv("ACEB200_NO_STREAM")) {
+        StreamParams p;
+        p.nS = T.nS; p.has_const = T.has_const; p.want_D = want_D ? 1 : 0; p.nchunks = m->stream_chunks;
+        p.stream = m->d_stream.as<uint4>(); p.w1 = m->d_w1.as<double>();
+        p.w0 = T.has_const ? m->ctilde[0].real() : 0.0;
+        p.Ac = m->ws_Ac.as<c2>(); p.ldA = ldA; p.Dt = m->ws_Dt.as<c2>(); p.E = m->ws_E.as<double>(); p.nenv = nenv;
+        const size_t smem = (size_t)(T.nS + 1) * 32 * sizeof(c2) + 3 * 32 * sizeof(uint4);
+        if (smem <= (size_t)m->smem_optin) {
+            const long long ntiles = (nenv + 31) / 32;
+            const int per_sm = std::max<int>(1, std::min<int>(32, (int)((size_t)m->smem_optin / (smem + 1024))));
+            const int grid = (int)std::min<long long>(ntiles, (long long)m->sm_count * per_sm);
+            if (m->stream_nf == 2) launch_stream_t<2>(m, p, grid, smem); else launch_stream_t<3>(m, p, grid, smem);
+            CU(cudaGetLastError());
+            m->launches++;
+            return;
+        }
+    }
     AdjointParams p;
     memset(&p, 0, sizeof(p));
     p.nS = T.nS; p.nA = T.nA; p.maxord = T.maxord; p.P = T.P; p.Ppad = m->Ppad; p.has_const = T.has_const; p.want_D = want_D ? 1 : 0;
     p.slot_pos = m->d_slot_pos; p.slot_neg = m->d_slot_neg; p.code = m->d_code;
     p.w1 = m->d_w1.as<double>(); p.w0 = m->d_w0.as<double>();
-    for (int nu = 2; nu <= T.maxord; ++nu) p.tree[nu] = m->tree[nu];
+    for (int nu = 2; nu <= T.maxord; ++nu) p.list[nu] = m->list[nu];
     p.Ac = m->ws_Ac.as<c2>(); p.ldA = ldA; p.Dt = m->ws_Dt.as<c2>(); p.E = m->ws_E.as<double>(); p.nenv = nenv;
     size_t smem = (size_t)T.nS * 32 * sizeof(c2);
     if (smem > (size_t)m->smem_optin)
@@ -372,20 +468,31 @@ static void launch_adjoint(aceb200_model* m, long long nenv, long long ldA, bool
 }
 
 template <int NMAX, int PB>
-static void launch_forces_t(aceb200_model* m, const ForceParams& p)
+static void launch_forces_t(aceb200_model* m, const ForceParams& p, unsigned grid, size_t smem)
 {
     auto kfn = k_forces<NMAX, PB>;
-    ACE_LAUNCH(kfn, dim3((unsigned)((p.nJ + kForceThreads - 1) / kForceThreads)), dim3(kForceThreads), 0, m->stream, p);
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ACE_LAUNCH(kfn, dim3(grid), dim3(kForceThreads), smem, m->stream, p);
 }
 
 static void launch_forces(aceb200_model* m, const BatchDev& B, long long nJ, long long ldA, double* G)
 {
     if (nJ == 0) return;
     ForceParams p;
-    p.rp = m->rp; p.ap = m->ap; p.C = m->C; p.B = B; p.envidx = m->ws_envidx.as<int>();
-    p.Dt = m->ws_Dt.as<c2>(); p.ldA = ldA; p.P = m->T.P; p.nprop = m->T.nprop; p.ncomp = m->T.ncomp; p.G = G; p.nJ = nJ;
+    p.rp = m->rp; p.ap = m->ap; p.C = m->C; p.B = B;
+    p.Dt = m->ws_Dt.as<c2>(); p.ldA = ldA; p.P = m->T.P; p.nprop = m->T.nprop; p.ncomp = m->T.ncomp; p.G = G;
     const int pb = m->PB == 1 ? 1 : (m->PB == 3 ? 3 : 2);
-#define ACE_F(NM) { if (pb == 1) launch_forces_t<NM, 1>(m, p); else if (pb == 3) launch_forces_t<NM, 3>(m, p); else launch_forces_t<NM, 2>(m, p); }
+    // environments per CTA: enough neighbours for a few rounds of 128 threads, bounded by the staging buffer
+    const double Jav = std::max(1.0, (double)nJ / (double)B.nenv);
+    int TE = (int)std::min<double>(16.0, std::max(1.0, std::ceil(256.0 / Jav)));
+    const size_t per_env = (size_t)m->T.nS * pb * sizeof(c2);
+    while (TE > 1 && per_env * TE > 64 * 1024) --TE;
+    if (per_env * TE > (size_t)m->smem_optin)
+        throw ModelError(ACEB200_EUNSUPPORTED, "one-particle basis too large for the shared-memory staging of k_forces");
+    p.TE = TE;
+    const size_t smem = per_env * TE;
+    const unsigned grid = (unsigned)((B.nenv + TE - 1) / TE);
+#define ACE_F(NM) { if (pb == 1) launch_forces_t<NM, 1>(m, p, grid, smem); else if (pb == 3) launch_forces_t<NM, 3>(m, p, grid, smem); else launch_forces_t<NM, 2>(m, p, grid, smem); }
     switch (m->NMAX) {
     case 4: ACE_F(4) break;
     case 8: ACE_F(8) break;
@@ -505,10 +612,9 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
         m->ws_Ac.reserve((size_t)T.nS * ldA * sizeof(c2));
         if (want & W_G) {
             m->ws_Dt.reserve((size_t)T.nS * P * ldA * sizeof(c2));
-            m->ws_envidx.reserve(std::max<long long>(nj, 1) * sizeof(int));
         }
         CU(cudaEventRecord(m->ev0, m->stream));
-        launch_pool(m, B, ldA, (want & W_G) ? m->ws_envidx.as<int>() : nullptr);
+        launch_pool(m, B, ldA);
 
         if (want & (W_E | W_G)) {
             m->ws_E.reserve((size_t)ne * P * sizeof(double));
@@ -681,8 +787,8 @@ int aceb200_model_destroy(aceb200_model* m)
     if (!m) return ACEB200_OK;
     cudaSetDevice(m->device);
     for (DevBuf& b : m->pool) b.release();
-    DevBuf* bufs[] = {&m->d_w0, &m->d_w1, &m->ws_Ac, &m->ws_Dt, &m->ws_envidx, &m->ws_E, &m->ws_G, &m->ws_A, &m->ws_AA,
-                      &m->ws_dA, &m->ws_dAA, &m->ws_out, &m->ws_err, &m->in_off, &m->in_R, &m->in_sp};
+    DevBuf* bufs[] = {&m->d_w0, &m->d_w1, &m->ws_Ac, &m->ws_Dt, &m->ws_E, &m->ws_G, &m->ws_A, &m->ws_AA,
+                      &m->ws_dA, &m->ws_dAA, &m->ws_out, &m->ws_err, &m->in_off, &m->in_R, &m->in_sp, &m->d_stream};
     for (DevBuf* b : bufs) b->release();
     for (int nu = 0; nu <= kMaxOrdDev; ++nu) m->d_lw[nu].release();
     if (m->ev0) cudaEventDestroy(m->ev0);

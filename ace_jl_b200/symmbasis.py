@@ -25,11 +25,14 @@ from .symmetrygroups import NoSym, O3
 class SparseCSC:
     """Minimal CSC container with vector-valued entries (SparseMatrixCSC{PROP,Int})."""
 
-    def __init__(self, m: int, n: int, colptr, rowval, nzval):
+    def __init__(self, m: int, n: int, colptr, rowval, nzval, ncomp: int = None):
         self.m, self.n = int(m), int(n)
         self.colptr = np.asarray(colptr, dtype=np.int32)
         self.rowval = np.asarray(rowval, dtype=np.int32)
-        self.nzval = np.asarray(nzval, dtype=np.complex128).reshape(len(self.rowval), -1)
+        nz = np.asarray(nzval, dtype=np.complex128)
+        if ncomp is None:
+            ncomp = nz.shape[1] if nz.ndim == 2 else 1
+        self.nzval = nz.reshape(len(self.rowval), ncomp)
 
     @property
     def shape(self):
@@ -65,7 +68,7 @@ class SparseCSC:
         for c in cols:
             colptr[c] += 1
         colptr = np.concatenate(([1], 1 + np.cumsum(colptr[1:] - 1)))
-        return cls(m, n, colptr, rows, np.array(vals).reshape(len(rows), ncomp))
+        return cls(m, n, colptr, rows, np.array(vals).reshape(len(rows), ncomp), ncomp)
 
     def select_columns(self, keep0: np.ndarray):
         """A[:, keep] with keep 0-based sorted."""
@@ -76,7 +79,7 @@ class SparseCSC:
             rows.extend(self.rowval[a:b])
             vals.extend(self.nzval[a:b])
             colptr.append(len(rows) + 1)
-        return SparseCSC(self.m, len(keep0), colptr, rows, np.array(vals).reshape(len(rows), self.ncomp))
+        return SparseCSC(self.m, len(keep0), colptr, rows, np.array(vals).reshape(len(rows), self.ncomp), self.ncomp)
 
     def select_rows(self, keep0: np.ndarray):
         newrow = -np.ones(self.m, dtype=np.int64)
@@ -90,7 +93,7 @@ class SparseCSC:
                     rows.append(r + 1)
                     vals.append(self.nzval[k])
             colptr.append(len(rows) + 1)
-        return SparseCSC(len(keep0), self.n, colptr, rows, np.array(vals).reshape(len(rows), self.ncomp))
+        return SparseCSC(len(keep0), self.n, colptr, rows, np.array(vals).reshape(len(rows), self.ncomp), self.ncomp)
 
     def col_norms(self) -> np.ndarray:
         """sum(norm, A, dims=1)."""

@@ -33,6 +33,9 @@ struct dim3 {
     dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 struct double2 { double x, y; };
+struct uint2 { unsigned x, y; };
+struct uint4 { unsigned x, y, z, w; };
+inline double __hiloint2double(int hi, int lo) { union { double d; unsigned long long u; } w; w.u = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo; return w.d; }
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
 
 namespace emu {

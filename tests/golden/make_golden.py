@@ -43,7 +43,7 @@ def main():
         E, G = o.energy_forces(R, off, sp)
         B, dB = o.eval_dB(R, off, sp)
         out = dict(R=R, offsets=off, c=c, E=E, G=G, A=o.eval_A(R, off, sp), AA=o.eval_AA(R, off, sp), B=B,
-                   dB_checksum=np.array([np.abs(dB).sum(), (dB * np.arange(dB.size).reshape(dB.shape) % 7).sum()]),
+                   dB_checksum=np.array([np.abs(dB).sum(), np.sqrt((dB ** 2).sum()), np.abs(dB).max()]),
                    ctilde=o.eff_coeffs())
         if sp is not None:
             out["species"] = sp
