@@ -25,7 +25,11 @@
 
 namespace aceb200 {
 
-struct c2 { double x, y; };   // complex value, 16 bytes
+#ifdef ACEB200_EMU
+struct alignas(16) c2 { double x, y; };   // complex value, 16 bytes
+#else
+struct __align__(16) c2 { double x, y; };   // complex value: 16-byte aligned so that it moves as one 128-bit access
+#endif
 
 ACE_HD inline c2 cmul(c2 a, c2 b) { return c2{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
 
@@ -56,6 +60,7 @@ struct ColumnsDev {
     int ncols, nS, nPused, nQ;
     const int* q; const int* l; const int* m; const int* cnt; const int* base; const int* ip;
     const int* colmap;      // [nQ][nPused]
+    const int* slot_n; const int* slot_ip; const int* slot_q;   // [nS] decode of a canonical slot
 };
 
 // Adjoint list of one correlation order: records of `stride` bytes, sorted by target.
@@ -78,6 +83,12 @@ struct BatchDev {
 // ------------------------------------------------------------------------------------------------
 // k_pool: A_{slot}[env] for a chunk of environments
 // ------------------------------------------------------------------------------------------------
+// A CTA owns TE consecutive environments and works through them in sub-tiles of at most 128 neighbours:
+// as many WHOLE environments as fit (or a 128-neighbour piece of one that does not).
+//   phase a  one thread per neighbour: R_n -> SR[row][n], Y_l^m (m >= 0) -> SY[row][ip]   (registers -> smem)
+//   phase b  one thread per (environment, slot) item, flat over the sub-tile: the reduction over the
+//            environment's neighbours is a serial loop over its staged rows -- no atomics, deterministic.
+// Row strides are odd (in 8- resp. 16-byte units) so that both phases are bank-conflict free.
 struct PoolParams {
     RadialParams rp;
     AlpParams ap;
@@ -87,87 +98,106 @@ struct PoolParams {
     long long ldA;
     int* errflag;           // set to ACEB200_EEMPTY / ACEB200_ECATEGORY on bad input
     int TE;                 // environments per CTA
-    int SK;                 // staging row stride in doubles (odd)
-    int colpass_size;       // columns handled per blockIdx.y
+    int SKR, SKY;           // staging row strides: doubles (radial) and c2 (harmonics)
 };
 
 constexpr int kPoolThreads = 128;
+constexpr int kPoolItems = 4;       // (environment, slot) items a thread can own per sub-tile
 
 template <int NMAX>
 __global__ void __launch_bounds__(kPoolThreads) k_pool(const PoolParams p)
 {
-    ACE_DYN_SMEM(double, smem);
-    double* S = smem;                                      // [kPoolThreads][SK]
-    int* sq = reinterpret_cast<int*>(S + (size_t)kPoolThreads * p.SK);   // [kPoolThreads] species of staged neighbour
+    ACE_DYN_SMEM(c2, smem);
+    c2* SY = smem;                                                            // [128][SKY]
+    double* SR = reinterpret_cast<double*>(SY + (size_t)kPoolThreads * p.SKY);  // [128][SKR]
+    int* sq = reinterpret_cast<int*>(SR + (size_t)kPoolThreads * p.SKR);         // [128] species of the staged neighbour
     const int tid = threadIdx.x;
-    const int N = p.rp.N;
+    const int N = p.rp.N, nS = p.C.nS;
     const long long e0 = (long long)blockIdx.x * p.TE;
     if (e0 >= p.B.nenv) return;
     const int ne = (int)((p.B.nenv - e0) < p.TE ? (p.B.nenv - e0) : p.TE);
-    const int col0 = blockIdx.y * p.colpass_size;
-    const int ncol_here = (p.C.ncols - col0) < p.colpass_size ? (p.C.ncols - col0) : p.colpass_size;
+    const long long* off = p.B.off + e0;
 
-    // work item of this thread in the pooling phase: (local environment, column)
-    const int el = tid / ncol_here;
-    const bool has_item = el < ne;
-    int cq = 0, ccnt = 0, cbase = 0, cip = 0;
-    long long jlo = 0, jhi = 0;
-    if (has_item) {
-        int col = col0 + tid % ncol_here;
-        cq = p.C.q[col]; ccnt = p.C.cnt[col]; cbase = p.C.base[col]; cip = p.C.ip[col];
-        jlo = p.B.off[e0 + el]; jhi = p.B.off[e0 + el + 1];
-        if (jhi <= jlo && blockIdx.y == 0 && tid % ncol_here == 0) atomicMax(p.errflag, 5);   // EEMPTY
-    }
-    c2 acc[NMAX];
+    c2 acc[kPoolItems];
 #pragma unroll
-    for (int n = 0; n < NMAX; ++n) acc[n] = c2{0.0, 0.0};
+    for (int it = 0; it < kPoolItems; ++it) acc[it] = c2{0.0, 0.0};
 
-    const long long jbeg = p.B.off[e0], jend = p.B.off[e0 + ne];
-    for (long long c0 = jbeg; c0 < jend; c0 += kPoolThreads) {
-        // ---- phase a: one thread per neighbour of this tile
-        const long long j = c0 + tid;
-        if (j < jend) {
+    int e = 0;
+    long long j0 = off[0];
+    while (e < ne) {
+        // ---- choose the sub-tile [j0, j1): whole environments e..e2-1, or a piece of environment e
+        const long long jend_e = off[e + 1];
+        int e2 = e + 1;
+        long long j1;
+        bool done_e;                      // the environments of this sub-tile are complete after it
+        if (j0 == off[e] && jend_e - j0 <= kPoolThreads) {
+            while (e2 < ne && off[e2 + 1] - j0 <= kPoolThreads && (e2 + 1 - e) * nS <= kPoolThreads * kPoolItems) ++e2;
+            j1 = off[e2];
+            done_e = true;
+        } else {
+            j1 = (j0 + kPoolThreads < jend_e) ? j0 + kPoolThreads : jend_e;
+            done_e = (j1 == jend_e);
+        }
+        const int nrows = (int)(j1 - j0);
+
+        // ---- phase a
+        if (tid < nrows) {
+            const long long j = j0 + tid;
             const double* r = p.B.R + 3 * (j - p.B.jbase);
             const double x = r[0], y = r[1], z = r[2];
             int q = 0;
             if (p.B.species) {
                 q = p.B.species[j - p.B.jbase] - 1;
-                if (q < 0 || q >= p.C.nQ) { atomicMax(p.errflag, 6); q = 0; }   // ECATEGORY
+                if (q < 0 || q >= p.C.nQ) { atomicMax(p.errflag, 6); q = 0; }   // ECATEGORY (src/discrete1pbasis.jl:39)
             }
             sq[tid] = q;
             const Spher sp = cart2spher(x, y, z);
             double Rn[NMAX];
             radial_e<NMAX>(p.rp, sp.r, Rn);
-            double* row = S + (size_t)tid * p.SK;
+            double* rowR = SR + (size_t)tid * p.SKR;
 #pragma unroll
-            for (int n = 0; n < NMAX; ++n) if (n < N) row[n] = Rn[n];
+            for (int n = 0; n < NMAX; ++n) if (n < N) rowR[n] = Rn[n];
+            c2* rowY = SY + (size_t)tid * p.SKY;
             for_each_lm(p.ap, sp, [&](int l, int m, double Pv, double epr, double epi) {
-                const int ip = index_p(l, m);
-                row[N + 2 * ip] = epr * Pv;
-                row[N + 2 * ip + 1] = epi * Pv;
+                rowY[index_p(l, m)] = c2{epr * Pv, epi * Pv};
             });
         }
         __syncthreads();
-        // ---- phase b: pool this tile's neighbours into the thread's column
-        if (has_item) {
-            long long a = jlo > c0 ? jlo : c0;
-            long long b = jhi < c0 + kPoolThreads ? jhi : c0 + kPoolThreads;
-            for (long long jj = a; jj < b; ++jj) {
-                const int t = (int)(jj - c0);
-                if (sq[t] != cq) continue;
-                const double* row = S + (size_t)t * p.SK;
-                const double yr = row[N + 2 * cip], yi = row[N + 2 * cip + 1];
+
+        // ---- phase b
+        const int nitems = (e2 - e) * nS;
 #pragma unroll
-                for (int n = 0; n < NMAX; ++n)
-                    if (n < ccnt) { const double rn = row[n]; acc[n].x += rn * yr; acc[n].y += rn * yi; }
+        for (int it = 0; it < kPoolItems; ++it) {
+            const int idx = tid + it * kPoolThreads;
+            if (idx < nitems) {
+                const int el = idx / nS, s = idx - el * nS;
+                const int n = __ldg(p.C.slot_n + s), ip = __ldg(p.C.slot_ip + s), q = __ldg(p.C.slot_q + s);
+                long long ra = off[e + el] - j0, rb = off[e + el + 1] - j0;
+                if (ra == rb && s == 0) atomicMax(p.errflag, 5);          // EEMPTY (src/product_1pbasis.jl:124)
+                if (ra < 0) ra = 0;
+                if (rb > nrows) rb = nrows;
+                c2 a = acc[it], a2 = c2{0.0, 0.0};
+                int r = (int)ra;
+                for (; r + 1 < (int)rb; r += 2) {
+                    const double r0 = (sq[r] == q) ? SR[(size_t)r * p.SKR + n] : 0.0;
+                    const double r1 = (sq[r + 1] == q) ? SR[(size_t)(r + 1) * p.SKR + n] : 0.0;
+                    const c2 y0 = SY[(size_t)r * p.SKY + ip], y1 = SY[(size_t)(r + 1) * p.SKY + ip];
+                    a.x += r0 * y0.x; a.y += r0 * y0.y;
+                    a2.x += r1 * y1.x; a2.y += r1 * y1.y;
+                }
+                if (r < (int)rb) {
+                    const double r0 = (sq[r] == q) ? SR[(size_t)r * p.SKR + n] : 0.0;
+                    const c2 y0 = SY[(size_t)r * p.SKY + ip];
+                    a.x += r0 * y0.x; a.y += r0 * y0.y;
+                }
+                a.x += a2.x; a.y += a2.y;
+                if (done_e) { p.Ac[(size_t)s * p.ldA + (e0 + e + el)] = a; a = c2{0.0, 0.0}; }
+                acc[it] = a;
             }
         }
         __syncthreads();
-    }
-    if (has_item) {
-#pragma unroll
-        for (int n = 0; n < NMAX; ++n)
-            if (n < ccnt) p.Ac[(size_t)(cbase + n) * p.ldA + (e0 + el)] = acc[n];
+        j0 = j1;
+        if (done_e) e = e2;
     }
 }
 
@@ -320,23 +350,28 @@ __global__ void __launch_bounds__(32) k_adjoint(const AdjointParams p)
 // ------------------------------------------------------------------------------------------------
 // k_adjoint_stream: the single-channel, real-weight fast path (energies + forces of an invariant model)
 // ------------------------------------------------------------------------------------------------
-// The adjoint lists of all targets and orders are flattened by the host into ONE stream of 16-byte
-// records, in exactly the order the kernel consumes them, grouped in blocks of 4 leaves of the same
-// (target, order):
-//     record = { u16 c0, u16 c1, u16 c2, u16 ctl, f64 w }        leaf value = w * A[c0] * A[c1] (* A[c2])
-// unused factors point at an extra slot that holds 1.  The ctl fields of a block's 4 records carry its
-// header: ctl0 = flags | order, ctl1 = A-code of the target, ctl2 = target index.
+// The adjoint lists of all targets and orders are flattened by the host into ONE stream of 32-byte
+// records, in exactly the order the kernel consumes them.  A block is one header record followed by 7
+// leaf records of the same (target, order):
+//   leaf   = { u32 off1, off2, off3|mask2, mask3|-, f64 wx, f64 wy }
+//            value = (wx Re, wy Im) of  A~[off1] * cj(A~[off2]) (* cj(A~[off3]))
+//            A~ are the canonical (m >= 0) slots; offN = slot * 512 is the byte offset of the slot row in
+//            shared memory; maskN = 0 or 0x80000000 conjugates the operand (XOR on the high word of Im);
+//            the conjugation of the first operand and all (-1)^m signs are folded into wx, wy by the host:
+//            prod_k (s_k cj^{k_k} A~_k) = (prod s_k) cj^{k_1}( A~_1 prod_{k>1} cj^{k_k xor k_1} A~_k ).
+//   header = { u32 flags|order, target off, target maskx, target masky, f64 w1, f64 1/order }
 // Because the stream is read strictly sequentially and identically by every lane, the warp fetches it
-// cooperatively -- 32 records (512 contiguous bytes) per coalesced load, two chunks ahead of use -- into a
-// small shared-memory ring, and reads records back as broadcasts.  Table latency is thereby hidden and
-// the leaf loop is branch-free; control (end of order segment / target / slot) is a warp-uniform branch
-// taken once per few dozen leaves.
+// cooperatively -- 1 KiB (4 blocks) per pair of coalesced 128-bit loads, two chunks ahead of use -- into a
+// small shared-memory ring and reads records back as broadcasts.  Table latency is hidden, the 7 leaves of
+// a block are independent (ILP without needing many warps), and control (end of order segment / target /
+// slot) is a warp-uniform branch once per block.
 constexpr unsigned kSegEnd = 8, kTgtEnd = 16, kTgtNeg = 32, kTgtOdd = 64, kSlotEnd = 128;
+constexpr int kBlkLeaves = 7;               // leaves per block
+constexpr int kChunkBlocks = 4;             // blocks per ring chunk (4 * 8 records * 32 B = 1 KiB)
 
 struct StreamParams {
-    int nS, has_const, want_D, nchunks;      // nchunks: stream length in chunks of 8 blocks = 32 records
+    int nS, has_const, want_D, nchunks;
     const uint4* stream;
-    const double* w1;                        // [nA] order-1 weights
     double w0;
     const c2* Ac; long long ldA;
     c2* Dt;                                  // [nS][ldA]
@@ -344,62 +379,97 @@ struct StreamParams {
     long long nenv;
 };
 
+__device__ __forceinline__ c2 lds_c2(const unsigned char* base, unsigned off)
+{
+    return *reinterpret_cast<const c2*>(base + off);
+}
+
+__device__ __forceinline__ double xor_hi(double v, unsigned mask)
+{
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(__double2hiint(v) ^ (int)mask, __double2loint(v));
+#else
+    union { double d; unsigned long long u; } w; w.d = v; w.u ^= ((unsigned long long)mask << 32); return w.d;
+#endif
+}
+
 template <int NF>
 __global__ void __launch_bounds__(32) k_adjoint_stream(const StreamParams p)
 {
     ACE_DYN_SMEM(c2, As);                                       // [nS + 1][32]; slot nS holds 1
-    uint4* ring = reinterpret_cast<uint4*>(As + (size_t)(p.nS + 1) * 32);   // [3][32]
+    uint4* ring = reinterpret_cast<uint4*>(As + (size_t)(p.nS + 1) * 32);   // [3][64]
     const int lane = threadIdx.x;
+    const unsigned char* Ab = reinterpret_cast<const unsigned char*>(As) + lane * 16;   // this lane's column
     const long long ntiles = (p.nenv + 31) / 32;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long e = tile * 32 + lane;
         for (int s = 0; s < p.nS; ++s) As[s * 32 + lane] = p.Ac[(size_t)s * p.ldA + e];
         As[p.nS * 32 + lane] = c2{1.0, 0.0};
         ring[lane] = __ldg(p.stream + lane);
-        if (p.nchunks > 1) ring[32 + lane] = __ldg(p.stream + 32 + lane);
+        ring[32 + lane] = __ldg(p.stream + 32 + lane);
+        if (p.nchunks > 1) { ring[64 + lane] = __ldg(p.stream + 64 + lane); ring[96 + lane] = __ldg(p.stream + 96 + lane); }
         __syncwarp();
         double E = p.has_const ? p.w0 : 0.0;
-        c2 D = c2{0.0, 0.0}, S = c2{0.0, 0.0}, acc0 = c2{0.0, 0.0}, acc1 = c2{0.0, 0.0};
+        c2 D = c2{0.0, 0.0}, S = c2{0.0, 0.0};
         int slot = 0;
         for (int ch = 0; ch < p.nchunks; ++ch) {
             const bool havepre = ch + 2 < p.nchunks;
-            uint4 pre = uint4{0u, 0u, 0u, 0u};
-            if (havepre) pre = __ldg(p.stream + (size_t)(ch + 2) * 32 + lane);
-            const uint4* rb = ring + (ch % 3) * 32;
+            uint4 pre0 = uint4{0u, 0u, 0u, 0u}, pre1 = pre0;
+            if (havepre) {
+                pre0 = __ldg(p.stream + (size_t)(ch + 2) * 64 + lane);
+                pre1 = __ldg(p.stream + (size_t)(ch + 2) * 64 + 32 + lane);
+            }
+            const uint4* rb = ring + (ch % 3) * 64;
 #pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                uint4 q[4];
+            for (int b = 0; b < kChunkBlocks; ++b) {
+                const uint4* blk = rb + b * 16;
+                c2 acc0 = c2{0.0, 0.0}, acc1 = c2{0.0, 0.0};
+                c2 a1 = c2{0.0, 0.0};
+                unsigned a1off = 0xffffffffu;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) q[k] = rb[4 * b + k];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    c2 prod = cmul(fetch_A(As, lane, q[k].x & 0xffffu), fetch_A(As, lane, q[k].x >> 16));
-                    if (NF >= 3) prod = cmul(prod, fetch_A(As, lane, q[k].y & 0xffffu));
-                    const double w = __hiloint2double((int)q[k].w, (int)q[k].z);
-                    if (k & 1) { acc1.x += w * prod.x; acc1.y += w * prod.y; }
-                    else { acc0.x += w * prod.x; acc0.y += w * prod.y; }
+                for (int k = 1; k <= kBlkLeaves; ++k) {
+                    const uint4 r0 = blk[2 * k], r1 = blk[2 * k + 1];
+                    // leaves are sorted by their first factor: re-fetch it only when it changes (warp-uniform)
+                    if (r0.x != a1off) { a1 = lds_c2(Ab, r0.x); a1off = r0.x; }
+                    c2 a2 = lds_c2(Ab, r0.y);
+                    c2 prod;
+                    if (NF == 2) {
+                        a2.y = xor_hi(a2.y, r0.z);
+                        prod = cmul(a1, a2);
+                    } else {
+                        c2 a3 = lds_c2(Ab, r0.z & 0x7fffffffu);
+                        a2.y = xor_hi(a2.y, r0.z & 0x80000000u);
+                        a3.y = xor_hi(a3.y, r0.w);
+                        prod = cmul(cmul(a1, a2), a3);
+                    }
+                    const double wx = __hiloint2double((int)r1.y, (int)r1.x), wy = __hiloint2double((int)r1.w, (int)r1.z);
+                    if (k & 1) { acc1.x += wx * prod.x; acc1.y += wy * prod.y; }
+                    else { acc0.x += wx * prod.x; acc0.y += wy * prod.y; }
                 }
-                const unsigned flags = q[0].y >> 16;
+                S.x += acc0.x + acc1.x;
+                S.y += acc0.y + acc1.y;
+                const uint4 h0 = blk[0];
+                const unsigned flags = h0.x;
                 if (flags & 0xf8u) {
-                    const c2 Aa = fetch_A(As, lane, q[1].y >> 16);
+                    const uint4 h1 = blk[1];
+                    c2 Aa = lds_c2(Ab, h0.y);
+                    Aa.x = xor_hi(Aa.x, h0.z);
+                    Aa.y = xor_hi(Aa.y, h0.w);
+                    const double w1 = __hiloint2double((int)h1.y, (int)h1.x), scale = __hiloint2double((int)h1.w, (int)h1.z);
+                    const bool neg = (flags & kTgtNeg) != 0u, odd = (flags & kTgtOdd) != 0u;
+                    // fold onto the m >= 0 slot: Re(D- grad(phi_-m)) = Re((-1)^m conj(D-) grad(phi_m))
+                    const double fx = (neg && odd) ? -1.0 : 1.0, fy = neg ? (odd ? 1.0 : -1.0) : 1.0;
                     if (flags & kSegEnd) {
-                        const c2 sg = c2{acc0.x + acc1.x, acc0.y + acc1.y};
-                        acc0 = c2{0.0, 0.0}; acc1 = c2{0.0, 0.0};
-                        const unsigned nu = flags & 7u;
-                        const double inv = nu == 2 ? 0.5 : (nu == 3 ? (1.0 / 3.0) : 0.25);
-                        S.x += sg.x; S.y += sg.y;
-                        E += (Aa.x * sg.x - Aa.y * sg.y) * inv;    // Euler: sum_a A_a dF_nu/dA_a = nu F_nu
+                        // Euler: sum_a A_a dF_nu/dA_a = nu F_nu  =>  E += Re(A_a S_seg) / nu
+                        E += (Aa.x * S.x - Aa.y * S.y) * scale;
+                        D.x += fx * S.x;
+                        D.y += fy * S.y;
+                        S = c2{0.0, 0.0};
                     }
                     if (flags & kTgtEnd) {
-                        const double w = __ldg(p.w1 + (q[2].y >> 16));
-                        S.x += w;
-                        E += Aa.x * w;
-                        if (flags & kTgtNeg) {
-                            // Re(D- grad(phi_-m)) = Re((-1)^m conj(D-) grad(phi_m)): fold onto the m > 0 slot
-                            const double sgn = (flags & kTgtOdd) ? -1.0 : 1.0;
-                            D.x += sgn * S.x; D.y -= sgn * S.y;
-                        } else { D.x += S.x; D.y += S.y; }
-                        S = c2{0.0, 0.0};
+                        // order-1 term of this target: dE/dA_a += c~ (real), E += Re(A_a) c~
+                        E += Aa.x * w1;
+                        D.x += fx * w1;
                     }
                     if (flags & kSlotEnd) {
                         if (p.want_D && e < p.nenv) p.Dt[(size_t)slot * p.ldA + e] = D;
@@ -408,7 +478,7 @@ __global__ void __launch_bounds__(32) k_adjoint_stream(const StreamParams p)
                     }
                 }
             }
-            if (havepre) ring[((ch + 2) % 3) * 32 + lane] = pre;
+            if (havepre) { ring[((ch + 2) % 3) * 64 + lane] = pre0; ring[((ch + 2) % 3) * 64 + 32 + lane] = pre1; }
             __syncwarp();
         }
         if (e < p.nenv) p.E[e] = E;
@@ -426,20 +496,43 @@ struct ForceParams {
     BatchDev B;
     const c2* Dt; long long ldA;
     int P, nprop, ncomp;
-    int TE;                  // environments per CTA
     double* G;               // [neighbour][nprop][3][ncomp], chunk-relative
 };
 
 constexpr int kForceThreads = 128;
+constexpr int kForceTE = 8;          // environments per CTA (compile-time: staging strides become immediates)
 
-// A CTA owns TE consecutive environments: it stages their folded adjoints D~ in shared memory
+// u += D[n] R[n], v += D[n] dR[n] for n < cnt, with n a compile-time register index: a fall-through
+// switch on the (warp-uniform) column length replaces a per-n predicate.
+template <int NMAX, int STRIDE>
+__device__ __forceinline__ void column_dot(const c2* D, int cnt, const double (&Rn)[NMAX], const double (&dRn)[NMAX],
+                                           double& ur, double& ui, double& vr, double& vi)
+{
+#define ACE_TERM(n)                                                                      \
+    case (n) + 1:                                                                        \
+        if ((n) < NMAX) {                                                                \
+            const c2 d = D[(size_t)(n) * STRIDE];                                        \
+            ur += d.x * Rn[(n) < NMAX ? (n) : 0]; ui += d.y * Rn[(n) < NMAX ? (n) : 0];      \
+            vr += d.x * dRn[(n) < NMAX ? (n) : 0]; vi += d.y * dRn[(n) < NMAX ? (n) : 0];    \
+        }
+    switch (cnt) {
+        ACE_TERM(31) ACE_TERM(30) ACE_TERM(29) ACE_TERM(28) ACE_TERM(27) ACE_TERM(26) ACE_TERM(25) ACE_TERM(24)
+        ACE_TERM(23) ACE_TERM(22) ACE_TERM(21) ACE_TERM(20) ACE_TERM(19) ACE_TERM(18) ACE_TERM(17) ACE_TERM(16)
+        ACE_TERM(15) ACE_TERM(14) ACE_TERM(13) ACE_TERM(12) ACE_TERM(11) ACE_TERM(10) ACE_TERM(9) ACE_TERM(8)
+        ACE_TERM(7) ACE_TERM(6) ACE_TERM(5) ACE_TERM(4) ACE_TERM(3) ACE_TERM(2) ACE_TERM(1) ACE_TERM(0)
+    default: break;
+    }
+#undef ACE_TERM
+}
+
+// A CTA owns kForceTE consecutive environments: it stages their folded adjoints D~ in shared memory
 // ([slot][channel][local env]), then runs one thread per neighbour of those environments.
 template <int NMAX, int PB>
 __global__ void __launch_bounds__(kForceThreads) k_forces(const ForceParams p)
 {
-    ACE_DYN_SMEM(c2, Ds);   // [nS][PB][TE]
+    ACE_DYN_SMEM(c2, Ds);   // [nS][PB][kForceTE]
+    constexpr int TE = kForceTE;
     const int tid = threadIdx.x;
-    const int TE = p.TE;
     const long long e0 = (long long)blockIdx.x * TE;
     if (e0 >= p.B.nenv) return;
     const int ne = (int)((p.B.nenv - e0) < TE ? (p.B.nenv - e0) : TE);
@@ -448,9 +541,9 @@ __global__ void __launch_bounds__(kForceThreads) k_forces(const ForceParams p)
 
     for (int pb = 0; pb < p.P; pb += PB) {
         __syncthreads();
-        for (int idx = tid; idx < nS * PB * ne; idx += kForceThreads) {
-            const int el = idx % ne, sc = idx / ne, c = sc % PB, s = sc / PB;
-            Ds[(size_t)sc * TE + el] = (pb + c < p.P) ? p.Dt[((size_t)s * p.P + pb + c) * p.ldA + e0 + el] : c2{0.0, 0.0};
+        for (int idx = tid; idx < nS * PB * TE; idx += kForceThreads) {
+            const int el = idx % TE, sc = idx / TE, c = sc % PB, s = sc / PB;
+            Ds[idx] = (pb + c < p.P && el < ne) ? p.Dt[((size_t)s * p.P + pb + c) * p.ldA + e0 + el] : c2{0.0, 0.0};
         }
         __syncthreads();
         for (long long jabs = jbeg + tid; jabs < jend; jabs += kForceThreads) {
@@ -476,15 +569,7 @@ __global__ void __launch_bounds__(kForceThreads) k_forces(const ForceParams p)
 #pragma unroll
                 for (int c = 0; c < PB; ++c) {
                     double ur = 0.0, ui = 0.0, vr = 0.0, vi = 0.0;
-                    const c2* D = Ds + ((size_t)base * PB + c) * TE + el;
-#pragma unroll
-                    for (int n = 0; n < NMAX; ++n) {
-                        if (n < cnt) {
-                            const c2 d = D[(size_t)n * PB * TE];
-                            ur += d.x * Rn[n]; ui += d.y * Rn[n];
-                            vr += d.x * dRn[n]; vi += d.y * dRn[n];
-                        }
-                    }
+                    column_dot<NMAX, PB * TE>(Ds + ((size_t)base * PB + c) * TE + el, cnt, Rn, dRn, ur, ui, vr, vi);
                     // z = u * ep ;  Re(v * ep)
                     const double zr = ur * epr - ui * epi, zi = ur * epi + ui * epr;
                     const double ve = vr * epr - vi * epi;

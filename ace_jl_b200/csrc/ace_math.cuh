@@ -28,7 +28,6 @@ struct AlpParams {
     int L;                  // highest l referenced by the model's one-particle basis
     double A[kMaxP], B[kMaxP];
     double diagc[kMaxL + 2];   // diagc[m] = sqrt(1 + 1/(2m)) (m >= 2), sqrt(1.5) (m = 1): P_m^m from P_{m-1}^{m-1}
-    double offc[kMaxL + 2];    // offc[m]  = sqrt(2m + 3): P_{m+1}^m from P_m^m
 };
 
 ACE_HD inline int index_p(int l, int m) { return m + (l * (l + 1)) / 2; }
@@ -157,6 +156,8 @@ ACE_HD inline Spher cart2spher(double x, double y, double z)
 // Walks the harmonics one m-column at a time, calling f(l, m, Pv, epr, epi) with
 //   Pv = P_l^m(cos th)  (src/polynomials/sphericalharmonics.jl:175-194, reorganised by column)
 //   ep = exp(i m phi) / sqrt(2)  (:385-393),  so that  Y_l^m = ep * Pv  and  Y_l^{-m} = (-1)^m conj(Y_l^m).
+// The coefficient tables hold A_{m+1}^m = sqrt(2m+3), B_{m+1}^m = 0 (:179, :191) so that one recurrence
+// serves every l > m and the callback is instantiated once.
 template <class F>
 ACE_HD inline void for_each_lm(const AlpParams& ap, const Spher& S, F&& f)
 {
@@ -168,21 +169,17 @@ ACE_HD inline void for_each_lm(const AlpParams& ap, const Spher& S, F&& f)
     for (int m = 0; m <= L; ++m) {
         if (m > 0) {
             dg = -ap.diagc[m] * S.sth * dg;   // :180, :192
-            double nr = epr * S.cphi - epi * S.sphi;
+            const double nr = epr * S.cphi - epi * S.sphi;
             epi = epr * S.sphi + epi * S.cphi;
             epr = nr;
         }
         double p2 = 0.0, p1 = dg;
-        f(m, m, p1, epr, epi);
-        if (m + 1 <= L) {
-            double p = ap.offc[m] * S.cth * dg;   // :179, :191
-            p2 = p1; p1 = p;
-            f(m + 1, m, p1, epr, epi);
-        }
-        for (int l = m + 2; l <= L; ++l) {
-            int ip = index_p(l, m);
-            double p = ap.A[ip] * (S.cth * p1 + ap.B[ip] * p2);   // :188-189
-            p2 = p1; p1 = p;
+        for (int l = m; l <= L; ++l) {
+            if (l > m) {
+                const int ip = index_p(l, m);
+                const double p = ap.A[ip] * (S.cth * p1 + ap.B[ip] * p2);   // :188-189
+                p2 = p1; p1 = p;
+            }
             f(l, m, p1, epr, epi);
         }
     }
@@ -207,28 +204,23 @@ ACE_HD inline void for_each_lm_ed(const AlpParams& ap, const Spher& S, F&& f)
             dgd = -ap.diagc[1] * (S.cth * dgt + S.sth * dgd);   // :229-230 (uses P_0^0, undivided)
             dgt = -ap.diagc[1] * dgt;
         } else if (m > 1) {
-            double nd = -ap.diagc[m] * (S.cth * dgt * S.sth + S.sth * dgd);   // :259-261
+            const double nd = -ap.diagc[m] * (S.cth * dgt * S.sth + S.sth * dgd);   // :259-261
             dgt = -ap.diagc[m] * S.sth * dgt;
             dgd = nd;
         }
         if (m > 0) {
-            double nr = epr * S.cphi - epi * S.sphi;
+            const double nr = epr * S.cphi - epi * S.sphi;
             epi = epr * S.sphi + epi * S.cphi;
             epr = nr;
         }
         double p2 = 0.0, d2 = 0.0, p1 = dgt, d1 = dgd;
-        f(m, m, p1, d1, epr, epi);
-        if (m + 1 <= L) {
-            double p = ap.offc[m] * S.cth * dgt;                        // :227, :255
-            double d = ap.offc[m] * (-sfac * dgt + S.cth * dgd);        // :228, :256-257
-            p2 = p1; d2 = d1; p1 = p; d1 = d;
-            f(m + 1, m, p1, d1, epr, epi);
-        }
-        for (int l = m + 2; l <= L; ++l) {
-            int ip = index_p(l, m);
-            double p = ap.A[ip] * (S.cth * p1 + ap.B[ip] * p2);                    // :236-238, :246-248
-            double d = ap.A[ip] * (-sfac * p1 + S.cth * d1 + ap.B[ip] * d2);       // :239-243, :249-253
-            p2 = p1; d2 = d1; p1 = p; d1 = d;
+        for (int l = m; l <= L; ++l) {
+            if (l > m) {
+                const int ip = index_p(l, m);
+                const double p = ap.A[ip] * (S.cth * p1 + ap.B[ip] * p2);                    // :236-238, :246-248, :255
+                const double d = ap.A[ip] * (-sfac * p1 + S.cth * d1 + ap.B[ip] * d2);       // :239-243, :249-253, :256
+                p2 = p1; d2 = d1; p1 = p; d1 = d;
+            }
             f(l, m, p1, d1, epr, epi);
         }
     }

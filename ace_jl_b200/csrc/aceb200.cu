@@ -7,6 +7,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <map>
 #include <mutex>
 #include <new>
 #include <string>
@@ -134,7 +136,7 @@ static void fill_params(aceb200_model* m, const aceb200_desc& d)
     ap.diagc[0] = 0.0;
     ap.diagc[1] = sqrt(1.5);                                   // :180
     for (int mm = 2; mm <= kMaxL + 1; ++mm) ap.diagc[mm] = sqrt(1.0 + 0.5 / mm);   // :192
-    for (int mm = 0; mm <= kMaxL + 1; ++mm) ap.offc[mm] = sqrt(2.0 * mm + 3.0);    // :179, :191
+    for (int mm = 0; mm + 1 <= ap.L; ++mm) { ap.A[index_p(mm + 1, mm)] = sqrt(2.0 * mm + 3.0); ap.B[index_p(mm + 1, mm)] = 0.0; }   // :179, :191
 }
 
 static void upload_stream(aceb200_model* m);
@@ -184,66 +186,149 @@ static void upload_weights(aceb200_model* m, const double* c)
     upload_stream(m);
 }
 
-// Flatten the adjoint lists into the record stream k_adjoint_stream consumes (see ace_kernels.cuh).
+// Flatten the adjoint lists into the record stream k_adjoint_stream consumes (layout: ace_kernels.cuh).
+//
+// Mirror folding.  With A_{n l -m} = (-1)^m conj(A_{n l m}) the AA function whose factors all have their m
+// negated equals (-1)^{sum m} conj(AA).  For real weights and a real output,
+//     c~_i Re(AA_i) + c~_i' Re(AA_i') = (c~_i + (-1)^{sum m} c~_i') Re(AA_i),
+// so only one function of each mirror pair is kept, with the folded weight.  This halves the stream; the
+// energy and its gradient are unchanged as functions of the positions (they differ from the unfolded
+// evaluation only in the order of floating-point additions).
 static void upload_stream(aceb200_model* m)
 {
     HostTables& T = m->T;
     m->stream_chunks = 0;
     if (T.P != 1 || m->cw || T.maxord < 2 || T.maxord > 4 || !T.symreal) return;
     const int NF = T.maxord <= 3 ? 2 : 3;
-    const uint16_t ONE = (uint16_t)(T.nS * 4);
-    std::vector<uint32_t> words;   // 4 per record
-    auto emit_block = [&](const uint16_t (*codes)[3], const double* w, int nleaf, unsigned flags, unsigned tcode, unsigned tidx) {
-        for (int k = 0; k < 4; ++k) {
-            uint16_t c0 = ONE, c1 = ONE, c2v = ONE;
-            double wk = 0.0;
-            if (k < nleaf) { c0 = codes[k][0]; c1 = codes[k][1]; c2v = codes[k][2]; wk = w[k]; }
-            unsigned ctl = k == 0 ? flags : (k == 1 ? tcode : (k == 2 ? tidx : 0u));
-            uint64_t wb; memcpy(&wb, &wk, 8);
-            words.push_back((uint32_t)c0 | ((uint32_t)c1 << 16));
-            words.push_back((uint32_t)c2v | (ctl << 16));
-            words.push_back((uint32_t)(wb & 0xffffffffu));
-            words.push_back((uint32_t)(wb >> 32));
+    const bool fold = !getenv("ACEB200_NO_MIRROR_FOLD");
+
+    // ---- effective (mirror-folded) coefficient of every AA function; non-canonical partners are dropped
+    std::vector<double> ceff(T.nAA);
+    std::vector<char> keep(T.nAA, 1);
+    for (int i = 0; i < T.nAA; ++i) ceff[i] = m->ctilde[i].real();
+    if (fold) {
+        std::map<std::tuple<int, int, int, int>, int> inv1p;
+        for (int a = 0; a < T.nA; ++a) inv1p[std::make_tuple(T.iA_q[a], T.iA_n[a], T.iA_l[a], T.iA_m[a])] = a;
+        std::vector<int> mirA(T.nA, -1);
+        for (int a = 0; a < T.nA; ++a) {
+            auto it = inv1p.find(std::make_tuple(T.iA_q[a], T.iA_n[a], T.iA_l[a], -T.iA_m[a]));
+            if (it != inv1p.end()) mirA[a] = it->second;
+        }
+        std::map<std::vector<int>, int> invAA;
+        auto keyof = [&](int i, bool mirror, bool& ok) {
+            std::vector<int> k;
+            ok = true;
+            for (int t = 0; t < T.orders[i]; ++t) {
+                int a = T.spec[(size_t)i * T.maxord + t];
+                if (mirror) { a = mirA[a]; if (a < 0) ok = false; }
+                k.push_back(a);
+            }
+            std::sort(k.begin(), k.end(), std::greater<int>());
+            return k;
+        };
+        bool ok;
+        for (int i = 0; i < T.nAA; ++i) invAA[keyof(i, false, ok)] = i;
+        for (int i = 0; i < T.nAA; ++i) {
+            if (!keep[i]) continue;
+            std::vector<int> k = keyof(i, true, ok);
+            if (!ok) continue;
+            auto it = invAA.find(k);
+            if (it == invAA.end() || it->second <= i) continue;     // no partner, self-mirror, or already handled
+            const int ip = it->second;
+            int summ = 0;
+            for (int t = 0; t < T.orders[i]; ++t) summ += T.iA_m[T.spec[(size_t)i * T.maxord + t]];
+            ceff[i] += ((summ & 1) ? -1.0 : 1.0) * m->ctilde[ip].real();
+            keep[ip] = 0;
+            ceff[ip] = 0.0;
+        }
+    }
+
+    const unsigned ONE = (unsigned)T.nS * 512u;
+    std::vector<uint32_t> words;   // 8 per record
+    auto put_f64 = [&](double v) { uint64_t b; memcpy(&b, &v, 8); words.push_back((uint32_t)(b & 0xffffffffu)); words.push_back((uint32_t)(b >> 32)); };
+    struct Leaf { unsigned off[3]; unsigned msk[3]; double wx, wy; };
+    auto make_leaf = [&](const uint16_t* codes, int nf, double w) {
+        Leaf L;
+        double sg = 1.0;
+        unsigned k1 = 0;
+        for (int f = 0; f < 3; ++f) {
+            if (f < nf) {
+                const unsigned c = codes[f];
+                const unsigned neg = c & 1u, odd = (c >> 1) & 1u;
+                if (neg && odd) sg = -sg;                 // (-1)^m
+                if (f == 0) k1 = neg;
+                L.off[f] = (c >> 2) * 512u;
+                L.msk[f] = (f > 0 && (neg ^ k1)) ? 0x80000000u : 0u;
+            } else { L.off[f] = ONE; L.msk[f] = 0u; }
+        }
+        L.wx = sg * w;
+        L.wy = k1 ? -sg * w : sg * w;                      // conj of the whole product when the first factor is conjugated
+        return L;
+    };
+    auto emit_block = [&](const std::vector<Leaf>& leaves, size_t i0, unsigned flags, int target, double invnu) {
+        unsigned toff = ONE, mx = 0u, my = 0u;
+        double w1 = 0.0;
+        if (target >= 0) {
+            const unsigned c = (unsigned)T.iA_code[target];
+            toff = (c >> 2) * 512u;
+            mx = (c & 2u) ? 0x80000000u : 0u;
+            my = ((c & 1u) && !(c & 2u)) ? 0x80000000u : 0u;
+            if (T.aa1_of_target[target] >= 0) w1 = ceff[T.aa1_of_target[target]];
+        }
+        words.push_back(flags); words.push_back(toff); words.push_back(mx); words.push_back(my);
+        put_f64(w1); put_f64(invnu);
+        for (int k = 0; k < kBlkLeaves; ++k) {
+            Leaf L;
+            if (i0 + k < leaves.size()) L = leaves[i0 + k];
+            else { L.off[0] = L.off[1] = L.off[2] = ONE; L.msk[0] = L.msk[1] = L.msk[2] = 0u; L.wx = L.wy = 0.0; }
+            words.push_back(L.off[0]); words.push_back(L.off[1]);
+            if (NF == 2) { words.push_back(L.msk[1]); words.push_back(0u); }
+            else { words.push_back(L.off[2] | L.msk[1]); words.push_back(L.msk[2]); }
+            put_f64(L.wx); put_f64(L.wy);
         }
     };
+    const std::vector<Leaf> none;
     for (int s = 0; s < T.nS; ++s) {
         int tg[2] = {T.slot_pos[s], T.slot_neg[s]};
-        int ntg = 0, last = -1;
-        for (int k = 0; k < 2; ++k) if (tg[k] >= 0) { ++ntg; last = k; }
-        if (ntg == 0) { emit_block(nullptr, nullptr, 0, kSlotEnd, ONE, 0); continue; }
+        int last = -1;
+        for (int k = 0; k < 2; ++k) if (tg[k] >= 0) last = k;
+        if (last < 0) { emit_block(none, 0, kSlotEnd, -1, 0.0); continue; }
         for (int k = 0; k < 2; ++k) {
             const int a = tg[k];
             if (a < 0) continue;
             unsigned tflags = kTgtEnd | (k == last ? kSlotEnd : 0u);
             if (T.iA_code[a] & 1) tflags |= kTgtNeg;
             if (T.iA_code[a] & 2) tflags |= kTgtOdd;
-            const unsigned tcode = (unsigned)T.iA_code[a];
+            // this target's kept leaves, per order
+            std::vector<std::vector<Leaf>> per(T.maxord + 1);
             int lastnu = 0;
-            for (int nu = 2; nu <= T.maxord; ++nu) if (T.trees[nu].ptr[a + 1] > T.trees[nu].ptr[a]) lastnu = nu;
-            if (lastnu == 0) { emit_block(nullptr, nullptr, 0, tflags | 2u, tcode, (unsigned)a); continue; }
             for (int nu = 2; nu <= T.maxord; ++nu) {
                 const Tree& tr = T.trees[nu];
-                const int i0 = tr.ptr[a], i1 = tr.ptr[a + 1];
-                for (int i = i0; i < i1; i += 4) {
-                    uint16_t codes[4][3];
-                    double w[4];
-                    const int n = std::min(4, i1 - i);
-                    for (int j = 0; j < n; ++j) {
-                        for (int f = 0; f < 3; ++f) codes[j][f] = (f < nu - 1) ? tr.codes[4 * (size_t)(i + j) + f] : ONE;
-                        w[j] = (m->ctilde[(size_t)tr.laa[i + j]] * (double)tr.lmult[i + j]).real();
-                    }
+                for (int i = tr.ptr[a]; i < tr.ptr[a + 1]; ++i) {
+                    if (!keep[tr.laa[i]]) continue;
+                    per[nu].push_back(make_leaf(&tr.codes[4 * (size_t)i], nu - 1, ceff[tr.laa[i]] * (double)tr.lmult[i]));
+                }
+                if (!per[nu].empty()) lastnu = nu;
+            }
+            if (lastnu == 0) { emit_block(none, 0, tflags, a, 0.0); continue; }
+            for (int nu = 2; nu <= T.maxord; ++nu) {
+                const std::vector<Leaf>& lv = per[nu];
+                for (size_t i = 0; i < lv.size(); i += kBlkLeaves) {
                     unsigned flags = (unsigned)nu;
-                    if (i + 4 >= i1) { flags |= kSegEnd; if (nu == lastnu) flags |= tflags; }
-                    emit_block(codes, w, n, flags, tcode, (unsigned)a);
+                    if (i + kBlkLeaves >= lv.size()) {
+                        flags |= kSegEnd | (tflags & (kTgtNeg | kTgtOdd));
+                        if (nu == lastnu) flags |= tflags;
+                    }
+                    emit_block(lv, i, flags, a, 1.0 / nu);
                 }
             }
         }
     }
-    // pad to whole chunks of 8 blocks with inert blocks
-    while ((words.size() / 16) % 8 != 0) emit_block(nullptr, nullptr, 0, 0u, ONE, 0);
-    m->d_stream.reserve(words.size() * sizeof(uint32_t));
+    // pad to whole chunks with inert blocks
+    while ((words.size() / 64) % kChunkBlocks != 0) emit_block(none, 0, 0u, -1, 0.0);
+    m->d_stream.reserve(words.size() * sizeof(uint32_t) + 4096);
     CU(cudaMemcpy(m->d_stream.p, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    m->stream_chunks = (int)(words.size() / 16 / 8);
+    m->stream_chunks = (int)(words.size() / 64 / kChunkBlocks);
     m->stream_nf = NF;
 }
 
@@ -257,6 +342,12 @@ static void upload_tables(aceb200_model* m)
     C.q = upload(m->pool, cq); C.l = upload(m->pool, cl); C.m = upload(m->pool, cm);
     C.cnt = upload(m->pool, cc); C.base = upload(m->pool, cb); C.ip = upload(m->pool, ci);
     C.colmap = upload(m->pool, T.colmap);
+    {
+        std::vector<int32_t> sn(T.nS), sip(T.nS), sqv(T.nS);
+        for (const Column& c : T.cols)
+            for (int n = 0; n < c.cnt; ++n) { sn[c.base + n] = n; sip[c.base + n] = c.ip; sqv[c.base + n] = c.q; }
+        C.slot_n = upload(m->pool, sn); C.slot_ip = upload(m->pool, sip); C.slot_q = upload(m->pool, sqv);
+    }
     m->d_slot_pos = upload(m->pool, T.slot_pos);
     m->d_slot_neg = upload(m->pool, T.slot_neg);
     m->d_code = upload(m->pool, T.iA_code);
@@ -386,12 +477,14 @@ static void launch_pool(aceb200_model* m, const BatchDev& B, long long ldA)
     PoolParams p;
     p.rp = m->rp; p.ap = m->ap; p.C = m->C; p.B = B;
     p.Ac = m->ws_Ac.as<c2>(); p.ldA = ldA; p.errflag = m->ws_err.as<int>();
-    p.colpass_size = std::min(T.ncols, kPoolThreads);
-    p.TE = std::max(1, kPoolThreads / p.colpass_size);
-    int nP = (T.Lused + 1) * (T.Lused + 2) / 2;
-    p.SK = (m->rp.N + 2 * nP) | 1;
-    size_t smem = (size_t)kPoolThreads * p.SK * sizeof(double) + kPoolThreads * sizeof(int);
-    dim3 grid((unsigned)((B.nenv + p.TE - 1) / p.TE), (unsigned)((T.ncols + p.colpass_size - 1) / p.colpass_size));
+    if (T.nS > kPoolThreads * kPoolItems)
+        throw ModelError(ACEB200_EUNSUPPORTED, "one-particle basis too large for k_pool (more than 512 canonical slots)");
+    p.TE = 8;
+    const int nP = (T.Lused + 1) * (T.Lused + 2) / 2;
+    p.SKR = m->rp.N | 1;
+    p.SKY = nP | 1;
+    const size_t smem = (size_t)kPoolThreads * (p.SKY * sizeof(c2) + p.SKR * sizeof(double) + sizeof(int));
+    dim3 grid((unsigned)((B.nenv + p.TE - 1) / p.TE));
     switch (m->NMAX) {
     case 4: launch_pool_t<4>(m, p, grid, smem); break;
     case 8: launch_pool_t<8>(m, p, grid, smem); break;
@@ -427,10 +520,10 @@ static void launch_adjoint(aceb200_model* m, long long nenv, long long ldA, bool
     if (m->stream_chunks > 0 && !getenv("ACEB200_NO_STREAM")) {
         StreamParams p;
         p.nS = T.nS; p.has_const = T.has_const; p.want_D = want_D ? 1 : 0; p.nchunks = m->stream_chunks;
-        p.stream = m->d_stream.as<uint4>(); p.w1 = m->d_w1.as<double>();
+        p.stream = m->d_stream.as<uint4>();
         p.w0 = T.has_const ? m->ctilde[0].real() : 0.0;
         p.Ac = m->ws_Ac.as<c2>(); p.ldA = ldA; p.Dt = m->ws_Dt.as<c2>(); p.E = m->ws_E.as<double>(); p.nenv = nenv;
-        const size_t smem = (size_t)(T.nS + 1) * 32 * sizeof(c2) + 3 * 32 * sizeof(uint4);
+        const size_t smem = (size_t)(T.nS + 1) * 32 * sizeof(c2) + 3 * 64 * sizeof(uint4);
         if (smem <= (size_t)m->smem_optin) {
             const long long ntiles = (nenv + 31) / 32;
             const int per_sm = std::max<int>(1, std::min<int>(32, (int)((size_t)m->smem_optin / (smem + 1024))));
@@ -482,16 +575,10 @@ static void launch_forces(aceb200_model* m, const BatchDev& B, long long nJ, lon
     p.rp = m->rp; p.ap = m->ap; p.C = m->C; p.B = B;
     p.Dt = m->ws_Dt.as<c2>(); p.ldA = ldA; p.P = m->T.P; p.nprop = m->T.nprop; p.ncomp = m->T.ncomp; p.G = G;
     const int pb = m->PB == 1 ? 1 : (m->PB == 3 ? 3 : 2);
-    // environments per CTA: enough neighbours for a few rounds of 128 threads, bounded by the staging buffer
-    const double Jav = std::max(1.0, (double)nJ / (double)B.nenv);
-    int TE = (int)std::min<double>(16.0, std::max(1.0, std::ceil(256.0 / Jav)));
-    const size_t per_env = (size_t)m->T.nS * pb * sizeof(c2);
-    while (TE > 1 && per_env * TE > 64 * 1024) --TE;
-    if (per_env * TE > (size_t)m->smem_optin)
+    const size_t smem = (size_t)m->T.nS * pb * kForceTE * sizeof(c2);
+    if (smem > (size_t)m->smem_optin)
         throw ModelError(ACEB200_EUNSUPPORTED, "one-particle basis too large for the shared-memory staging of k_forces");
-    p.TE = TE;
-    const size_t smem = per_env * TE;
-    const unsigned grid = (unsigned)((B.nenv + TE - 1) / TE);
+    const unsigned grid = (unsigned)((B.nenv + kForceTE - 1) / kForceTE);
 #define ACE_F(NM) { if (pb == 1) launch_forces_t<NM, 1>(m, p, grid, smem); else if (pb == 3) launch_forces_t<NM, 3>(m, p, grid, smem); else launch_forces_t<NM, 2>(m, p, grid, smem); }
     switch (m->NMAX) {
     case 4: ACE_F(4) break;
