@@ -369,9 +369,11 @@ constexpr unsigned kSegEnd = 8, kTgtEnd = 16, kTgtNeg = 32, kTgtOdd = 64, kSlotE
 constexpr int kBlkLeaves = 7;               // leaves per block
 constexpr int kChunkBlocks = 4;             // blocks per ring chunk (4 * 8 records * 32 B = 1 KiB)
 
+constexpr int kStreamWarps = 4;             // warps per CTA; each walks its own sub-stream over the same A tile
+
 struct StreamParams {
-    int nS, has_const, want_D, nchunks;
-    const uint4* stream;
+    int nS, has_const, want_D, nchunks;      // nchunks: length of EVERY sub-stream (padded to the longest)
+    const uint4* stream;                     // [kStreamWarps][nchunks][64]
     double w0;
     const c2* Ac; long long ldA;
     c2* Dt;                                  // [nS][ldA]
@@ -393,31 +395,36 @@ __device__ __forceinline__ double xor_hi(double v, unsigned mask)
 #endif
 }
 
+// One CTA = kStreamWarps warps sharing one shared-memory tile of A (32 environments, one per lane).  The
+// host splits the targets into kStreamWarps balanced sub-streams; warp w walks sub-stream w.  More warps
+// per byte of shared memory is what hides the FP64 and shared-memory latencies of the leaf products.
 template <int NF>
-__global__ void __launch_bounds__(32) k_adjoint_stream(const StreamParams p)
+__global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const StreamParams p)
 {
     ACE_DYN_SMEM(c2, As);                                       // [nS + 1][32]; slot nS holds 1
-    uint4* ring = reinterpret_cast<uint4*>(As + (size_t)(p.nS + 1) * 32);   // [3][64]
-    const int lane = threadIdx.x;
+    uint4* rings = reinterpret_cast<uint4*>(As + (size_t)(p.nS + 1) * 32);   // [kStreamWarps][3][64]
+    double* Epart = reinterpret_cast<double*>(rings + kStreamWarps * 3 * 64); // [kStreamWarps][32]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4* ring = rings + warp * 3 * 64;
+    const uint4* stream = p.stream + (size_t)warp * p.nchunks * 64;
     const unsigned char* Ab = reinterpret_cast<const unsigned char*>(As) + lane * 16;   // this lane's column
     const long long ntiles = (p.nenv + 31) / 32;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long e = tile * 32 + lane;
-        for (int s = 0; s < p.nS; ++s) As[s * 32 + lane] = p.Ac[(size_t)s * p.ldA + e];
-        As[p.nS * 32 + lane] = c2{1.0, 0.0};
-        ring[lane] = __ldg(p.stream + lane);
-        ring[32 + lane] = __ldg(p.stream + 32 + lane);
-        if (p.nchunks > 1) { ring[64 + lane] = __ldg(p.stream + 64 + lane); ring[96 + lane] = __ldg(p.stream + 96 + lane); }
-        __syncwarp();
-        double E = p.has_const ? p.w0 : 0.0;
+        for (int s = warp; s < p.nS; s += kStreamWarps) As[s * 32 + lane] = p.Ac[(size_t)s * p.ldA + e];
+        if (warp == 0) As[p.nS * 32 + lane] = c2{1.0, 0.0};
+        ring[lane] = __ldg(stream + lane);
+        ring[32 + lane] = __ldg(stream + 32 + lane);
+        if (p.nchunks > 1) { ring[64 + lane] = __ldg(stream + 64 + lane); ring[96 + lane] = __ldg(stream + 96 + lane); }
+        __syncthreads();
+        double E = (p.has_const && warp == 0) ? p.w0 : 0.0;
         c2 D = c2{0.0, 0.0}, S = c2{0.0, 0.0};
-        int slot = 0;
         for (int ch = 0; ch < p.nchunks; ++ch) {
             const bool havepre = ch + 2 < p.nchunks;
             uint4 pre0 = uint4{0u, 0u, 0u, 0u}, pre1 = pre0;
             if (havepre) {
-                pre0 = __ldg(p.stream + (size_t)(ch + 2) * 64 + lane);
-                pre1 = __ldg(p.stream + (size_t)(ch + 2) * 64 + 32 + lane);
+                pre0 = __ldg(stream + (size_t)(ch + 2) * 64 + lane);
+                pre1 = __ldg(stream + (size_t)(ch + 2) * 64 + 32 + lane);
             }
             const uint4* rb = ring + (ch % 3) * 64;
 #pragma unroll
@@ -472,17 +479,23 @@ __global__ void __launch_bounds__(32) k_adjoint_stream(const StreamParams p)
                         D.x += fx * w1;
                     }
                     if (flags & kSlotEnd) {
-                        if (p.want_D && e < p.nenv) p.Dt[(size_t)slot * p.ldA + e] = D;
+                        if (p.want_D && e < p.nenv) p.Dt[(size_t)(flags >> 8) * p.ldA + e] = D;
                         D = c2{0.0, 0.0};
-                        ++slot;
                     }
                 }
             }
             if (havepre) { ring[((ch + 2) % 3) * 64 + lane] = pre0; ring[((ch + 2) % 3) * 64 + 32 + lane] = pre1; }
             __syncwarp();
         }
-        if (e < p.nenv) p.E[e] = E;
-        __syncwarp();
+        Epart[warp * 32 + lane] = E;
+        __syncthreads();
+        if (warp == 0 && e < p.nenv) {
+            double Et = 0.0;
+#pragma unroll
+            for (int w = 0; w < kStreamWarps; ++w) Et += Epart[w * 32 + lane];
+            p.E[e] = Et;
+        }
+        __syncthreads();
     }
 }
 

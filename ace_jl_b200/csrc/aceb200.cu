@@ -68,6 +68,28 @@ static T* upload(std::vector<DevBuf>& pool, const std::vector<T>& v)
 // ----------------------------------------------------------------------------------------------
 // the model handle
 // ----------------------------------------------------------------------------------------------
+constexpr int kLanes = 3;
+
+struct Lane {
+    DevBuf ws_Ac, ws_Dt, ws_E, ws_G, ws_A, ws_AA, ws_dA, ws_dAA, ws_out;
+    DevBuf in_off, in_R, in_sp;
+    cudaStream_t stream = nullptr;       // the stream this lane currently launches on
+    cudaStream_t own_stream = nullptr;   // private non-blocking stream (host-batch pipeline)
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
+    bool busy = false;                   // has un-synchronised work with pending timing events
+    bool timed_ef = false;
+    void release()
+    {
+        DevBuf* bufs[] = {&ws_Ac, &ws_Dt, &ws_E, &ws_G, &ws_A, &ws_AA, &ws_dA, &ws_dAA, &ws_out, &in_off, &in_R, &in_sp};
+        for (DevBuf* b : bufs) b->release();
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (evA) cudaEventDestroy(evA);
+        if (evB) cudaEventDestroy(evB);
+        if (own_stream) cudaStreamDestroy(own_stream);
+    }
+};
+
 struct aceb200_model {
     int device = 0;
     HostTables T;
@@ -88,12 +110,14 @@ struct aceb200_model {
     DevBuf d_lw[kMaxOrdDev + 1];
     DevBuf d_stream;                // k_adjoint_stream records (single channel, real weights)
     int stream_chunks = 0, stream_nf = 0;   // 0 chunks: use the generic k_adjoint
-    // per-call workspace (guarded by mu)
+    // per-call workspace (guarded by mu).  Three lanes: device-resident batches use lane 0 on the caller's
+    // stream; host-resident batches are pipelined chunk by chunk over all lanes (H2D copy, kernels and D2H
+    // copy of consecutive chunks overlap on the lanes' private streams).
     std::mutex mu;
-    DevBuf ws_Ac, ws_Dt, ws_E, ws_G, ws_A, ws_AA, ws_dA, ws_dAA, ws_out, ws_err;
-    DevBuf in_off, in_R, in_sp;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
+    Lane lanes[kLanes];
+    Lane* cur = nullptr;
+    DevBuf ws_err;
+    cudaStream_t user_stream = nullptr;
     double last_ms = 0.0;
     double stage_ms[3] = {0.0, 0.0, 0.0};   // pool, adjoint, forces of the last energy(_forces) call
     long long launches = 0;
@@ -288,15 +312,19 @@ static void upload_stream(aceb200_model* m)
         }
     };
     const std::vector<Leaf> none;
+    // ---- one word list per slot, then an LPT split of the slots over the kStreamWarps sub-streams
+    std::vector<std::vector<uint32_t>> slotwords(T.nS);
     for (int s = 0; s < T.nS; ++s) {
+        words.clear();
+        const unsigned sbits = (unsigned)s << 8;
         int tg[2] = {T.slot_pos[s], T.slot_neg[s]};
         int last = -1;
         for (int k = 0; k < 2; ++k) if (tg[k] >= 0) last = k;
-        if (last < 0) { emit_block(none, 0, kSlotEnd, -1, 0.0); continue; }
+        if (last < 0) { emit_block(none, 0, kSlotEnd | sbits, -1, 0.0); slotwords[s] = words; continue; }
         for (int k = 0; k < 2; ++k) {
             const int a = tg[k];
             if (a < 0) continue;
-            unsigned tflags = kTgtEnd | (k == last ? kSlotEnd : 0u);
+            unsigned tflags = kTgtEnd | (k == last ? (kSlotEnd | sbits) : 0u);
             if (T.iA_code[a] & 1) tflags |= kTgtNeg;
             if (T.iA_code[a] & 2) tflags |= kTgtOdd;
             // this target's kept leaves, per order
@@ -323,12 +351,30 @@ static void upload_stream(aceb200_model* m)
                 }
             }
         }
+        slotwords[s] = words;
     }
-    // pad to whole chunks with inert blocks
-    while ((words.size() / 64) % kChunkBlocks != 0) emit_block(none, 0, 0u, -1, 0.0);
-    m->d_stream.reserve(words.size() * sizeof(uint32_t) + 4096);
-    CU(cudaMemcpy(m->d_stream.p, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    m->stream_chunks = (int)(words.size() / 64 / kChunkBlocks);
+    std::vector<int> order(T.nS);
+    for (int s = 0; s < T.nS; ++s) order[s] = s;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return slotwords[x].size() > slotwords[y].size(); });
+    std::vector<std::vector<uint32_t>> sub(kStreamWarps);
+    for (int s : order) {
+        int best = 0;
+        for (int w = 1; w < kStreamWarps; ++w) if (sub[w].size() < sub[best].size()) best = w;
+        sub[best].insert(sub[best].end(), slotwords[s].begin(), slotwords[s].end());
+    }
+    size_t longest = 0;
+    for (auto& v : sub) longest = std::max(longest, v.size());
+    const size_t chunk_words = (size_t)64 * kChunkBlocks;               // 8 words per record, 8 records per block
+    const size_t nchunks = std::max<size_t>(1, (longest + chunk_words - 1) / chunk_words);
+    std::vector<uint32_t> all;
+    for (auto& v : sub) {
+        words = v;
+        while (words.size() < nchunks * chunk_words) emit_block(none, 0, 0u, -1, 0.0);   // inert padding blocks
+        all.insert(all.end(), words.begin(), words.end());
+    }
+    m->d_stream.reserve(all.size() * sizeof(uint32_t) + 4096);
+    CU(cudaMemcpy(m->d_stream.p, all.data(), all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    m->stream_chunks = (int)nchunks;
     m->stream_nf = NF;
 }
 
@@ -414,12 +460,12 @@ static std::vector<long long> boundary_offsets(aceb200_model* m, const aceb200_b
     if (b->space == ACEB200_HOST) {
         for (long long i = 0; i <= nb; ++i) out[i] = b->offsets[std::min(i * step, (long long)b->nenv)];
     } else {
-        m->ws_out.reserve((nb + 1) * sizeof(long long));
+        m->cur->ws_out.reserve((nb + 1) * sizeof(long long));
         auto kfn = k_gather_offsets;
-        ACE_LAUNCH(kfn, dim3((unsigned)((nb + 1 + 127) / 128)), dim3(128), 0, m->stream, reinterpret_cast<const long long*>(b->offsets), (long long)b->nenv, step, nb, m->ws_out.as<long long>());
+        ACE_LAUNCH(kfn, dim3((unsigned)((nb + 1 + 127) / 128)), dim3(128), 0, m->cur->stream, reinterpret_cast<const long long*>(b->offsets), (long long)b->nenv, step, nb, m->cur->ws_out.as<long long>());
         CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(out.data(), m->ws_out.p, (nb + 1) * sizeof(long long), cudaMemcpyDeviceToHost, m->stream));
-        CU(cudaStreamSynchronize(m->stream));
+        CU(cudaMemcpyAsync(out.data(), m->cur->ws_out.p, (nb + 1) * sizeof(long long), cudaMemcpyDeviceToHost, m->cur->stream));
+        CU(cudaStreamSynchronize(m->cur->stream));
     }
     for (long long i = 0; i < nb; ++i)
         if (out[i + 1] < out[i]) throw ModelError(ACEB200_EDESC, "offsets must be non-decreasing");
@@ -437,17 +483,17 @@ static Staged stage_chunk(aceb200_model* m, const aceb200_batch* b, const Chunk&
         s.jbase = c.j0;
         return s;
     }
-    m->in_off.reserve((ne + 1) * sizeof(long long));
-    m->in_R.reserve(std::max<long long>(nj, 1) * 3 * sizeof(double));
-    CU(cudaMemcpyAsync(m->in_off.p, b->offsets + c.e0, (ne + 1) * sizeof(long long), cudaMemcpyHostToDevice, m->stream));
-    if (nj > 0) CU(cudaMemcpyAsync(m->in_R.p, b->R + 3 * c.j0, nj * 3 * sizeof(double), cudaMemcpyHostToDevice, m->stream));
-    s.off = m->in_off.as<long long>();
-    s.R = m->in_R.as<double>();
+    m->cur->in_off.reserve((ne + 1) * sizeof(long long));
+    m->cur->in_R.reserve(std::max<long long>(nj, 1) * 3 * sizeof(double));
+    CU(cudaMemcpyAsync(m->cur->in_off.p, b->offsets + c.e0, (ne + 1) * sizeof(long long), cudaMemcpyHostToDevice, m->cur->stream));
+    if (nj > 0) CU(cudaMemcpyAsync(m->cur->in_R.p, b->R + 3 * c.j0, nj * 3 * sizeof(double), cudaMemcpyHostToDevice, m->cur->stream));
+    s.off = m->cur->in_off.as<long long>();
+    s.R = m->cur->in_R.as<double>();
     s.species = nullptr;
     if (b->species) {
-        m->in_sp.reserve(std::max<long long>(nj, 1) * sizeof(int));
-        if (nj > 0) CU(cudaMemcpyAsync(m->in_sp.p, b->species + c.j0, nj * sizeof(int), cudaMemcpyHostToDevice, m->stream));
-        s.species = m->in_sp.as<int>();
+        m->cur->in_sp.reserve(std::max<long long>(nj, 1) * sizeof(int));
+        if (nj > 0) CU(cudaMemcpyAsync(m->cur->in_sp.p, b->species + c.j0, nj * sizeof(int), cudaMemcpyHostToDevice, m->cur->stream));
+        s.species = m->cur->in_sp.as<int>();
     }
     s.jbase = c.j0;
     return s;
@@ -468,7 +514,7 @@ static void launch_pool_t(aceb200_model* m, const PoolParams& p, dim3 grid, size
 {
     auto kfn = k_pool<NMAX>;
     CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ACE_LAUNCH(kfn, grid, dim3(kPoolThreads), smem, m->stream, p);
+    ACE_LAUNCH(kfn, grid, dim3(kPoolThreads), smem, m->cur->stream, p);
 }
 
 static void launch_pool(aceb200_model* m, const BatchDev& B, long long ldA)
@@ -476,7 +522,7 @@ static void launch_pool(aceb200_model* m, const BatchDev& B, long long ldA)
     HostTables& T = m->T;
     PoolParams p;
     p.rp = m->rp; p.ap = m->ap; p.C = m->C; p.B = B;
-    p.Ac = m->ws_Ac.as<c2>(); p.ldA = ldA; p.errflag = m->ws_err.as<int>();
+    p.Ac = m->cur->ws_Ac.as<c2>(); p.ldA = ldA; p.errflag = m->ws_err.as<int>();
     if (T.nS > kPoolThreads * kPoolItems)
         throw ModelError(ACEB200_EUNSUPPORTED, "one-particle basis too large for k_pool (more than 512 canonical slots)");
     p.TE = 8;
@@ -503,7 +549,7 @@ static void launch_adjoint_t(aceb200_model* m, const AdjointParams& p, int grid,
 {
     auto kfn = k_adjoint<PB, CW>;
     CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ACE_LAUNCH(kfn, dim3(grid), dim3(32), smem, m->stream, p);
+    ACE_LAUNCH(kfn, dim3(grid), dim3(32), smem, m->cur->stream, p);
 }
 
 template <int NF>
@@ -511,7 +557,7 @@ static void launch_stream_t(aceb200_model* m, const StreamParams& p, int grid, s
 {
     auto kfn = k_adjoint_stream<NF>;
     CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ACE_LAUNCH(kfn, dim3(grid), dim3(32), smem, m->stream, p);
+    ACE_LAUNCH(kfn, dim3(grid), dim3(32 * kStreamWarps), smem, m->cur->stream, p);
 }
 
 static void launch_adjoint(aceb200_model* m, long long nenv, long long ldA, bool want_D)
@@ -522,8 +568,8 @@ static void launch_adjoint(aceb200_model* m, long long nenv, long long ldA, bool
         p.nS = T.nS; p.has_const = T.has_const; p.want_D = want_D ? 1 : 0; p.nchunks = m->stream_chunks;
         p.stream = m->d_stream.as<uint4>();
         p.w0 = T.has_const ? m->ctilde[0].real() : 0.0;
-        p.Ac = m->ws_Ac.as<c2>(); p.ldA = ldA; p.Dt = m->ws_Dt.as<c2>(); p.E = m->ws_E.as<double>(); p.nenv = nenv;
-        const size_t smem = (size_t)(T.nS + 1) * 32 * sizeof(c2) + 3 * 64 * sizeof(uint4);
+        p.Ac = m->cur->ws_Ac.as<c2>(); p.ldA = ldA; p.Dt = m->cur->ws_Dt.as<c2>(); p.E = m->cur->ws_E.as<double>(); p.nenv = nenv;
+        const size_t smem = (size_t)(T.nS + 1) * 32 * sizeof(c2) + (size_t)kStreamWarps * (3 * 64 * sizeof(uint4) + 32 * sizeof(double));
         if (smem <= (size_t)m->smem_optin) {
             const long long ntiles = (nenv + 31) / 32;
             const int per_sm = std::max<int>(1, std::min<int>(32, (int)((size_t)m->smem_optin / (smem + 1024))));
@@ -540,7 +586,7 @@ static void launch_adjoint(aceb200_model* m, long long nenv, long long ldA, bool
     p.slot_pos = m->d_slot_pos; p.slot_neg = m->d_slot_neg; p.code = m->d_code;
     p.w1 = m->d_w1.as<double>(); p.w0 = m->d_w0.as<double>();
     for (int nu = 2; nu <= T.maxord; ++nu) p.list[nu] = m->list[nu];
-    p.Ac = m->ws_Ac.as<c2>(); p.ldA = ldA; p.Dt = m->ws_Dt.as<c2>(); p.E = m->ws_E.as<double>(); p.nenv = nenv;
+    p.Ac = m->cur->ws_Ac.as<c2>(); p.ldA = ldA; p.Dt = m->cur->ws_Dt.as<c2>(); p.E = m->cur->ws_E.as<double>(); p.nenv = nenv;
     size_t smem = (size_t)T.nS * 32 * sizeof(c2);
     if (smem > (size_t)m->smem_optin)
         throw ModelError(ACEB200_EUNSUPPORTED, "one-particle basis too large for the shared-memory tile of k_adjoint");
@@ -565,7 +611,7 @@ static void launch_forces_t(aceb200_model* m, const ForceParams& p, unsigned gri
 {
     auto kfn = k_forces<NMAX, PB>;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ACE_LAUNCH(kfn, dim3(grid), dim3(kForceThreads), smem, m->stream, p);
+    ACE_LAUNCH(kfn, dim3(grid), dim3(kForceThreads), smem, m->cur->stream, p);
 }
 
 static void launch_forces(aceb200_model* m, const BatchDev& B, long long nJ, long long ldA, double* G)
@@ -573,7 +619,7 @@ static void launch_forces(aceb200_model* m, const BatchDev& B, long long nJ, lon
     if (nJ == 0) return;
     ForceParams p;
     p.rp = m->rp; p.ap = m->ap; p.C = m->C; p.B = B;
-    p.Dt = m->ws_Dt.as<c2>(); p.ldA = ldA; p.P = m->T.P; p.nprop = m->T.nprop; p.ncomp = m->T.ncomp; p.G = G;
+    p.Dt = m->cur->ws_Dt.as<c2>(); p.ldA = ldA; p.P = m->T.P; p.nprop = m->T.nprop; p.ncomp = m->T.ncomp; p.G = G;
     const int pb = m->PB == 1 ? 1 : (m->PB == 3 ? 3 : 2);
     const size_t smem = (size_t)m->T.nS * pb * kForceTE * sizeof(c2);
     if (smem > (size_t)m->smem_optin)
@@ -598,7 +644,7 @@ template <int NMAX>
 static void launch_dA_t(aceb200_model* m, const dAParams& p)
 {
     auto kfn = k_dA<NMAX>;
-    ACE_LAUNCH(kfn, dim3((unsigned)((p.nJ + 127) / 128)), dim3(128), 0, m->stream, p);
+    ACE_LAUNCH(kfn, dim3((unsigned)((p.nJ + 127) / 128)), dim3(128), 0, m->cur->stream, p);
 }
 
 static void launch_dA(aceb200_model* m, const BatchDev& B, long long nJ, c2* dA)
@@ -625,8 +671,8 @@ static unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1)
 static void check_errflag(aceb200_model* m)
 {
     int flag = 0;
-    CU(cudaMemcpyAsync(&flag, m->ws_err.p, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
-    CU(cudaStreamSynchronize(m->stream));
+    CU(cudaMemcpyAsync(&flag, m->ws_err.p, sizeof(int), cudaMemcpyDeviceToHost, m->cur->stream));
+    CU(cudaStreamSynchronize(m->cur->stream));
     if (flag == 5) throw ModelError(ACEB200_EEMPTY, "Product1pBasis can only be evaluated with non-empty configurations");
     if (flag == 6) throw ModelError(ACEB200_ECATEGORY, "species code not found in the category list");
 }
@@ -635,7 +681,7 @@ static void check_errflag(aceb200_model* m)
 static void deliver(aceb200_model* m, const aceb200_batch* b, void* user, const void* dev, size_t bytes)
 {
     if (!user || bytes == 0 || user == dev) return;
-    CU(cudaMemcpyAsync(user, dev, bytes, b->space == ACEB200_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, m->stream));
+    CU(cudaMemcpyAsync(user, dev, bytes, b->space == ACEB200_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, m->cur->stream));
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -646,6 +692,24 @@ enum Want { W_A = 1, W_AA = 2, W_B = 4, W_dA = 8, W_dAA = 16, W_dB = 32, W_E = 6
 struct Outputs {
     double *A = nullptr, *AA = nullptr, *B = nullptr, *dA = nullptr, *dAA = nullptr, *dB = nullptr, *E = nullptr, *G = nullptr;
 };
+
+// Collect the timing events of a lane whose work has been synchronised.
+static void harvest(aceb200_model* m, Lane& L, double& kernel_ms, double (&stage_ms)[3])
+{
+    if (!L.busy) return;
+    CU(cudaStreamSynchronize(L.stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, L.ev0, L.ev1));
+    kernel_ms += ms;
+    if (L.timed_ef) {
+        float a = 0.f, bb = 0.f, cc = 0.f;
+        CU(cudaEventElapsedTime(&a, L.ev0, L.evA));
+        CU(cudaEventElapsedTime(&bb, L.evA, L.evB));
+        CU(cudaEventElapsedTime(&cc, L.evB, L.ev1));
+        stage_ms[0] += a; stage_ms[1] += bb; stage_ms[2] += cc;
+    }
+    L.busy = false;
+}
 
 static void run(aceb200_model* m, const aceb200_batch* b, int want, const Outputs& o)
 {
@@ -662,6 +726,12 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
     const bool need_AA = want & (W_AA | W_B | W_dAA | W_dB);
     const bool need_dA = want & (W_dA | W_dAA | W_dB);
     const bool need_dAA = want & (W_dAA | W_dB);
+    const bool host = b->space == ACEB200_HOST;
+
+    // lanes: a device-resident batch runs on the caller's stream; a host-resident batch is pipelined
+    const int nlanes = host ? kLanes : 1;
+    for (int l = 0; l < kLanes; ++l) { m->lanes[l].stream = host ? m->lanes[l].own_stream : m->user_stream; m->lanes[l].busy = false; }
+    m->cur = &m->lanes[0];
 
     // workspace bytes per environment (J-dependent parts use the batch average, bounded below)
     std::vector<long long> ends = boundary_offsets(m, b, b->nenv);   // total neighbour count
@@ -676,8 +746,14 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
     if (need_dA) per_env += (size_t)(Jav * nA * 48.0);
     if (need_dAA) per_env += (size_t)(Jav * nAA * 24.0 * ca);
     if (want & W_dB) per_env += (size_t)(Jav * nB * 24.0 * ncomp * cs);
-    if (b->space == ACEB200_HOST) per_env += (size_t)(Jav * 28.0) + 8;
+    if (host) per_env += (size_t)(Jav * 28.0) + 8;
     long long step = chunk_envs(b->nenv, per_env, (size_t)3 << 30);
+    if (host) {
+        // pipeline granularity: a few MiB of positions per chunk, at least ~6 chunks when the batch is large
+        long long pipe = std::max<long long>(4096, (long long)((32.0 * 1048576.0) / (24.0 * Jav)));
+        pipe = std::min<long long>(pipe, std::max<long long>(4096, (b->nenv + 5) / 6));
+        step = std::min<long long>(step, ((pipe + 31) / 32) * 32);
+    }
     if (const char* ov = getenv("ACEB200_CHUNK_ENVS")) {   // test hook: force the multi-chunk path on small batches
         long long v = atoll(ov);
         if (v >= 32) step = std::min<long long>(step, (v / 32) * 32);
@@ -685,106 +761,101 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
     std::vector<long long> bo = boundary_offsets(m, b, step);
 
     m->ws_err.reserve(sizeof(int));
-    CU(cudaMemsetAsync(m->ws_err.p, 0, sizeof(int), m->stream));
+    CU(cudaMemsetAsync(m->ws_err.p, 0, sizeof(int), m->lanes[0].stream));
+    CU(cudaStreamSynchronize(m->lanes[0].stream));
     double kernel_ms = 0.0;
     double stage_ms[3] = {0.0, 0.0, 0.0};
     const long long nchunks = (b->nenv + step - 1) / step;
     for (long long ic = 0; ic < nchunks; ++ic) {
+        Lane& L = m->lanes[ic % nlanes];
+        m->cur = &L;
+        harvest(m, L, kernel_ms, stage_ms);      // the lane's previous chunk must be done before its buffers are reused
         Chunk c;
         c.e0 = ic * step; c.e1 = std::min<long long>(b->nenv, c.e0 + step); c.j0 = bo[ic]; c.j1 = bo[ic + 1];
         const long long ne = c.e1 - c.e0, nj = c.j1 - c.j0;
         const long long ldA = ((ne + 31) / 32) * 32;
         Staged st = stage_chunk(m, b, c);
         BatchDev B = batch_dev(st, c);
-        m->ws_Ac.reserve((size_t)T.nS * ldA * sizeof(c2));
-        if (want & W_G) {
-            m->ws_Dt.reserve((size_t)T.nS * P * ldA * sizeof(c2));
-        }
-        CU(cudaEventRecord(m->ev0, m->stream));
+        L.ws_Ac.reserve((size_t)T.nS * ldA * sizeof(c2));
+        if (want & W_G) L.ws_Dt.reserve((size_t)T.nS * P * ldA * sizeof(c2));
+        CU(cudaEventRecord(L.ev0, L.stream));
         launch_pool(m, B, ldA);
+        L.timed_ef = (want & (W_E | W_G)) != 0;
 
         if (want & (W_E | W_G)) {
-            m->ws_E.reserve((size_t)ne * P * sizeof(double));
+            L.ws_E.reserve((size_t)ne * P * sizeof(double));
             double* Gdev = nullptr;
-            CU(cudaEventRecord(m->evA, m->stream));
+            CU(cudaEventRecord(L.evA, L.stream));
             launch_adjoint(m, ne, ldA, (want & W_G) != 0);
-            CU(cudaEventRecord(m->evB, m->stream));
+            CU(cudaEventRecord(L.evB, L.stream));
             if (want & W_G) {
                 const size_t gper = (size_t)P * 3;
-                if (b->space == ACEB200_DEVICE) Gdev = o.G + (size_t)c.j0 * gper;
-                else { m->ws_G.reserve(std::max<long long>(nj, 1) * gper * sizeof(double)); Gdev = m->ws_G.as<double>(); }
+                if (!host) Gdev = o.G + (size_t)c.j0 * gper;
+                else { L.ws_G.reserve(std::max<long long>(nj, 1) * gper * sizeof(double)); Gdev = L.ws_G.as<double>(); }
                 launch_forces(m, B, nj, ldA, Gdev);
             }
-            CU(cudaEventRecord(m->ev1, m->stream));
-            if (o.E) deliver(m, b, o.E + (size_t)c.e0 * P, m->ws_E.p, (size_t)ne * P * sizeof(double));
-            if ((want & W_G) && b->space == ACEB200_HOST)
+            CU(cudaEventRecord(L.ev1, L.stream));
+            if (o.E) deliver(m, b, o.E + (size_t)c.e0 * P, L.ws_E.p, (size_t)ne * P * sizeof(double));
+            if ((want & W_G) && host)
                 deliver(m, b, o.G + (size_t)c.j0 * P * 3, Gdev, (size_t)nj * P * 3 * sizeof(double));
         } else {
             // basis values / Jacobians
             c2* dA_dev = nullptr; double* AA_dev = nullptr; double* dAA_dev = nullptr;
-            m->ws_A.reserve((size_t)ne * nA * sizeof(c2));
+            L.ws_A.reserve((size_t)ne * nA * sizeof(c2));
             { auto kfn = k_expand_A;
-              ACE_LAUNCH(kfn, dim3(blocks_for(ne * nA, 256)), dim3(256), 0, m->stream, ne, nA, m->d_code, m->ws_Ac.as<c2>(), ldA, m->ws_A.as<c2>());
+              ACE_LAUNCH(kfn, dim3(blocks_for(ne * nA, 256)), dim3(256), 0, L.stream, ne, nA, m->d_code, L.ws_Ac.as<c2>(), ldA, L.ws_A.as<c2>());
               CU(cudaGetLastError()); m->launches++; }
             if (need_AA) {
-                m->ws_AA.reserve((size_t)ne * nAA * 8 * ca);
-                AA_dev = m->ws_AA.as<double>();
+                L.ws_AA.reserve((size_t)ne * nAA * 8 * ca);
+                AA_dev = L.ws_AA.as<double>();
                 auto kfn = k_AA;
-                ACE_LAUNCH(kfn, dim3(blocks_for(ne * nAA, 256)), dim3(256), 0, m->stream, ne, nA, nAA, std::max(1, T.maxord), m->d_orders, m->d_spec,
-                           (const c2*)m->ws_A.as<c2>(), T.pireal, AA_dev);
+                ACE_LAUNCH(kfn, dim3(blocks_for(ne * nAA, 256)), dim3(256), 0, L.stream, ne, nA, nAA, std::max(1, T.maxord), m->d_orders, m->d_spec,
+                           (const c2*)L.ws_A.as<c2>(), T.pireal, AA_dev);
                 CU(cudaGetLastError()); m->launches++;
             }
             double* B_dev = nullptr;
             if (want & W_B) {
-                m->ws_out.reserve((size_t)ne * nB * ncomp * 8 * cs);
-                B_dev = m->ws_out.as<double>();
+                L.ws_out.reserve((size_t)ne * nB * ncomp * 8 * cs);
+                B_dev = L.ws_out.as<double>();
                 auto kfn = k_B;
-                ACE_LAUNCH(kfn, dim3(blocks_for(ne * nB * ncomp, 256)), dim3(256), 0, m->stream, ne, nB, nAA, ncomp, m->d_csr_ptr, m->d_csr_col, m->d_csr_val,
+                ACE_LAUNCH(kfn, dim3(blocks_for(ne * nB * ncomp, 256)), dim3(256), 0, L.stream, ne, nB, nAA, ncomp, m->d_csr_ptr, m->d_csr_col, m->d_csr_val,
                            (const double*)AA_dev, T.pireal, T.symreal, B_dev);
                 CU(cudaGetLastError()); m->launches++;
             }
             if (need_dA) {
-                m->ws_dA.reserve(std::max<long long>(nj, 1) * nA * 3 * sizeof(c2));
-                dA_dev = m->ws_dA.as<c2>();
+                L.ws_dA.reserve(std::max<long long>(nj, 1) * nA * 3 * sizeof(c2));
+                dA_dev = L.ws_dA.as<c2>();
                 launch_dA(m, B, nj, dA_dev);
             }
             if (need_dAA) {
-                m->ws_dAA.reserve(std::max<long long>(nj, 1) * nAA * 24 * ca);
-                dAA_dev = m->ws_dAA.as<double>();
+                L.ws_dAA.reserve(std::max<long long>(nj, 1) * nAA * 24 * ca);
+                dAA_dev = L.ws_dAA.as<double>();
                 auto kfn = k_dAA;
-                ACE_LAUNCH(kfn, dim3(blocks_for(ne * nAA, 128)), dim3(128), 0, m->stream, ne, st.off, nA, nAA, std::max(1, T.maxord), m->d_orders, m->d_spec,
-                           (const c2*)m->ws_A.as<c2>(), (const c2*)dA_dev, T.pireal, dAA_dev);
+                ACE_LAUNCH(kfn, dim3(blocks_for(ne * nAA, 128)), dim3(128), 0, L.stream, ne, st.off, nA, nAA, std::max(1, T.maxord), m->d_orders, m->d_spec,
+                           (const c2*)L.ws_A.as<c2>(), (const c2*)dA_dev, T.pireal, dAA_dev);
                 CU(cudaGetLastError()); m->launches++;
             }
             double* dB_dev = nullptr;
             if ((want & W_dB) && nj > 0) {
-                m->ws_G.reserve((size_t)nj * nB * 24 * ncomp * cs);
-                dB_dev = m->ws_G.as<double>();
+                L.ws_G.reserve((size_t)nj * nB * 24 * ncomp * cs);
+                dB_dev = L.ws_G.as<double>();
                 auto kfn = k_dB;
-                ACE_LAUNCH(kfn, dim3(blocks_for(nj * nB * 3, 128)), dim3(128), 0, m->stream, nj, nB, nAA, ncomp, m->d_csr_ptr, m->d_csr_col, m->d_csr_val,
+                ACE_LAUNCH(kfn, dim3(blocks_for(nj * nB * 3, 128)), dim3(128), 0, L.stream, nj, nB, nAA, ncomp, m->d_csr_ptr, m->d_csr_col, m->d_csr_val,
                            (const double*)dAA_dev, T.pireal, T.symreal, dB_dev);
                 CU(cudaGetLastError()); m->launches++;
             }
-            CU(cudaEventRecord(m->ev1, m->stream));
-            if (o.A) deliver(m, b, o.A + (size_t)c.e0 * nA * 2, m->ws_A.p, (size_t)ne * nA * sizeof(c2));
+            CU(cudaEventRecord(L.ev1, L.stream));
+            if (o.A) deliver(m, b, o.A + (size_t)c.e0 * nA * 2, L.ws_A.p, (size_t)ne * nA * sizeof(c2));
             if (o.AA) deliver(m, b, o.AA + (size_t)c.e0 * nAA * ca, AA_dev, (size_t)ne * nAA * 8 * ca);
             if (o.B) deliver(m, b, o.B + (size_t)c.e0 * nB * ncomp * cs, B_dev, (size_t)ne * nB * ncomp * 8 * cs);
             if (o.dA) deliver(m, b, o.dA + (size_t)c.j0 * nA * 6, dA_dev, (size_t)nj * nA * 3 * sizeof(c2));
             if (o.dAA) deliver(m, b, o.dAA + (size_t)c.j0 * nAA * 3 * ca, dAA_dev, (size_t)nj * nAA * 24 * ca);
             if (o.dB) deliver(m, b, o.dB + (size_t)c.j0 * nB * 3 * ncomp * cs, dB_dev, (size_t)nj * nB * 24 * ncomp * cs);
         }
-        CU(cudaStreamSynchronize(m->stream));
-        float ms = 0.f;
-        CU(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
-        kernel_ms += ms;
-        if (want & (W_E | W_G)) {
-            float a = 0.f, bb = 0.f, cc = 0.f;
-            CU(cudaEventElapsedTime(&a, m->ev0, m->evA));
-            CU(cudaEventElapsedTime(&bb, m->evA, m->evB));
-            CU(cudaEventElapsedTime(&cc, m->evB, m->ev1));
-            stage_ms[0] += a; stage_ms[1] += bb; stage_ms[2] += cc;
-        }
+        L.busy = true;
     }
+    for (int l = 0; l < nlanes; ++l) harvest(m, m->lanes[l], kernel_ms, stage_ms);
+    m->cur = &m->lanes[0];
     m->last_ms = kernel_ms;
     for (int i = 0; i < 3; ++i) m->stage_ms[i] = stage_ms[i];
     check_errflag(m);
@@ -856,10 +927,11 @@ int aceb200_model_create(const aceb200_desc* desc, aceb200_model** out)
         m->Ppad = ((m->T.P + m->PB - 1) / m->PB) * m->PB;
         CU(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, m->device));
         CU(cudaDeviceGetAttribute(&m->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
-        CU(cudaEventCreate(&m->ev0));
-        CU(cudaEventCreate(&m->ev1));
-        CU(cudaEventCreate(&m->evA));
-        CU(cudaEventCreate(&m->evB));
+        for (Lane& L : m->lanes) {
+            CU(cudaEventCreate(&L.ev0)); CU(cudaEventCreate(&L.ev1)); CU(cudaEventCreate(&L.evA)); CU(cudaEventCreate(&L.evB));
+            CU(cudaStreamCreateWithFlags(&L.own_stream, cudaStreamNonBlocking));
+        }
+        m->cur = &m->lanes[0];
         upload_tables(m);
         upload_weights(m, desc->c);
         *out = m;
@@ -874,14 +946,9 @@ int aceb200_model_destroy(aceb200_model* m)
     if (!m) return ACEB200_OK;
     cudaSetDevice(m->device);
     for (DevBuf& b : m->pool) b.release();
-    DevBuf* bufs[] = {&m->d_w0, &m->d_w1, &m->ws_Ac, &m->ws_Dt, &m->ws_E, &m->ws_G, &m->ws_A, &m->ws_AA,
-                      &m->ws_dA, &m->ws_dAA, &m->ws_out, &m->ws_err, &m->in_off, &m->in_R, &m->in_sp, &m->d_stream};
-    for (DevBuf* b : bufs) b->release();
+    m->d_w0.release(); m->d_w1.release(); m->d_stream.release(); m->ws_err.release();
     for (int nu = 0; nu <= kMaxOrdDev; ++nu) m->d_lw[nu].release();
-    if (m->ev0) cudaEventDestroy(m->ev0);
-    if (m->ev1) cudaEventDestroy(m->ev1);
-    if (m->evA) cudaEventDestroy(m->evA);
-    if (m->evB) cudaEventDestroy(m->evB);
+    for (Lane& L : m->lanes) L.release();
     delete m;
     return ACEB200_OK;
 }
@@ -908,7 +975,7 @@ int aceb200_get_eff_coeffs(aceb200_model* m, double* ctilde)
 int aceb200_set_stream(aceb200_model* m, void* cuda_stream)
 {
     if (!m) return fail(ACEB200_EDESC, "null model");
-    m->stream = (cudaStream_t)cuda_stream;
+    m->user_stream = (cudaStream_t)cuda_stream;
     return ACEB200_OK;
 }
 

@@ -41,7 +41,7 @@ inline double __hiloint2double(int hi, int lo) { union { double d; unsigned long
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
 
 namespace emu {
-struct BlockCtx { pthread_barrier_t bar; unsigned char* smem; };
+struct BlockCtx { pthread_barrier_t bar; pthread_barrier_t wbar[32]; unsigned char* smem; };
 inline thread_local uint3 t_threadIdx, t_blockIdx;
 inline thread_local dim3 t_blockDim, t_gridDim;
 inline thread_local BlockCtx* t_ctx;
@@ -56,6 +56,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem, F fn)
     for (unsigned bx = 0; bx < grid.x; ++bx) {
         BlockCtx ctx;
         pthread_barrier_init(&ctx.bar, nullptr, nt);
+        for (unsigned w = 0; w * 32 < nt; ++w) pthread_barrier_init(&ctx.wbar[w], nullptr, std::min(32u, nt - w * 32));
         ctx.smem = (unsigned char*)aligned_alloc(128, ((smem + 127) / 128 + 1) * 128);
         std::vector<std::thread> th;
         th.reserve(nt);
@@ -71,6 +72,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem, F fn)
         for (auto& x : th) x.join();
         free(ctx.smem);
         pthread_barrier_destroy(&ctx.bar);
+        for (unsigned w = 0; w * 32 < nt; ++w) pthread_barrier_destroy(&ctx.wbar[w]);
     }
 }
 }  // namespace emu
@@ -80,7 +82,11 @@ inline void launch(dim3 grid, dim3 block, size_t smem, F fn)
 #define blockDim emu::t_blockDim
 #define gridDim emu::t_gridDim
 inline void __syncthreads() { pthread_barrier_wait(&emu::t_ctx->bar); }
-inline void __syncwarp() { if (emu::t_blockDim.x * emu::t_blockDim.y * emu::t_blockDim.z <= 32) __syncthreads(); }
+inline void __syncwarp()
+{
+    unsigned t = emu::t_threadIdx.x + emu::t_blockDim.x * (emu::t_threadIdx.y + emu::t_blockDim.y * emu::t_threadIdx.z);
+    pthread_barrier_wait(&emu::t_ctx->wbar[t / 32]);
+}
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline void sincos(double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }
 inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
@@ -110,6 +116,9 @@ inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyK
 inline cudaError_t cudaMemset(void* d, int v, size_t n) { if (n) memset(d, v, n); return 0; }
 inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { if (n) memset(d, v, n); return 0; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+enum { cudaStreamNonBlocking = 1 };
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return 0; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 inline cudaError_t cudaDeviceSynchronize() { return 0; }
 inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emuEvent{0}; return 0; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }
