@@ -137,7 +137,8 @@ int aceb200_model_destroy(aceb200_model *m);
 int aceb200_set_params(aceb200_model *m, const double *c, int64_t n);
 /* read back c~ = A2Bmap^T c as [nAA][nprop][ncomp] complex (ProductEvaluator.coeffs, src/evaluator.jl:11) */
 int aceb200_get_eff_coeffs(aceb200_model *m, double *ctilde);
-/* run subsequent calls on this CUDA stream (a cudaStream_t); NULL = the legacy default stream */
+/* run subsequent DEVICE-resident calls on this CUDA stream (a cudaStream_t); NULL = the legacy default
+ * stream.  HOST-resident batches are pipelined over three private streams and return when all copies are done. */
 int aceb200_set_stream(aceb200_model *m, void *cuda_stream);
 /* number of kernels this handle has launched so far (monotone counter, for audits) */
 int64_t aceb200_launch_count(const aceb200_model *m);
