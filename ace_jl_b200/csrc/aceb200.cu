@@ -464,6 +464,7 @@ static std::vector<long long> boundary_offsets(aceb200_model* m, const aceb200_b
         auto kfn = k_gather_offsets;
         ACE_LAUNCH(kfn, dim3((unsigned)((nb + 1 + 127) / 128)), dim3(128), 0, m->cur->stream, reinterpret_cast<const long long*>(b->offsets), (long long)b->nenv, step, nb, m->cur->ws_out.as<long long>());
         CU(cudaGetLastError());
+        m->launches++;
         CU(cudaMemcpyAsync(out.data(), m->cur->ws_out.p, (nb + 1) * sizeof(long long), cudaMemcpyDeviceToHost, m->cur->stream));
         CU(cudaStreamSynchronize(m->cur->stream));
     }

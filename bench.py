@@ -70,6 +70,13 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
@@ -81,23 +88,28 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([time.time()] + [x.strip() for x in line.split(",")])
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        smax = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = [r for r in self.rows if len(r) >= 10 and r[2].replace(".", "").isdigit()]
+        # samples taken inside the timed region (a sample reports the ~100 ms before it was printed)
+        inreg = [r for r in rows if self.t0 is not None and self.t0 <= r[0] <= (self.t1 or 1e30) + 0.12]
+        scope = "timed region"
+        if not inreg:   # region shorter than the sampling period: fall back to everything under load since warm-up
+            inreg, scope = rows, "warm-up + timed region"
+        sm = [float(r[2]) for r in inreg]
+        smax = [float(r[3]) for r in inreg]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+        for r in inreg:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[6:10]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "scope": scope}
 
 
 def cpu_reference_rate(basis, c, nenv_sample: int, repeats: int = 1):
@@ -156,7 +168,7 @@ def workload_config(nenv, ngpu):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--envs", type=int, default=1_000_000, help="environments per GPU")
     ap.add_argument("--cpu-envs", type=int, default=100_000, help="environments in the CPU baseline sample")
@@ -209,16 +221,17 @@ def main():
         torch.cuda.synchronize()
 
     fp64_peak = measure_fp64_tflops()
-    for _ in range(args.warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
     stage = {"pool": 0.0, "adjoint": 0.0, "forces": 0.0}
     l0 = h.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
         step()
@@ -226,6 +239,7 @@ def main():
             stage[k] += v
     e1.record()
     barrier()
+    sampler.mark_end()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
