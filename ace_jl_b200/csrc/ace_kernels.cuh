@@ -350,30 +350,32 @@ __global__ void __launch_bounds__(32) k_adjoint(const AdjointParams p)
 // ------------------------------------------------------------------------------------------------
 // k_adjoint_stream: the single-channel, real-weight fast path (energies + forces of an invariant model)
 // ------------------------------------------------------------------------------------------------
-// The adjoint lists of all targets and orders are flattened by the host into ONE stream of 32-byte
-// records, in exactly the order the kernel consumes them.  A block is one header record followed by 7
-// leaf records of the same (target, order):
-//   leaf   = { u32 off1, off2, off3|mask2, mask3|-, f64 wx, f64 wy }
-//            value = (wx Re, wy Im) of  A~[off1] * cj(A~[off2]) (* cj(A~[off3]))
-//            A~ are the canonical (m >= 0) slots; offN = slot * 512 is the byte offset of the slot row in
-//            shared memory; maskN = 0 or 0x80000000 conjugates the operand (XOR on the high word of Im);
-//            the conjugation of the first operand and all (-1)^m signs are folded into wx, wy by the host:
-//            prod_k (s_k cj^{k_k} A~_k) = (prod s_k) cj^{k_1}( A~_1 prod_{k>1} cj^{k_k xor k_1} A~_k ).
-//   header = { u32 flags|order, target off, target maskx, target masky, f64 w1, f64 1/order }
-// Because the stream is read strictly sequentially and identically by every lane, the warp fetches it
-// cooperatively -- 1 KiB (4 blocks) per pair of coalesced 128-bit loads, two chunks ahead of use -- into a
-// small shared-memory ring and reads records back as broadcasts.  Table latency is hidden, the 7 leaves of
-// a block are independent (ILP without needing many warps), and control (end of order segment / target /
-// slot) is a warp-uniform branch once per block.
+// The adjoint lists of all targets and orders are flattened by the host into streams in exactly the order
+// the kernel consumes them.  The kernel is bound by shared-memory -> register bandwidth (every byte a lane
+// receives costs the same, broadcast or not), so the per-leaf stream is as small as it can be:
+//   leaf block (4 leaves of one (target, order) segment) = { u32 code[4], f64 w[4] }            48 bytes
+//     code = slot1 | flipIm<<15 | slot2<<16 | conj2<<31      (NF = 3: a second word: slot3 | conj3<<31)
+//     value = (w Re, +-w Im) of  A~[slot1] * cj(A~[slot2]) (* cj(A~[slot3]))
+//     A~ are the canonical (m >= 0) slots; unused factors point at an extra slot that holds 1; the conjugation
+//     of the first operand and all (-1)^m signs are folded into w / flipIm by the host:
+//       prod_k (s_k cj^{k_k} A~_k) = (prod s_k) cj^{k_1}( A~_1 prod_{k>1} cj^{k_k xor k_1} A~_k ).
+//   ctl[block]  (u32, global)  0 for most blocks; else flags | order | slot<<8: end of segment / target / slot
+//   tinfo[k]    (32 B, global) consumed in order, one per non-zero ctl: target slot+masks, order-1 weight, 1/order
+// The leaf blocks are read strictly sequentially and identically by every lane, so the warp fetches them
+// cooperatively (three coalesced 128-bit loads per lane = 32 blocks, two chunks ahead of use) into a 2-slot
+// shared-memory ring and reads them back as broadcasts.  Table latency is hidden, the 4 leaves of a block are
+// independent, and control is a warp-uniform branch on ctl.
 constexpr unsigned kSegEnd = 8, kTgtEnd = 16, kTgtNeg = 32, kTgtOdd = 64, kSlotEnd = 128;
-constexpr int kBlkLeaves = 7;               // leaves per block
-constexpr int kChunkBlocks = 4;             // blocks per ring chunk (4 * 8 records * 32 B = 1 KiB)
-
-constexpr int kStreamWarps = 4;             // warps per CTA; each walks its own sub-stream over the same A tile
+constexpr int kBlkLeaves = 4;               // leaves per block
+constexpr int kChunkBlocks = 32;            // blocks per ring chunk
+constexpr int kStreamWarps = 8;             // warps per CTA; each walks its own sub-stream over the same A tile
 
 struct StreamParams {
     int nS, has_const, want_D, nchunks;      // nchunks: length of EVERY sub-stream (padded to the longest)
-    const uint4* stream;                     // [kStreamWarps][nchunks][64]
+    const uint4* stream;                     // [kStreamWarps][nchunks][kChunkBlocks * Q]   (Q = 3 or 4 uint4 per block)
+    const unsigned* ctl;                     // [kStreamWarps][nchunks * kChunkBlocks]
+    const uint4* tinfo;                      // [kStreamWarps][ntinfo][2]
+    int ntinfo;
     double w0;
     const c2* Ac; long long ldA;
     c2* Dt;                                  // [nS][ldA]
@@ -384,6 +386,19 @@ struct StreamParams {
 __device__ __forceinline__ c2 lds_c2(const unsigned char* base, unsigned off)
 {
     return *reinterpret_cast<const c2*>(base + off);
+}
+
+// a = *(c2*)(base + off) only if pred: a predicated LDS.128 costs no shared-memory bandwidth when it is off.
+// (Written as PTX because the compiler otherwise turns the uniform branch into load + select.)
+__device__ __forceinline__ void lds_c2_if(c2& a, const unsigned char* base, unsigned off, bool pred)
+{
+#ifdef __CUDA_ARCH__
+    const unsigned saddr = (unsigned)__cvta_generic_to_shared(base) + off;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p ld.shared.v2.f64 {%0, %1}, [%2];\n\t}"
+                 : "+d"(a.x), "+d"(a.y) : "r"(saddr), "r"((int)pred));
+#else
+    if (pred) a = *reinterpret_cast<const c2*>(base + off);
+#endif
 }
 
 __device__ __forceinline__ double xor_hi(double v, unsigned mask)
@@ -401,68 +416,86 @@ __device__ __forceinline__ double xor_hi(double v, unsigned mask)
 template <int NF>
 __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const StreamParams p)
 {
+    constexpr int Q = (NF == 2) ? 3 : 4;                        // uint4 per leaf block
+    constexpr int CH = kChunkBlocks * Q;                        // uint4 per chunk (= Q per lane)
     ACE_DYN_SMEM(c2, As);                                       // [nS + 1][32]; slot nS holds 1
-    uint4* rings = reinterpret_cast<uint4*>(As + (size_t)(p.nS + 1) * 32);   // [kStreamWarps][3][64]
-    double* Epart = reinterpret_cast<double*>(rings + kStreamWarps * 3 * 64); // [kStreamWarps][32]
+    uint4* rings = reinterpret_cast<uint4*>(As + (size_t)(p.nS + 1) * 32);   // [kStreamWarps][2][CH]
+    double* Epart = reinterpret_cast<double*>(rings + kStreamWarps * 2 * CH); // [kStreamWarps][32]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint4* ring = rings + warp * 3 * 64;
-    const uint4* stream = p.stream + (size_t)warp * p.nchunks * 64;
+    uint4* ring = rings + warp * 2 * CH;
+    const uint4* stream = p.stream + (size_t)warp * p.nchunks * CH;
+    const unsigned* ctl = p.ctl + (size_t)warp * p.nchunks * kChunkBlocks;
+    const uint4* tinfo = p.tinfo + (size_t)warp * p.ntinfo * 2;
     const unsigned char* Ab = reinterpret_cast<const unsigned char*>(As) + lane * 16;   // this lane's column
     const long long ntiles = (p.nenv + 31) / 32;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long e = tile * 32 + lane;
         for (int s = warp; s < p.nS; s += kStreamWarps) As[s * 32 + lane] = p.Ac[(size_t)s * p.ldA + e];
         if (warp == 0) As[p.nS * 32 + lane] = c2{1.0, 0.0};
-        ring[lane] = __ldg(stream + lane);
-        ring[32 + lane] = __ldg(stream + 32 + lane);
-        if (p.nchunks > 1) { ring[64 + lane] = __ldg(stream + 64 + lane); ring[96 + lane] = __ldg(stream + 96 + lane); }
+#pragma unroll
+        for (int k = 0; k < Q; ++k) ring[k * 32 + lane] = __ldg(stream + k * 32 + lane);
+        if (p.nchunks > 1) {
+#pragma unroll
+            for (int k = 0; k < Q; ++k) ring[CH + k * 32 + lane] = __ldg(stream + CH + k * 32 + lane);
+        }
         __syncthreads();
         double E = (p.has_const && warp == 0) ? p.w0 : 0.0;
         c2 D = c2{0.0, 0.0}, S = c2{0.0, 0.0};
+        int ti = 0;
         for (int ch = 0; ch < p.nchunks; ++ch) {
             const bool havepre = ch + 2 < p.nchunks;
-            uint4 pre0 = uint4{0u, 0u, 0u, 0u}, pre1 = pre0;
-            if (havepre) {
-                pre0 = __ldg(stream + (size_t)(ch + 2) * 64 + lane);
-                pre1 = __ldg(stream + (size_t)(ch + 2) * 64 + 32 + lane);
-            }
-            const uint4* rb = ring + (ch % 3) * 64;
+            uint4 pre[Q];
 #pragma unroll
+            for (int k = 0; k < Q; ++k) pre[k] = uint4{0u, 0u, 0u, 0u};
+            if (havepre) {
+#pragma unroll
+                for (int k = 0; k < Q; ++k) pre[k] = __ldg(stream + (size_t)(ch + 2) * CH + k * 32 + lane);
+            }
+            const uint4* rb = ring + (ch & 1) * CH;
+            const unsigned* cb = ctl + (size_t)ch * kChunkBlocks;
+#pragma unroll 4
             for (int b = 0; b < kChunkBlocks; ++b) {
-                const uint4* blk = rb + b * 16;
+                const uint4* blk = rb + b * Q;
+                const unsigned flags = __ldg(cb + b);
+                const uint4 cw = blk[0];
+                double w[4];
+                { const uint4 u = blk[Q - 2], v = blk[Q - 1];
+                  w[0] = __hiloint2double((int)u.y, (int)u.x); w[1] = __hiloint2double((int)u.w, (int)u.z);
+                  w[2] = __hiloint2double((int)v.y, (int)v.x); w[3] = __hiloint2double((int)v.w, (int)v.z); }
+                const unsigned code[4] = {cw.x, cw.y, cw.z, cw.w};
+                unsigned code3[4] = {0u, 0u, 0u, 0u};
+                if (NF == 3) { const uint4 c3 = blk[1]; code3[0] = c3.x; code3[1] = c3.y; code3[2] = c3.z; code3[3] = c3.w; }
                 c2 acc0 = c2{0.0, 0.0}, acc1 = c2{0.0, 0.0};
                 c2 a1 = c2{0.0, 0.0};
-                unsigned a1off = 0xffffffffu;
+                unsigned s1prev = 0xffffffffu;
 #pragma unroll
-                for (int k = 1; k <= kBlkLeaves; ++k) {
-                    const uint4 r0 = blk[2 * k], r1 = blk[2 * k + 1];
+                for (int k = 0; k < kBlkLeaves; ++k) {
+                    const unsigned c = code[k];
+                    const unsigned s1 = c & 0x3fffu;
                     // leaves are sorted by their first factor: re-fetch it only when it changes (warp-uniform)
-                    if (r0.x != a1off) { a1 = lds_c2(Ab, r0.x); a1off = r0.x; }
-                    c2 a2 = lds_c2(Ab, r0.y);
-                    c2 prod;
-                    if (NF == 2) {
-                        a2.y = xor_hi(a2.y, r0.z);
-                        prod = cmul(a1, a2);
-                    } else {
-                        c2 a3 = lds_c2(Ab, r0.z & 0x7fffffffu);
-                        a2.y = xor_hi(a2.y, r0.z & 0x80000000u);
-                        a3.y = xor_hi(a3.y, r0.w);
-                        prod = cmul(cmul(a1, a2), a3);
+                    lds_c2_if(a1, Ab, s1 << 9, s1 != s1prev);
+                    s1prev = s1;
+                    c2 a2 = lds_c2(Ab, ((c >> 16) & 0x3fffu) << 9);
+                    a2.y = xor_hi(a2.y, c & 0x80000000u);
+                    c2 prod = cmul(a1, a2);
+                    if (NF == 3) {
+                        c2 a3 = lds_c2(Ab, (code3[k] & 0x3fffu) << 9);
+                        a3.y = xor_hi(a3.y, code3[k] & 0x80000000u);
+                        prod = cmul(prod, a3);
                     }
-                    const double wx = __hiloint2double((int)r1.y, (int)r1.x), wy = __hiloint2double((int)r1.w, (int)r1.z);
-                    if (k & 1) { acc1.x += wx * prod.x; acc1.y += wy * prod.y; }
-                    else { acc0.x += wx * prod.x; acc0.y += wy * prod.y; }
+                    const double wy = xor_hi(w[k], (c & 0x8000u) << 16);
+                    if (k & 1) { acc1.x += w[k] * prod.x; acc1.y += wy * prod.y; }
+                    else { acc0.x += w[k] * prod.x; acc0.y += wy * prod.y; }
                 }
                 S.x += acc0.x + acc1.x;
                 S.y += acc0.y + acc1.y;
-                const uint4 h0 = blk[0];
-                const unsigned flags = h0.x;
-                if (flags & 0xf8u) {
-                    const uint4 h1 = blk[1];
-                    c2 Aa = lds_c2(Ab, h0.y);
-                    Aa.x = xor_hi(Aa.x, h0.z);
-                    Aa.y = xor_hi(Aa.y, h0.w);
-                    const double w1 = __hiloint2double((int)h1.y, (int)h1.x), scale = __hiloint2double((int)h1.w, (int)h1.z);
+                if (flags) {
+                    const uint4 t0 = __ldg(tinfo + 2 * ti), t1 = __ldg(tinfo + 2 * ti + 1);
+                    ++ti;
+                    c2 Aa = lds_c2(Ab, t0.x);
+                    Aa.x = xor_hi(Aa.x, t0.y);
+                    Aa.y = xor_hi(Aa.y, t0.z);
+                    const double w1 = __hiloint2double((int)t1.y, (int)t1.x), scale = __hiloint2double((int)t1.w, (int)t1.z);
                     const bool neg = (flags & kTgtNeg) != 0u, odd = (flags & kTgtOdd) != 0u;
                     // fold onto the m >= 0 slot: Re(D- grad(phi_-m)) = Re((-1)^m conj(D-) grad(phi_m))
                     const double fx = (neg && odd) ? -1.0 : 1.0, fy = neg ? (odd ? 1.0 : -1.0) : 1.0;
@@ -484,7 +517,11 @@ __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const Stre
                     }
                 }
             }
-            if (havepre) { ring[((ch + 2) % 3) * 64 + lane] = pre0; ring[((ch + 2) % 3) * 64 + 32 + lane] = pre1; }
+            __syncwarp();            // every lane is done reading this ring slot
+            if (havepre) {
+#pragma unroll
+                for (int k = 0; k < Q; ++k) ring[(ch & 1) * CH + k * 32 + lane] = pre[k];
+            }
             __syncwarp();
         }
         Epart[warp * 32 + lane] = E;

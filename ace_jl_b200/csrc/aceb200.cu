@@ -108,8 +108,8 @@ struct aceb200_model {
     ListDev list[kMaxOrdDev + 1];
     DevBuf d_w0, d_w1;
     DevBuf d_lw[kMaxOrdDev + 1];
-    DevBuf d_stream;                // k_adjoint_stream records (single channel, real weights)
-    int stream_chunks = 0, stream_nf = 0;   // 0 chunks: use the generic k_adjoint
+    DevBuf d_stream, d_ctl, d_tinfo;   // k_adjoint_stream tables (single channel, real weights)
+    int stream_chunks = 0, stream_nf = 0, stream_ntinfo = 0;   // 0 chunks: use the generic k_adjoint
     // per-call workspace (guarded by mu).  Three lanes: device-resident batches use lane 0 on the caller's
     // stream; host-resident batches are pipelined chunk by chunk over all lanes (H2D copy, kernels and D2H
     // copy of consecutive chunks overlap on the lanes' private streams).
@@ -267,67 +267,70 @@ static void upload_stream(aceb200_model* m)
         }
     }
 
-    const unsigned ONE = (unsigned)T.nS * 512u;
-    std::vector<uint32_t> words;   // 8 per record
-    auto put_f64 = [&](double v) { uint64_t b; memcpy(&b, &v, 8); words.push_back((uint32_t)(b & 0xffffffffu)); words.push_back((uint32_t)(b >> 32)); };
-    struct Leaf { unsigned off[3]; unsigned msk[3]; double wx, wy; };
+    const unsigned ONE = (unsigned)T.nS;                 // slot index of the constant 1
+    if (T.nS + 1 >= (1 << 14)) return;                   // 14-bit slot fields
+    const int Q = (NF == 2) ? 3 : 4;                     // uint4 per leaf block
+    struct Leaf { unsigned code, code3; double w; };
     auto make_leaf = [&](const uint16_t* codes, int nf, double w) {
-        Leaf L;
+        unsigned slot[3] = {ONE, ONE, ONE}, cj[3] = {0u, 0u, 0u};
         double sg = 1.0;
         unsigned k1 = 0;
-        for (int f = 0; f < 3; ++f) {
-            if (f < nf) {
-                const unsigned c = codes[f];
-                const unsigned neg = c & 1u, odd = (c >> 1) & 1u;
-                if (neg && odd) sg = -sg;                 // (-1)^m
-                if (f == 0) k1 = neg;
-                L.off[f] = (c >> 2) * 512u;
-                L.msk[f] = (f > 0 && (neg ^ k1)) ? 0x80000000u : 0u;
-            } else { L.off[f] = ONE; L.msk[f] = 0u; }
+        for (int f = 0; f < nf; ++f) {
+            const unsigned c = codes[f];
+            const unsigned neg = c & 1u, odd = (c >> 1) & 1u;
+            if (neg && odd) sg = -sg;                     // (-1)^m
+            if (f == 0) k1 = neg;
+            slot[f] = c >> 2;
+            cj[f] = (f > 0 && (neg ^ k1)) ? 1u : 0u;
         }
-        L.wx = sg * w;
-        L.wy = k1 ? -sg * w : sg * w;                      // conj of the whole product when the first factor is conjugated
+        Leaf L;
+        L.code = slot[0] | (k1 << 15) | (slot[1] << 16) | (cj[1] << 31);   // flipIm = conj of the whole product
+        L.code3 = slot[2] | (cj[2] << 31);
+        L.w = sg * w;
         return L;
     };
-    auto emit_block = [&](const std::vector<Leaf>& leaves, size_t i0, unsigned flags, int target, double invnu) {
-        unsigned toff = ONE, mx = 0u, my = 0u;
-        double w1 = 0.0;
-        if (target >= 0) {
-            const unsigned c = (unsigned)T.iA_code[target];
-            toff = (c >> 2) * 512u;
-            mx = (c & 2u) ? 0x80000000u : 0u;
-            my = ((c & 1u) && !(c & 2u)) ? 0x80000000u : 0u;
-            if (T.aa1_of_target[target] >= 0) w1 = ceff[T.aa1_of_target[target]];
-        }
-        words.push_back(flags); words.push_back(toff); words.push_back(mx); words.push_back(my);
-        put_f64(w1); put_f64(invnu);
+    struct Sub { std::vector<uint32_t> blocks, ctl, tinfo; };
+    auto put_f64 = [](std::vector<uint32_t>& v, double x) { uint64_t b; memcpy(&b, &x, 8); v.push_back((uint32_t)(b & 0xffffffffu)); v.push_back((uint32_t)(b >> 32)); };
+    auto emit_block = [&](Sub& S, const std::vector<Leaf>& leaves, size_t i0, unsigned flags, int target, double invnu) {
+        Leaf L[kBlkLeaves];
         for (int k = 0; k < kBlkLeaves; ++k) {
-            Leaf L;
-            if (i0 + k < leaves.size()) L = leaves[i0 + k];
-            else { L.off[0] = L.off[1] = L.off[2] = ONE; L.msk[0] = L.msk[1] = L.msk[2] = 0u; L.wx = L.wy = 0.0; }
-            words.push_back(L.off[0]); words.push_back(L.off[1]);
-            if (NF == 2) { words.push_back(L.msk[1]); words.push_back(0u); }
-            else { words.push_back(L.off[2] | L.msk[1]); words.push_back(L.msk[2]); }
-            put_f64(L.wx); put_f64(L.wy);
+            if (i0 + k < leaves.size()) L[k] = leaves[i0 + k];
+            else { L[k].code = ONE | (ONE << 16); L[k].code3 = ONE; L[k].w = 0.0; }
+        }
+        for (int k = 0; k < kBlkLeaves; ++k) S.blocks.push_back(L[k].code);
+        if (NF == 3) for (int k = 0; k < kBlkLeaves; ++k) S.blocks.push_back(L[k].code3);
+        for (int k = 0; k < kBlkLeaves; ++k) put_f64(S.blocks, L[k].w);
+        S.ctl.push_back(flags);
+        if (flags) {
+            unsigned toff = ONE * 512u, mx = 0u, my = 0u;
+            double w1 = 0.0;
+            if (target >= 0) {
+                const unsigned c = (unsigned)T.iA_code[target];
+                toff = (c >> 2) * 512u;
+                mx = (c & 2u) ? 0x80000000u : 0u;
+                my = ((c & 1u) && !(c & 2u)) ? 0x80000000u : 0u;
+                if (T.aa1_of_target[target] >= 0) w1 = ceff[T.aa1_of_target[target]];
+            }
+            S.tinfo.push_back(toff); S.tinfo.push_back(mx); S.tinfo.push_back(my); S.tinfo.push_back(0u);
+            put_f64(S.tinfo, w1); put_f64(S.tinfo, invnu);
         }
     };
     const std::vector<Leaf> none;
-    // ---- one word list per slot, then an LPT split of the slots over the kStreamWarps sub-streams
-    std::vector<std::vector<uint32_t>> slotwords(T.nS);
+    // ---- one block list per slot, then an LPT split of the slots over the kStreamWarps sub-streams
+    std::vector<Sub> perslot(T.nS);
     for (int s = 0; s < T.nS; ++s) {
-        words.clear();
+        Sub& S = perslot[s];
         const unsigned sbits = (unsigned)s << 8;
         int tg[2] = {T.slot_pos[s], T.slot_neg[s]};
         int last = -1;
         for (int k = 0; k < 2; ++k) if (tg[k] >= 0) last = k;
-        if (last < 0) { emit_block(none, 0, kSlotEnd | sbits, -1, 0.0); slotwords[s] = words; continue; }
+        if (last < 0) { emit_block(S, none, 0, kSlotEnd | sbits, -1, 0.0); continue; }
         for (int k = 0; k < 2; ++k) {
             const int a = tg[k];
             if (a < 0) continue;
             unsigned tflags = kTgtEnd | (k == last ? (kSlotEnd | sbits) : 0u);
             if (T.iA_code[a] & 1) tflags |= kTgtNeg;
             if (T.iA_code[a] & 2) tflags |= kTgtOdd;
-            // this target's kept leaves, per order
             std::vector<std::vector<Leaf>> per(T.maxord + 1);
             int lastnu = 0;
             for (int nu = 2; nu <= T.maxord; ++nu) {
@@ -338,44 +341,59 @@ static void upload_stream(aceb200_model* m)
                 }
                 if (!per[nu].empty()) lastnu = nu;
             }
-            if (lastnu == 0) { emit_block(none, 0, tflags, a, 0.0); continue; }
+            if (lastnu == 0) { emit_block(S, none, 0, tflags, a, 0.0); continue; }
             for (int nu = 2; nu <= T.maxord; ++nu) {
                 const std::vector<Leaf>& lv = per[nu];
                 for (size_t i = 0; i < lv.size(); i += kBlkLeaves) {
-                    unsigned flags = (unsigned)nu;
+                    unsigned flags = 0u;
                     if (i + kBlkLeaves >= lv.size()) {
-                        flags |= kSegEnd | (tflags & (kTgtNeg | kTgtOdd));
+                        flags = (unsigned)nu | kSegEnd | (tflags & (kTgtNeg | kTgtOdd));
                         if (nu == lastnu) flags |= tflags;
                     }
-                    emit_block(lv, i, flags, a, 1.0 / nu);
+                    emit_block(S, lv, i, flags, a, 1.0 / nu);
                 }
             }
         }
-        slotwords[s] = words;
     }
     std::vector<int> order(T.nS);
     for (int s = 0; s < T.nS; ++s) order[s] = s;
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return slotwords[x].size() > slotwords[y].size(); });
-    std::vector<std::vector<uint32_t>> sub(kStreamWarps);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return perslot[x].ctl.size() > perslot[y].ctl.size(); });
+    std::vector<Sub> sub(kStreamWarps);
     for (int s : order) {
         int best = 0;
-        for (int w = 1; w < kStreamWarps; ++w) if (sub[w].size() < sub[best].size()) best = w;
-        sub[best].insert(sub[best].end(), slotwords[s].begin(), slotwords[s].end());
+        for (int w = 1; w < kStreamWarps; ++w) if (sub[w].ctl.size() < sub[best].ctl.size()) best = w;
+        Sub& d = sub[best];
+        d.blocks.insert(d.blocks.end(), perslot[s].blocks.begin(), perslot[s].blocks.end());
+        d.ctl.insert(d.ctl.end(), perslot[s].ctl.begin(), perslot[s].ctl.end());
+        d.tinfo.insert(d.tinfo.end(), perslot[s].tinfo.begin(), perslot[s].tinfo.end());
     }
-    size_t longest = 0;
-    for (auto& v : sub) longest = std::max(longest, v.size());
-    const size_t chunk_words = (size_t)64 * kChunkBlocks;               // 8 words per record, 8 records per block
-    const size_t nchunks = std::max<size_t>(1, (longest + chunk_words - 1) / chunk_words);
-    std::vector<uint32_t> all;
+    size_t longest = 1, ntinfo = 1;
+    for (auto& v : sub) { longest = std::max(longest, v.ctl.size()); ntinfo = std::max(ntinfo, v.tinfo.size() / 8); }
+    const size_t nchunks = (longest + kChunkBlocks - 1) / kChunkBlocks;
+    std::vector<uint32_t> allb, allc, allt;
     for (auto& v : sub) {
-        words = v;
-        while (words.size() < nchunks * chunk_words) emit_block(none, 0, 0u, -1, 0.0);   // inert padding blocks
-        all.insert(all.end(), words.begin(), words.end());
+        while (v.ctl.size() < nchunks * kChunkBlocks) emit_block(v, none, 0, 0u, -1, 0.0);   // inert padding blocks
+        v.tinfo.resize(ntinfo * 8, 0u);
+        allb.insert(allb.end(), v.blocks.begin(), v.blocks.end());
+        allc.insert(allc.end(), v.ctl.begin(), v.ctl.end());
+        allt.insert(allt.end(), v.tinfo.begin(), v.tinfo.end());
     }
-    m->d_stream.reserve(all.size() * sizeof(uint32_t) + 4096);
-    CU(cudaMemcpy(m->d_stream.p, all.data(), all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    (void)Q;
+    m->d_stream.reserve(allb.size() * 4 + 4096);
+    m->d_ctl.reserve(allc.size() * 4 + 256);
+    m->d_tinfo.reserve(allt.size() * 4 + 256);
+    CU(cudaMemcpy(m->d_stream.p, allb.data(), allb.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(m->d_ctl.p, allc.data(), allc.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(m->d_tinfo.p, allt.data(), allt.size() * 4, cudaMemcpyHostToDevice));
     m->stream_chunks = (int)nchunks;
+    m->stream_ntinfo = (int)ntinfo;
     m->stream_nf = NF;
+    if (getenv("ACEB200_VERBOSE")) {
+        size_t kept = 0, total = 0;
+        for (int i = 0; i < T.nAA; ++i) { total += T.orders[i] >= 2; kept += (T.orders[i] >= 2 && keep[i]); }
+        fprintf(stderr, "[aceb200] stream: %d sub-streams x %zu chunks of %d blocks (%d leaves per block), AA functions of order >= 2 kept %zu of %zu\n",
+                kStreamWarps, nchunks, kChunkBlocks, kBlkLeaves, kept, total);
+    }
 }
 
 static void upload_tables(aceb200_model* m)
@@ -567,10 +585,10 @@ static void launch_adjoint(aceb200_model* m, long long nenv, long long ldA, bool
     if (m->stream_chunks > 0 && !getenv("ACEB200_NO_STREAM")) {
         StreamParams p;
         p.nS = T.nS; p.has_const = T.has_const; p.want_D = want_D ? 1 : 0; p.nchunks = m->stream_chunks;
-        p.stream = m->d_stream.as<uint4>();
+        p.stream = m->d_stream.as<uint4>(); p.ctl = m->d_ctl.as<unsigned>(); p.tinfo = m->d_tinfo.as<uint4>(); p.ntinfo = m->stream_ntinfo;
         p.w0 = T.has_const ? m->ctilde[0].real() : 0.0;
         p.Ac = m->cur->ws_Ac.as<c2>(); p.ldA = ldA; p.Dt = m->cur->ws_Dt.as<c2>(); p.E = m->cur->ws_E.as<double>(); p.nenv = nenv;
-        const size_t smem = (size_t)(T.nS + 1) * 32 * sizeof(c2) + (size_t)kStreamWarps * (3 * 64 * sizeof(uint4) + 32 * sizeof(double));
+        const size_t smem = (size_t)(T.nS + 1) * 32 * sizeof(c2) + (size_t)kStreamWarps * (2 * kChunkBlocks * (m->stream_nf == 2 ? 3 : 4) * sizeof(uint4) + 32 * sizeof(double));
         if (smem <= (size_t)m->smem_optin) {
             const long long ntiles = (nenv + 31) / 32;
             const int per_sm = std::max<int>(1, std::min<int>(32, (int)((size_t)m->smem_optin / (smem + 1024))));
@@ -748,7 +766,7 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
     if (need_dAA) per_env += (size_t)(Jav * nAA * 24.0 * ca);
     if (want & W_dB) per_env += (size_t)(Jav * nB * 24.0 * ncomp * cs);
     if (host) per_env += (size_t)(Jav * 28.0) + 8;
-    long long step = chunk_envs(b->nenv, per_env, (size_t)3 << 30);
+    long long step = chunk_envs(b->nenv, per_env, (size_t)8 << 30);
     if (host) {
         // pipeline granularity: a few MiB of positions per chunk, at least ~6 chunks when the batch is large
         long long pipe = std::max<long long>(4096, (long long)((32.0 * 1048576.0) / (24.0 * Jav)));
@@ -947,7 +965,7 @@ int aceb200_model_destroy(aceb200_model* m)
     if (!m) return ACEB200_OK;
     cudaSetDevice(m->device);
     for (DevBuf& b : m->pool) b.release();
-    m->d_w0.release(); m->d_w1.release(); m->d_stream.release(); m->ws_err.release();
+    m->d_w0.release(); m->d_w1.release(); m->d_stream.release(); m->d_ctl.release(); m->d_tinfo.release(); m->ws_err.release();
     for (int nu = 0; nu <= kMaxOrdDev; ++nu) m->d_lw[nu].release();
     for (Lane& L : m->lanes) L.release();
     delete m;

@@ -118,6 +118,7 @@ def cpu_reference_rate(basis, c, nenv_sample: int, repeats: int = 1):
     from ace_jl_b200.descriptor import basis_descriptor
     from ace_jl_b200.utils import philox, rand_envs
     o = orc.Oracle(basis_descriptor(basis, c.reshape(-1, 1)))
+    o.set_threads(len(os.sched_getaffinity(0)))   # all host cores (torchrun exports OMP_NUM_THREADS=1)
     R, off, _ = rand_envs(philox(SEED + 7), basis.pibasis.basis1p.component(0), nenv_sample, J)
     o.energy_forces(R[: J * 64], off[:65])  # warm-up (thread pool, page faults)
     best = float("inf")

@@ -810,6 +810,15 @@ int oracle_naive_energy_forces(const aceb200_desc *d, const aceb200_batch *b, co
     OMP_ENV_LOOP_END
 }
 
+void oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP

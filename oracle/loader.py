@@ -42,7 +42,7 @@ class Oracle:
             build()
         self.lib = C.CDLL(lib_path())
         if threads is not None:
-            os.environ["OMP_NUM_THREADS"] = str(threads)
+            self.lib.oracle_set_threads(int(threads))
         self.lib.oracle_transform.restype = C.c_double
         self.lib.oracle_transform.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_double]
         self.lib.oracle_transform_d.restype = C.c_double
@@ -69,6 +69,10 @@ class Oracle:
 
     def num_threads(self) -> int:
         return int(self.lib.oracle_num_threads())
+
+    def set_threads(self, n: int):
+        """Explicit thread count (torchrun exports OMP_NUM_THREADS=1, which would hide the host's cores)."""
+        self.lib.oracle_set_threads(int(n))
 
     # ---- components --------------------------------------------------------------------
     def transform(self, r):
