@@ -85,10 +85,11 @@ struct BatchDev {
 // ------------------------------------------------------------------------------------------------
 // A CTA owns TE consecutive environments and works through them in sub-tiles of at most 128 neighbours:
 // as many WHOLE environments as fit (or a 128-neighbour piece of one that does not).
-//   phase a  one thread per neighbour: R_n -> SR[row][n], Y_l^m (m >= 0) -> SY[row][ip]   (registers -> smem)
+//   phase a  one thread per neighbour: R_n -> SR[n][row], Y_l^m (m >= 0) -> SY[ip][row]   (registers -> smem)
 //   phase b  one thread per (environment, slot) item, flat over the sub-tile: the reduction over the
 //            environment's neighbours is a serial loop over its staged rows -- no atomics, deterministic.
-// Row strides are odd (in 8- resp. 16-byte units) so that both phases are bank-conflict free.
+// Staging is [function][row] with a row pitch of 129: phase a writes and phase b reads are both
+// bank-conflict free, and consecutive neighbours are adjacent so the unrolled reduction uses immediate offsets.
 struct PoolParams {
     RadialParams rp;
     AlpParams ap;
@@ -97,69 +98,70 @@ struct PoolParams {
     c2* Ac;                 // [nS][ldA]
     long long ldA;
     int* errflag;           // set to ACEB200_EEMPTY / ACEB200_ECATEGORY on bad input
-    int TE;                 // environments per CTA
-    int SKR, SKY;           // staging row strides: doubles (radial) and c2 (harmonics)
+    int TE;                 // environments per CTA (<= kPoolTEmax)
+    int nP;                 // harmonics staged per neighbour: sizeP(L)
 };
 
 constexpr int kPoolThreads = 128;
 constexpr int kPoolItems = 4;       // (environment, slot) items a thread can own per sub-tile
+constexpr int kPoolPitch = 129;     // staging row pitch (elements)
+constexpr int kPoolTEmax = 16;
 
-template <int NMAX>
+template <int NMAX, bool SPECIES>
 __global__ void __launch_bounds__(kPoolThreads) k_pool(const PoolParams p)
 {
     ACE_DYN_SMEM(c2, smem);
-    c2* SY = smem;                                                            // [128][SKY]
-    double* SR = reinterpret_cast<double*>(SY + (size_t)kPoolThreads * p.SKY);  // [128][SKR]
-    int* sq = reinterpret_cast<int*>(SR + (size_t)kPoolThreads * p.SKR);         // [128] species of the staged neighbour
+    c2* SY = smem;                                                            // [nP][129]
+    double* SR = reinterpret_cast<double*>(SY + (size_t)p.nP * kPoolPitch);    // [N][129]
+    int* sq = reinterpret_cast<int*>(SR + (size_t)p.rp.N * kPoolPitch);        // [128] species of the staged neighbour
+    int* joff = sq + kPoolThreads;                                             // [TE + 1] neighbour offsets relative to the CTA's first
     const int tid = threadIdx.x;
     const int N = p.rp.N, nS = p.C.nS;
     const long long e0 = (long long)blockIdx.x * p.TE;
     if (e0 >= p.B.nenv) return;
     const int ne = (int)((p.B.nenv - e0) < p.TE ? (p.B.nenv - e0) : p.TE);
-    const long long* off = p.B.off + e0;
+    const long long jbeg = p.B.off[e0];
+    if (tid <= ne) joff[tid] = (int)(p.B.off[e0 + tid] - jbeg);
+    const double* Rb = p.B.R + 3 * (jbeg - p.B.jbase);
+    const int* spb = SPECIES ? p.B.species + (jbeg - p.B.jbase) : nullptr;
+    __syncthreads();
 
     c2 acc[kPoolItems];
 #pragma unroll
     for (int it = 0; it < kPoolItems; ++it) acc[it] = c2{0.0, 0.0};
 
-    int e = 0;
-    long long j0 = off[0];
+    int e = 0, j0 = 0;
     while (e < ne) {
         // ---- choose the sub-tile [j0, j1): whole environments e..e2-1, or a piece of environment e
-        const long long jend_e = off[e + 1];
-        int e2 = e + 1;
-        long long j1;
+        const int jend_e = joff[e + 1];
+        int e2 = e + 1, j1;
         bool done_e;                      // the environments of this sub-tile are complete after it
-        if (j0 == off[e] && jend_e - j0 <= kPoolThreads) {
-            while (e2 < ne && off[e2 + 1] - j0 <= kPoolThreads && (e2 + 1 - e) * nS <= kPoolThreads * kPoolItems) ++e2;
-            j1 = off[e2];
+        if (j0 == joff[e] && jend_e - j0 <= kPoolThreads) {
+            while (e2 < ne && joff[e2 + 1] - j0 <= kPoolThreads && (e2 + 1 - e) * nS <= kPoolThreads * kPoolItems) ++e2;
+            j1 = joff[e2];
             done_e = true;
         } else {
             j1 = (j0 + kPoolThreads < jend_e) ? j0 + kPoolThreads : jend_e;
             done_e = (j1 == jend_e);
         }
-        const int nrows = (int)(j1 - j0);
+        const int nrows = j1 - j0;
 
         // ---- phase a
         if (tid < nrows) {
-            const long long j = j0 + tid;
-            const double* r = p.B.R + 3 * (j - p.B.jbase);
-            const double x = r[0], y = r[1], z = r[2];
-            int q = 0;
-            if (p.B.species) {
-                q = p.B.species[j - p.B.jbase] - 1;
+            const int j = j0 + tid;
+            const double x = Rb[3 * j], y = Rb[3 * j + 1], z = Rb[3 * j + 2];
+            if (SPECIES) {
+                int q = spb[j] - 1;
                 if (q < 0 || q >= p.C.nQ) { atomicMax(p.errflag, 6); q = 0; }   // ECATEGORY (src/discrete1pbasis.jl:39)
+                sq[tid] = q;
             }
-            sq[tid] = q;
             const Spher sp = cart2spher(x, y, z);
             double Rn[NMAX];
             radial_e<NMAX>(p.rp, sp.r, Rn);
-            double* rowR = SR + (size_t)tid * p.SKR;
 #pragma unroll
-            for (int n = 0; n < NMAX; ++n) if (n < N) rowR[n] = Rn[n];
-            c2* rowY = SY + (size_t)tid * p.SKY;
+            for (int n = 0; n < NMAX; ++n) if (n < N) SR[n * kPoolPitch + tid] = Rn[n];
             for_each_lm(p.ap, sp, [&](int l, int m, double Pv, double epr, double epi) {
-                rowY[index_p(l, m)] = c2{epr * Pv, epi * Pv};
+                SY[index_p(l, m) * kPoolPitch + tid] = c2{epr * Pv, epi * Pv};
             });
         }
         __syncthreads();
@@ -171,24 +173,31 @@ __global__ void __launch_bounds__(kPoolThreads) k_pool(const PoolParams p)
             const int idx = tid + it * kPoolThreads;
             if (idx < nitems) {
                 const int el = idx / nS, s = idx - el * nS;
-                const int n = __ldg(p.C.slot_n + s), ip = __ldg(p.C.slot_ip + s), q = __ldg(p.C.slot_q + s);
-                long long ra = off[e + el] - j0, rb = off[e + el + 1] - j0;
+                const int n = __ldg(p.C.slot_n + s), ip = __ldg(p.C.slot_ip + s);
+                int ra = joff[e + el] - j0, rb = joff[e + el + 1] - j0;
                 if (ra == rb && s == 0) atomicMax(p.errflag, 5);          // EEMPTY (src/product_1pbasis.jl:124)
                 if (ra < 0) ra = 0;
                 if (rb > nrows) rb = nrows;
+                const double* pr = SR + n * kPoolPitch;
+                const c2* py = SY + ip * kPoolPitch;
                 c2 a = acc[it], a2 = c2{0.0, 0.0};
-                int r = (int)ra;
-                for (; r + 1 < (int)rb; r += 2) {
-                    const double r0 = (sq[r] == q) ? SR[(size_t)r * p.SKR + n] : 0.0;
-                    const double r1 = (sq[r + 1] == q) ? SR[(size_t)(r + 1) * p.SKR + n] : 0.0;
-                    const c2 y0 = SY[(size_t)r * p.SKY + ip], y1 = SY[(size_t)(r + 1) * p.SKY + ip];
-                    a.x += r0 * y0.x; a.y += r0 * y0.y;
-                    a2.x += r1 * y1.x; a2.y += r1 * y1.y;
-                }
-                if (r < (int)rb) {
-                    const double r0 = (sq[r] == q) ? SR[(size_t)r * p.SKR + n] : 0.0;
-                    const c2 y0 = SY[(size_t)r * p.SKY + ip];
-                    a.x += r0 * y0.x; a.y += r0 * y0.y;
+                if (SPECIES) {
+                    const int q = __ldg(p.C.slot_q + s);
+                    for (int r = ra; r < rb; ++r) {
+                        const double rn = (sq[r] == q) ? pr[r] : 0.0;
+                        const c2 yv = py[r];
+                        a.x += rn * yv.x; a.y += rn * yv.y;
+                    }
+                } else {
+                    int r = ra;
+#pragma unroll 2
+                    for (; r + 1 < rb; r += 2) {
+                        const double r0 = pr[r], r1 = pr[r + 1];
+                        const c2 y0 = py[r], y1 = py[r + 1];
+                        a.x += r0 * y0.x; a.y += r0 * y0.y;
+                        a2.x += r1 * y1.x; a2.y += r1 * y1.y;
+                    }
+                    if (r < rb) { const double r0 = pr[r]; const c2 y0 = py[r]; a.x += r0 * y0.x; a.y += r0 * y0.y; }
                 }
                 a.x += a2.x; a.y += a2.y;
                 if (done_e) { p.Ac[(size_t)s * p.ldA + (e0 + e + el)] = a; a = c2{0.0, 0.0}; }
@@ -576,18 +585,29 @@ __device__ __forceinline__ void column_dot(const c2* D, int cnt, const double (&
 }
 
 // A CTA owns kForceTE consecutive environments: it stages their folded adjoints D~ in shared memory
-// ([slot][channel][local env]), then runs one thread per neighbour of those environments.
-template <int NMAX, int PB>
+// ([slot][channel][local env]) together with the (species, l, m) -> column table and the environments'
+// neighbour offsets, then runs one thread per neighbour of those environments.
+template <int NMAX, int PB, bool SPECIES>
 __global__ void __launch_bounds__(kForceThreads) k_forces(const ForceParams p)
 {
-    ACE_DYN_SMEM(c2, Ds);   // [nS][PB][kForceTE]
+    ACE_DYN_SMEM(c2, Ds);   // [nS][PB][kForceTE], then int colinfo[nQ * nPused], int joff[kForceTE + 1]
     constexpr int TE = kForceTE;
     const int tid = threadIdx.x;
     const long long e0 = (long long)blockIdx.x * TE;
     if (e0 >= p.B.nenv) return;
     const int ne = (int)((p.B.nenv - e0) < TE ? (p.B.nenv - e0) : TE);
-    const long long jbeg = p.B.off[e0], jend = p.B.off[e0 + ne];
-    const int nS = p.C.nS;
+    const long long jbeg = p.B.off[e0];
+    const int nS = p.C.nS, ncol = p.C.nQ * p.C.nPused;
+    int* colinfo = reinterpret_cast<int*>(Ds + (size_t)nS * PB * TE);
+    int* joff = colinfo + ncol;
+    for (int i = tid; i < ncol; i += kForceThreads) {
+        const int col = __ldg(p.C.colmap + i);
+        colinfo[i] = col < 0 ? -1 : (__ldg(p.C.base + col) | (__ldg(p.C.cnt + col) << 16));
+    }
+    if (tid <= ne) joff[tid] = (int)(p.B.off[e0 + tid] - jbeg);
+    const double* Rb = p.B.R + 3 * (jbeg - p.B.jbase);
+    const int* spb = SPECIES ? p.B.species + (jbeg - p.B.jbase) : nullptr;
+    double* Gb = p.G + (size_t)(jbeg - p.B.off[0]) * p.nprop * 3 * p.ncomp;
 
     for (int pb = 0; pb < p.P; pb += PB) {
         __syncthreads();
@@ -596,30 +616,31 @@ __global__ void __launch_bounds__(kForceThreads) k_forces(const ForceParams p)
             Ds[idx] = (pb + c < p.P && el < ne) ? p.Dt[((size_t)s * p.P + pb + c) * p.ldA + e0 + el] : c2{0.0, 0.0};
         }
         __syncthreads();
-        for (long long jabs = jbeg + tid; jabs < jend; jabs += kForceThreads) {
+        const int nj = joff[ne];
+        for (int j = tid; j < nj; j += kForceThreads) {
             int el = 0;
-            while (el + 1 < ne && p.B.off[e0 + el + 1] <= jabs) ++el;
-            const double* r = p.B.R + 3 * (jabs - p.B.jbase);
-            const double x = r[0], y = r[1], z = r[2];
+            while (el + 1 < ne && joff[el + 1] <= j) ++el;
+            const double x = Rb[3 * j], y = Rb[3 * j + 1], z = Rb[3 * j + 2];
             int q = 0;
-            if (p.B.species) { q = p.B.species[jabs - p.B.jbase] - 1; if (q < 0 || q >= p.C.nQ) q = 0; }
+            if (SPECIES) { q = spb[j] - 1; if (q < 0 || q >= p.C.nQ) q = 0; }
             const Spher sp = cart2spher(x, y, z);
             double Rn[NMAX], dRn[NMAX];
             radial_ed<NMAX>(p.rp, sp.r, Rn, dRn);
-            const int* cmap = p.C.colmap + (size_t)q * p.C.nPused;
+            const int* cinfo = colinfo + (SPECIES ? q * p.C.nPused : 0);
+            const c2* Dj = Ds + el;
             double S0[PB], S1[PB], S2[PB];
 #pragma unroll
             for (int c = 0; c < PB; ++c) { S0[c] = 0.0; S1[c] = 0.0; S2[c] = 0.0; }
             for_each_lm_ed(p.ap, sp, [&](int l, int m, double Pt, double dP, double epr, double epi) {
-                const int col = __ldg(cmap + index_p(l, m));
-                if (col < 0) return;
-                const int cnt = __ldg(p.C.cnt + col), base = __ldg(p.C.base + col);
+                const int ci = cinfo[index_p(l, m)];
+                if (ci < 0) return;
+                const int cnt = ci >> 16, base = ci & 0xffff;
                 const double f0 = (m == 0) ? Pt : Pt * sp.sth;    // |Y| factor:  Y = ep * f0
                 const double f1 = (double)m * Pt;
 #pragma unroll
                 for (int c = 0; c < PB; ++c) {
                     double ur = 0.0, ui = 0.0, vr = 0.0, vi = 0.0;
-                    column_dot<NMAX, PB * TE>(Ds + ((size_t)base * PB + c) * TE + el, cnt, Rn, dRn, ur, ui, vr, vi);
+                    column_dot<NMAX, PB * TE>(Dj + ((size_t)base * PB + c) * TE, cnt, Rn, dRn, ur, ui, vr, vi);
                     // z = u * ep ;  Re(v * ep)
                     const double zr = ur * epr - ui * epi, zi = ur * epi + ui * epr;
                     const double ve = vr * epr - vi * epi;
@@ -630,7 +651,6 @@ __global__ void __launch_bounds__(kForceThreads) k_forces(const ForceParams p)
             });
             // g = rhat S0 + (1/r) [ sphi S1 + cphi cth S2,  -cphi S1 + sphi cth S2,  -sth S2 ]
             const double rx = x * sp.rinv, ry = y * sp.rinv, rz = z * sp.rinv;
-            const long long jl = jabs - p.B.off[0];
 #pragma unroll
             for (int c = 0; c < PB; ++c) {
                 if (pb + c >= p.P) break;
@@ -638,7 +658,7 @@ __global__ void __launch_bounds__(kForceThreads) k_forces(const ForceParams p)
                 const double gy = ry * S0[c] + sp.rinv * (-sp.cphi * S1[c] + sp.sphi * sp.cth * S2[c]);
                 const double gz = rz * S0[c] - sp.rinv * sp.sth * S2[c];
                 const int ch = pb + c, prop = ch / p.ncomp, comp = ch % p.ncomp;
-                double* g = p.G + (((size_t)jl * p.nprop + prop) * 3) * p.ncomp + comp;
+                double* g = Gb + (((size_t)j * p.nprop + prop) * 3) * p.ncomp + comp;
                 g[0] = gx; g[p.ncomp] = gy; g[2 * p.ncomp] = gz;
             }
         }

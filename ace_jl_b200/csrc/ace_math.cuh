@@ -140,16 +140,27 @@ struct Spher {
 
 ACE_HD inline Spher cart2spher(double x, double y, double z)
 {
+    // two reciprocal square roots instead of two square roots and two divisions (each a ~20-instruction
+    // FP64 sequence); r = r2 * rsqrt(r2) is within 2 ulp of sqrt(r2)
     Spher S;
-    double rho2 = x * x + y * y;
-    double r2 = rho2 + z * z;
-    S.r = sqrt(r2);
-    S.rinv = 1.0 / S.r;
-    double rho = sqrt(rho2);
-    if (rho > 0.0) { double ir = 1.0 / rho; S.cphi = x * ir; S.sphi = y * ir; }
-    else { S.cphi = 1.0; S.sphi = 0.0; }
+    const double rho2 = x * x + y * y;
+    const double r2 = rho2 + z * z;
+#ifdef __CUDA_ARCH__
+    S.rinv = rsqrt(r2);
+#else
+    S.rinv = 1.0 / sqrt(r2);
+#endif
+    S.r = r2 * S.rinv;
+    if (rho2 > 0.0) {
+#ifdef __CUDA_ARCH__
+        const double ir = rsqrt(rho2);
+#else
+        const double ir = 1.0 / sqrt(rho2);
+#endif
+        S.cphi = x * ir; S.sphi = y * ir;
+        S.sth = (rho2 * ir) * S.rinv;
+    } else { S.cphi = 1.0; S.sphi = 0.0; S.sth = 0.0; }
     S.cth = z * S.rinv;
-    S.sth = rho * S.rinv;
     return S;
 }
 

@@ -531,7 +531,13 @@ static BatchDev batch_dev(const Staged& s, const Chunk& c)
 template <int NMAX>
 static void launch_pool_t(aceb200_model* m, const PoolParams& p, dim3 grid, size_t smem)
 {
-    auto kfn = k_pool<NMAX>;
+    if (p.B.species) {
+        auto kfn = k_pool<NMAX, true>;
+        CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ACE_LAUNCH(kfn, grid, dim3(kPoolThreads), smem, m->cur->stream, p);
+        return;
+    }
+    auto kfn = k_pool<NMAX, false>;
     CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ACE_LAUNCH(kfn, grid, dim3(kPoolThreads), smem, m->cur->stream, p);
 }
@@ -545,10 +551,8 @@ static void launch_pool(aceb200_model* m, const BatchDev& B, long long ldA)
     if (T.nS > kPoolThreads * kPoolItems)
         throw ModelError(ACEB200_EUNSUPPORTED, "one-particle basis too large for k_pool (more than 512 canonical slots)");
     p.TE = 8;
-    const int nP = (T.Lused + 1) * (T.Lused + 2) / 2;
-    p.SKR = m->rp.N | 1;
-    p.SKY = nP | 1;
-    const size_t smem = (size_t)kPoolThreads * (p.SKY * sizeof(c2) + p.SKR * sizeof(double) + sizeof(int));
+    p.nP = (T.Lused + 1) * (T.Lused + 2) / 2;
+    const size_t smem = (size_t)kPoolPitch * (p.nP * sizeof(c2) + m->rp.N * sizeof(double)) + (kPoolThreads + kPoolTEmax + 1) * sizeof(int);
     dim3 grid((unsigned)((B.nenv + p.TE - 1) / p.TE));
     switch (m->NMAX) {
     case 4: launch_pool_t<4>(m, p, grid, smem); break;
@@ -625,10 +629,10 @@ static void launch_adjoint(aceb200_model* m, long long nenv, long long ldA, bool
     m->launches++;
 }
 
-template <int NMAX, int PB>
+template <int NMAX, int PB, bool SPECIES>
 static void launch_forces_t(aceb200_model* m, const ForceParams& p, unsigned grid, size_t smem)
 {
-    auto kfn = k_forces<NMAX, PB>;
+    auto kfn = k_forces<NMAX, PB, SPECIES>;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ACE_LAUNCH(kfn, dim3(grid), dim3(kForceThreads), smem, m->cur->stream, p);
 }
@@ -640,11 +644,13 @@ static void launch_forces(aceb200_model* m, const BatchDev& B, long long nJ, lon
     p.rp = m->rp; p.ap = m->ap; p.C = m->C; p.B = B;
     p.Dt = m->cur->ws_Dt.as<c2>(); p.ldA = ldA; p.P = m->T.P; p.nprop = m->T.nprop; p.ncomp = m->T.ncomp; p.G = G;
     const int pb = m->PB == 1 ? 1 : (m->PB == 3 ? 3 : 2);
-    const size_t smem = (size_t)m->T.nS * pb * kForceTE * sizeof(c2);
+    const size_t smem = (size_t)m->T.nS * pb * kForceTE * sizeof(c2) + ((size_t)m->C.nQ * m->C.nPused + kForceTE + 1) * sizeof(int);
+    const bool sp = B.species != nullptr;
     if (smem > (size_t)m->smem_optin)
         throw ModelError(ACEB200_EUNSUPPORTED, "one-particle basis too large for the shared-memory staging of k_forces");
     const unsigned grid = (unsigned)((B.nenv + kForceTE - 1) / kForceTE);
-#define ACE_F(NM) { if (pb == 1) launch_forces_t<NM, 1>(m, p, grid, smem); else if (pb == 3) launch_forces_t<NM, 3>(m, p, grid, smem); else launch_forces_t<NM, 2>(m, p, grid, smem); }
+#define ACE_F2(NM, PBV) { if (sp) launch_forces_t<NM, PBV, true>(m, p, grid, smem); else launch_forces_t<NM, PBV, false>(m, p, grid, smem); }
+#define ACE_F(NM) { if (pb == 1) ACE_F2(NM, 1) else if (pb == 3) ACE_F2(NM, 3) else ACE_F2(NM, 2) }
     switch (m->NMAX) {
     case 4: ACE_F(4) break;
     case 8: ACE_F(8) break;
@@ -655,6 +661,7 @@ static void launch_forces(aceb200_model* m, const BatchDev& B, long long nJ, lon
     default: ACE_F(32) break;
     }
 #undef ACE_F
+#undef ACE_F2
     CU(cudaGetLastError());
     m->launches++;
 }
