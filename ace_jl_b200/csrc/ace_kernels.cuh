@@ -357,38 +357,51 @@ __global__ void __launch_bounds__(32) k_adjoint(const AdjointParams p)
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_adjoint_stream: the single-channel, real-weight fast path (energies + forces of an invariant model)
+// k_adjoint_stream: energies and folded adjoints for PB output channels per pass
 // ------------------------------------------------------------------------------------------------
 // The adjoint lists of all targets and orders are flattened by the host into streams in exactly the order
 // the kernel consumes them.  The kernel is bound by shared-memory -> register bandwidth (every byte a lane
 // receives costs the same, broadcast or not), so the per-leaf stream is as small as it can be:
-//   leaf block (4 leaves of one (target, order) segment) = { u32 code[4], f64 w[4] }            48 bytes
-//     code = slot1 | flipIm<<15 | slot2<<16 | conj2<<31      (NF = 3: a second word: slot3 | conj3<<31)
-//     value = (w Re, +-w Im) of  A~[slot1] * cj(A~[slot2]) (* cj(A~[slot3]))
+//   leaf block (4 leaves of one (target, order) segment) = { u32 code[4] (x2 for NF > 2), w[4][PB] }
+//     code  = slot1 | flipIm<<15 | slot2<<16 | conj2<<31        code' = slot3 | conj3<<15 | slot4<<16 | conj4<<31
+//     X     = A~[slot1] * cj(A~[slot2]) (* cj(A~[slot3]) * cj(A~[slot4])),  Im X negated if flipIm
+//     value = w[p] * X   for each channel p (w real, or complex when CW)
 //     A~ are the canonical (m >= 0) slots; unused factors point at an extra slot that holds 1; the conjugation
-//     of the first operand and all (-1)^m signs are folded into w / flipIm by the host:
+//     of the first operand and all (-1)^m signs are folded into flipIm / w by the host:
 //       prod_k (s_k cj^{k_k} A~_k) = (prod s_k) cj^{k_1}( A~_1 prod_{k>1} cj^{k_k xor k_1} A~_k ).
 //   ctl[block]  (u32, global)  0 for most blocks; else flags | order | slot<<8: end of segment / target / slot
-//   tinfo[k]    (32 B, global) consumed in order, one per non-zero ctl: target slot+masks, order-1 weight, 1/order
+//   tinfo[k]    (global) consumed in order, one per non-zero ctl: target slot + masks, 1/order, order-1 weights
 // The leaf blocks are read strictly sequentially and identically by every lane, so the warp fetches them
-// cooperatively (three coalesced 128-bit loads per lane = 32 blocks, two chunks ahead of use) into a 2-slot
-// shared-memory ring and reads them back as broadcasts.  Table latency is hidden, the 4 leaves of a block are
-// independent, and control is a warp-uniform branch on ctl.
+// cooperatively (coalesced 128-bit loads, two chunks ahead of use) into a 2-slot shared-memory ring and reads
+// them back as broadcasts.  Table latency is hidden, the leaves of a block are independent, and control is a
+// warp-uniform branch on ctl.  The energy falls out of the same pass by Euler's identity
+// sum_a A_a dF_nu/dA_a = nu F_nu.
 constexpr unsigned kSegEnd = 8, kTgtEnd = 16, kTgtNeg = 32, kTgtOdd = 64, kSlotEnd = 128;
 constexpr int kBlkLeaves = 4;               // leaves per block
-constexpr int kChunkBlocks = 32;            // blocks per ring chunk
 constexpr int kStreamWarps = 8;             // warps per CTA; each walks its own sub-stream over the same A tile
 
+template <int NF, int PB, bool CW>
+struct StreamGeom {
+    static constexpr int CS = CW ? 2 : 1;
+    static constexpr int CWORDS = (NF == 2) ? 1 : 2;                     // code words per leaf
+    static constexpr int QB = CWORDS + 2 * PB * CS;                      // uint4 per block (4 leaves)
+    static constexpr int KB = (QB <= 4) ? 32 : 8;                        // blocks per ring chunk
+    static constexpr int QBP = (KB == 32) ? QB : ((QB + 3) / 4) * 4;     // padded so that a chunk is a multiple of 32 uint4
+    static constexpr int CH = KB * QBP;                                  // uint4 per chunk
+    static constexpr int LPC = CH / 32;                                  // uint4 each lane loads per chunk
+    static constexpr int TIQ = 1 + (1 + PB * CS + 1) / 2;                // uint4 per tinfo record
+};
+
 struct StreamParams {
-    int nS, has_const, want_D, nchunks;      // nchunks: length of EVERY sub-stream (padded to the longest)
-    const uint4* stream;                     // [kStreamWarps][nchunks][kChunkBlocks * Q]   (Q = 3 or 4 uint4 per block)
-    const unsigned* ctl;                     // [kStreamWarps][nchunks * kChunkBlocks]
-    const uint4* tinfo;                      // [kStreamWarps][ntinfo][2]
-    int ntinfo;
-    double w0;
+    int nS, has_const, want_D, nchunks, ntinfo;
+    int P, pb0;                              // channels [pb0, pb0 + PB) of P are computed by this launch
+    const uint4* stream;                     // [kStreamWarps][nchunks][CH]
+    const unsigned* ctl;                     // [kStreamWarps][nchunks * KB]
+    const uint4* tinfo;                      // [kStreamWarps][ntinfo][TIQ]
+    const double* w0;                        // [PB * CS] the constant term of each channel
     const c2* Ac; long long ldA;
-    c2* Dt;                                  // [nS][ldA]
-    double* E;                               // [nenv]
+    c2* Dt;                                  // [nS][P][ldA]
+    double* E;                               // [nenv][P]
     long long nenv;
 };
 
@@ -422,19 +435,19 @@ __device__ __forceinline__ double xor_hi(double v, unsigned mask)
 // One CTA = kStreamWarps warps sharing one shared-memory tile of A (32 environments, one per lane).  The
 // host splits the targets into kStreamWarps balanced sub-streams; warp w walks sub-stream w.  More warps
 // per byte of shared memory is what hides the FP64 and shared-memory latencies of the leaf products.
-template <int NF>
+template <int NF, int PB, bool CW>
 __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const StreamParams p)
 {
-    constexpr int Q = (NF == 2) ? 3 : 4;                        // uint4 per leaf block
-    constexpr int CH = kChunkBlocks * Q;                        // uint4 per chunk (= Q per lane)
+    typedef StreamGeom<NF, PB, CW> G;
+    constexpr int CS = G::CS, CH = G::CH, QBP = G::QBP, KB = G::KB, LPC = G::LPC, TIQ = G::TIQ;
     ACE_DYN_SMEM(c2, As);                                       // [nS + 1][32]; slot nS holds 1
     uint4* rings = reinterpret_cast<uint4*>(As + (size_t)(p.nS + 1) * 32);   // [kStreamWarps][2][CH]
-    double* Epart = reinterpret_cast<double*>(rings + kStreamWarps * 2 * CH); // [kStreamWarps][32]
+    double* Epart = reinterpret_cast<double*>(rings);            // aliases the rings once the stream is consumed
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4* ring = rings + warp * 2 * CH;
     const uint4* stream = p.stream + (size_t)warp * p.nchunks * CH;
-    const unsigned* ctl = p.ctl + (size_t)warp * p.nchunks * kChunkBlocks;
-    const uint4* tinfo = p.tinfo + (size_t)warp * p.ntinfo * 2;
+    const unsigned* ctl = p.ctl + (size_t)warp * p.nchunks * KB;
+    const uint4* tinfo = p.tinfo + (size_t)warp * p.ntinfo * TIQ;
     const unsigned char* Ab = reinterpret_cast<const unsigned char*>(As) + lane * 16;   // this lane's column
     const long long ntiles = (p.nenv + 31) / 32;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -442,39 +455,41 @@ __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const Stre
         for (int s = warp; s < p.nS; s += kStreamWarps) As[s * 32 + lane] = p.Ac[(size_t)s * p.ldA + e];
         if (warp == 0) As[p.nS * 32 + lane] = c2{1.0, 0.0};
 #pragma unroll
-        for (int k = 0; k < Q; ++k) ring[k * 32 + lane] = __ldg(stream + k * 32 + lane);
+        for (int k = 0; k < LPC; ++k) ring[k * 32 + lane] = __ldg(stream + k * 32 + lane);
         if (p.nchunks > 1) {
 #pragma unroll
-            for (int k = 0; k < Q; ++k) ring[CH + k * 32 + lane] = __ldg(stream + CH + k * 32 + lane);
+            for (int k = 0; k < LPC; ++k) ring[CH + k * 32 + lane] = __ldg(stream + CH + k * 32 + lane);
         }
         __syncthreads();
-        double E = (p.has_const && warp == 0) ? p.w0 : 0.0;
-        c2 D = c2{0.0, 0.0}, S = c2{0.0, 0.0};
+        double E[PB];
+        c2 D[PB], S[PB];
+#pragma unroll
+        for (int q = 0; q < PB; ++q) {
+            E[q] = (p.has_const && warp == 0) ? __ldg(p.w0 + q * CS) : 0.0;
+            D[q] = c2{0.0, 0.0}; S[q] = c2{0.0, 0.0};
+        }
         int ti = 0;
         for (int ch = 0; ch < p.nchunks; ++ch) {
             const bool havepre = ch + 2 < p.nchunks;
-            uint4 pre[Q];
+            uint4 pre[LPC];
 #pragma unroll
-            for (int k = 0; k < Q; ++k) pre[k] = uint4{0u, 0u, 0u, 0u};
+            for (int k = 0; k < LPC; ++k) pre[k] = uint4{0u, 0u, 0u, 0u};
             if (havepre) {
 #pragma unroll
-                for (int k = 0; k < Q; ++k) pre[k] = __ldg(stream + (size_t)(ch + 2) * CH + k * 32 + lane);
+                for (int k = 0; k < LPC; ++k) pre[k] = __ldg(stream + (size_t)(ch + 2) * CH + k * 32 + lane);
             }
             const uint4* rb = ring + (ch & 1) * CH;
-            const unsigned* cb = ctl + (size_t)ch * kChunkBlocks;
+            const unsigned* cb = ctl + (size_t)ch * KB;
 #pragma unroll 4
-            for (int b = 0; b < kChunkBlocks; ++b) {
-                const uint4* blk = rb + b * Q;
+            for (int b = 0; b < KB; ++b) {
+                const uint4* blk = rb + b * QBP;
                 const unsigned flags = __ldg(cb + b);
                 const uint4 cw = blk[0];
-                double w[4];
-                { const uint4 u = blk[Q - 2], v = blk[Q - 1];
-                  w[0] = __hiloint2double((int)u.y, (int)u.x); w[1] = __hiloint2double((int)u.w, (int)u.z);
-                  w[2] = __hiloint2double((int)v.y, (int)v.x); w[3] = __hiloint2double((int)v.w, (int)v.z); }
                 const unsigned code[4] = {cw.x, cw.y, cw.z, cw.w};
-                unsigned code3[4] = {0u, 0u, 0u, 0u};
-                if (NF == 3) { const uint4 c3 = blk[1]; code3[0] = c3.x; code3[1] = c3.y; code3[2] = c3.z; code3[3] = c3.w; }
-                c2 acc0 = c2{0.0, 0.0}, acc1 = c2{0.0, 0.0};
+                unsigned code2[4] = {0u, 0u, 0u, 0u};
+                if (NF > 2) { const uint4 c3 = blk[1]; code2[0] = c3.x; code2[1] = c3.y; code2[2] = c3.z; code2[3] = c3.w; }
+                const double* wb = reinterpret_cast<const double*>(blk + G::CWORDS);     // [4][PB][CS]
+                c2 acc1 = c2{0.0, 0.0};          // second accumulator (PB == 1 only): halves the dependent chain
                 c2 a1 = c2{0.0, 0.0};
                 unsigned s1prev = 0xffffffffu;
 #pragma unroll
@@ -486,60 +501,93 @@ __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const Stre
                     s1prev = s1;
                     c2 a2 = lds_c2(Ab, ((c >> 16) & 0x3fffu) << 9);
                     a2.y = xor_hi(a2.y, c & 0x80000000u);
-                    c2 prod = cmul(a1, a2);
-                    if (NF == 3) {
-                        c2 a3 = lds_c2(Ab, (code3[k] & 0x3fffu) << 9);
-                        a3.y = xor_hi(a3.y, code3[k] & 0x80000000u);
-                        prod = cmul(prod, a3);
+                    c2 X = cmul(a1, a2);
+                    if (NF > 2) {
+                        c2 a3 = lds_c2(Ab, (code2[k] & 0x3fffu) << 9);
+                        a3.y = xor_hi(a3.y, (code2[k] & 0x8000u) << 16);
+                        X = cmul(X, a3);
                     }
-                    const double wy = xor_hi(w[k], (c & 0x8000u) << 16);
-                    if (k & 1) { acc1.x += w[k] * prod.x; acc1.y += wy * prod.y; }
-                    else { acc0.x += w[k] * prod.x; acc0.y += wy * prod.y; }
+                    if (NF > 3) {
+                        c2 a4 = lds_c2(Ab, ((code2[k] >> 16) & 0x3fffu) << 9);
+                        a4.y = xor_hi(a4.y, code2[k] & 0x80000000u);
+                        X = cmul(X, a4);
+                    }
+                    X.y = xor_hi(X.y, (c & 0x8000u) << 16);
+#pragma unroll
+                    for (int q = 0; q < PB; ++q) {
+                        if (CW) {
+                            const double wr = wb[(k * PB + q) * 2], wi = wb[(k * PB + q) * 2 + 1];
+                            S[q].x += wr * X.x - wi * X.y;
+                            S[q].y += wr * X.y + wi * X.x;
+                        } else {
+                            const double w = wb[k * PB + q];
+                            if (PB == 1 && (k & 1)) { acc1.x += w * X.x; acc1.y += w * X.y; }
+                            else { S[q].x += w * X.x; S[q].y += w * X.y; }
+                        }
+                    }
                 }
-                S.x += acc0.x + acc1.x;
-                S.y += acc0.y + acc1.y;
+                if (PB == 1 && !CW) { S[0].x += acc1.x; S[0].y += acc1.y; }
                 if (flags) {
-                    const uint4 t0 = __ldg(tinfo + 2 * ti), t1 = __ldg(tinfo + 2 * ti + 1);
+                    const uint4 t0 = __ldg(tinfo + (size_t)ti * TIQ);
+                    const double* td = reinterpret_cast<const double*>(tinfo + (size_t)ti * TIQ + 1);   // scale, w1[PB][CS]
                     ++ti;
                     c2 Aa = lds_c2(Ab, t0.x);
                     Aa.x = xor_hi(Aa.x, t0.y);
                     Aa.y = xor_hi(Aa.y, t0.z);
-                    const double w1 = __hiloint2double((int)t1.y, (int)t1.x), scale = __hiloint2double((int)t1.w, (int)t1.z);
                     const bool neg = (flags & kTgtNeg) != 0u, odd = (flags & kTgtOdd) != 0u;
                     // fold onto the m >= 0 slot: Re(D- grad(phi_-m)) = Re((-1)^m conj(D-) grad(phi_m))
                     const double fx = (neg && odd) ? -1.0 : 1.0, fy = neg ? (odd ? 1.0 : -1.0) : 1.0;
                     if (flags & kSegEnd) {
-                        // Euler: sum_a A_a dF_nu/dA_a = nu F_nu  =>  E += Re(A_a S_seg) / nu
-                        E += (Aa.x * S.x - Aa.y * S.y) * scale;
-                        D.x += fx * S.x;
-                        D.y += fy * S.y;
-                        S = c2{0.0, 0.0};
+                        const double scale = __ldg(td);
+#pragma unroll
+                        for (int q = 0; q < PB; ++q) {
+                            E[q] += (Aa.x * S[q].x - Aa.y * S[q].y) * scale;
+                            D[q].x += fx * S[q].x;
+                            D[q].y += fy * S[q].y;
+                            S[q] = c2{0.0, 0.0};
+                        }
                     }
                     if (flags & kTgtEnd) {
-                        // order-1 term of this target: dE/dA_a += c~ (real), E += Re(A_a) c~
-                        E += Aa.x * w1;
-                        D.x += fx * w1;
+                        // order-1 term of this target: dE/dA_a += c~, E += Re(A_a c~)
+#pragma unroll
+                        for (int q = 0; q < PB; ++q) {
+                            const double wr = __ldg(td + 1 + q * CS), wi = CW ? __ldg(td + 2 + q * CS) : 0.0;
+                            E[q] += Aa.x * wr - Aa.y * wi;
+                            D[q].x += fx * wr;
+                            D[q].y += fy * wi;
+                        }
                     }
                     if (flags & kSlotEnd) {
-                        if (p.want_D && e < p.nenv) p.Dt[(size_t)(flags >> 8) * p.ldA + e] = D;
-                        D = c2{0.0, 0.0};
+#pragma unroll
+                        for (int q = 0; q < PB; ++q) {
+                            if (p.want_D && e < p.nenv && p.pb0 + q < p.P)
+                                p.Dt[((size_t)(flags >> 8) * p.P + p.pb0 + q) * p.ldA + e] = D[q];
+                            D[q] = c2{0.0, 0.0};
+                        }
                     }
                 }
             }
             __syncwarp();            // every lane is done reading this ring slot
             if (havepre) {
 #pragma unroll
-                for (int k = 0; k < Q; ++k) ring[(ch & 1) * CH + k * 32 + lane] = pre[k];
+                for (int k = 0; k < LPC; ++k) ring[(ch & 1) * CH + k * 32 + lane] = pre[k];
             }
             __syncwarp();
         }
-        Epart[warp * 32 + lane] = E;
+        __syncthreads();             // all warps are done with their rings: reuse them for the energy partials
+#pragma unroll
+        for (int q = 0; q < PB; ++q) Epart[(warp * PB + q) * 32 + lane] = E[q];
         __syncthreads();
         if (warp == 0 && e < p.nenv) {
-            double Et = 0.0;
 #pragma unroll
-            for (int w = 0; w < kStreamWarps; ++w) Et += Epart[w * 32 + lane];
-            p.E[e] = Et;
+            for (int q = 0; q < PB; ++q) {
+                if (p.pb0 + q < p.P) {
+                    double Et = 0.0;
+#pragma unroll
+                    for (int w = 0; w < kStreamWarps; ++w) Et += Epart[(w * PB + q) * 32 + lane];
+                    p.E[(size_t)e * p.P + p.pb0 + q] = Et;
+                }
+            }
         }
         __syncthreads();
     }

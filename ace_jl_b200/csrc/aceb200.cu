@@ -90,6 +90,8 @@ struct Lane {
     }
 };
 
+struct StreamPass { DevBuf blocks, tinfo, w0; int pb0 = 0; };
+
 struct aceb200_model {
     int device = 0;
     HostTables T;
@@ -108,8 +110,9 @@ struct aceb200_model {
     ListDev list[kMaxOrdDev + 1];
     DevBuf d_w0, d_w1;
     DevBuf d_lw[kMaxOrdDev + 1];
-    DevBuf d_stream, d_ctl, d_tinfo;   // k_adjoint_stream tables (single channel, real weights)
-    int stream_chunks = 0, stream_nf = 0, stream_ntinfo = 0;   // 0 chunks: use the generic k_adjoint
+    DevBuf d_ctl;                      // k_adjoint_stream control words (shared by all passes)
+    std::vector<StreamPass> passes;    // per-pass leaf blocks and target records (PB channels each)
+    int stream_chunks = 0, stream_nf = 0, stream_ntinfo = 0, stream_pb = 1;   // 0 chunks: use the generic k_adjoint
     // per-call workspace (guarded by mu).  Three lanes: device-resident batches use lane 0 on the caller's
     // stream; host-resident batches are pipelined chunk by chunk over all lanes (H2D copy, kernels and D2H
     // copy of consecutive chunks overlap on the lanes' private streams).
@@ -210,26 +213,55 @@ static void upload_weights(aceb200_model* m, const double* c)
     upload_stream(m);
 }
 
-// Flatten the adjoint lists into the record stream k_adjoint_stream consumes (layout: ace_kernels.cuh).
+// Host mirror of StreamGeom (ace_kernels.cuh)
+struct HostGeom { int CS, CWORDS, QB, KB, QBP, CH, TIQ; };
+static HostGeom stream_geom(int NF, int PB, bool CW)
+{
+    HostGeom g;
+    g.CS = CW ? 2 : 1;
+    g.CWORDS = (NF == 2) ? 1 : 2;
+    g.QB = g.CWORDS + 2 * PB * g.CS;
+    g.KB = (g.QB <= 4) ? 32 : 8;
+    g.QBP = (g.KB == 32) ? g.QB : ((g.QB + 3) / 4) * 4;
+    g.CH = g.KB * g.QBP;
+    g.TIQ = 1 + (1 + PB * g.CS + 1) / 2;
+    return g;
+}
+
+static size_t stream_smem(int nS, const HostGeom& g)
+{
+    return (size_t)(nS + 1) * 32 * sizeof(c2) + (size_t)kStreamWarps * 2 * g.CH * sizeof(uint4);
+}
+
+// Flatten the adjoint lists into the streams k_adjoint_stream consumes (layout: ace_kernels.cuh).
 //
 // Mirror folding.  With A_{n l -m} = (-1)^m conj(A_{n l m}) the AA function whose factors all have their m
-// negated equals (-1)^{sum m} conj(AA).  For real weights and a real output,
-//     c~_i Re(AA_i) + c~_i' Re(AA_i') = (c~_i + (-1)^{sum m} c~_i') Re(AA_i),
-// so only one function of each mirror pair is kept, with the folded weight.  This halves the stream; the
-// energy and its gradient are unchanged as functions of the positions (they differ from the unfolded
-// evaluation only in the order of floating-point additions).
+// negated equals s conj(AA), s = (-1)^{sum m}.  Under the real part that every output of this path takes,
+//     Re(c~_i AA_i) + Re(c~_i' AA_i') = Re((c~_i + s conj(c~_i')) AA_i),
+// so only one function of each mirror pair is kept, with the folded weight.  This halves the stream; energy and
+// gradient are unchanged as functions of the positions (only the order of floating-point additions differs).
 static void upload_stream(aceb200_model* m)
 {
     HostTables& T = m->T;
     m->stream_chunks = 0;
-    if (T.P != 1 || m->cw || T.maxord < 2 || T.maxord > 4 || !T.symreal) return;
-    const int NF = T.maxord <= 3 ? 2 : 3;
+    for (StreamPass& sp : m->passes) { sp.blocks.release(); sp.tinfo.release(); sp.w0.release(); }
+    m->passes.clear();
+    if (T.maxord < 2 || T.maxord > 5 || !T.symreal || getenv("ACEB200_NO_STREAM")) return;
+    if (T.nS + 1 >= (1 << 14)) return;                   // 14-bit slot fields
+    const int NF = T.maxord <= 3 ? 2 : (T.maxord == 4 ? 3 : 4);
+    const bool CW = m->cw;
+    const int P = T.P;
+    // channels per pass: the largest power of two <= 8 whose ring still fits next to the A tile
+    int PB = 1;
+    while (PB < P && PB < 8) PB *= 2;
+    while (PB > 1 && stream_smem(T.nS, stream_geom(NF, PB, CW)) > (size_t)m->smem_optin) PB /= 2;
+    const HostGeom g = stream_geom(NF, PB, CW);
+    if (stream_smem(T.nS, g) > (size_t)m->smem_optin) return;    // falls back to the list kernel
     const bool fold = !getenv("ACEB200_NO_MIRROR_FOLD");
 
-    // ---- effective (mirror-folded) coefficient of every AA function; non-canonical partners are dropped
-    std::vector<double> ceff(T.nAA);
+    // ---- effective (mirror-folded) coefficients; non-canonical partners are dropped
+    std::vector<cplx> ceff(m->ctilde);
     std::vector<char> keep(T.nAA, 1);
-    for (int i = 0; i < T.nAA; ++i) ceff[i] = m->ctilde[i].real();
     if (fold) {
         std::map<std::tuple<int, int, int, int>, int> inv1p;
         for (int a = 0; a < T.nA; ++a) inv1p[std::make_tuple(T.iA_q[a], T.iA_n[a], T.iA_l[a], T.iA_m[a])] = a;
@@ -244,7 +276,7 @@ static void upload_stream(aceb200_model* m)
             ok = true;
             for (int t = 0; t < T.orders[i]; ++t) {
                 int a = T.spec[(size_t)i * T.maxord + t];
-                if (mirror) { a = mirA[a]; if (a < 0) ok = false; }
+                if (mirror) { a = mirA[a]; if (a < 0) { ok = false; a = 0; } }
                 k.push_back(a);
             }
             std::sort(k.begin(), k.end(), std::greater<int>());
@@ -261,18 +293,19 @@ static void upload_stream(aceb200_model* m)
             const int ip = it->second;
             int summ = 0;
             for (int t = 0; t < T.orders[i]; ++t) summ += T.iA_m[T.spec[(size_t)i * T.maxord + t]];
-            ceff[i] += ((summ & 1) ? -1.0 : 1.0) * m->ctilde[ip].real();
+            const double sg = (summ & 1) ? -1.0 : 1.0;
+            for (int pch = 0; pch < P; ++pch) {
+                ceff[(size_t)i * P + pch] += sg * std::conj(m->ctilde[(size_t)ip * P + pch]);
+                ceff[(size_t)ip * P + pch] = cplx(0, 0);
+            }
             keep[ip] = 0;
-            ceff[ip] = 0.0;
         }
     }
 
     const unsigned ONE = (unsigned)T.nS;                 // slot index of the constant 1
-    if (T.nS + 1 >= (1 << 14)) return;                   // 14-bit slot fields
-    const int Q = (NF == 2) ? 3 : 4;                     // uint4 per leaf block
-    struct Leaf { unsigned code, code3; double w; };
-    auto make_leaf = [&](const uint16_t* codes, int nf, double w) {
-        unsigned slot[3] = {ONE, ONE, ONE}, cj[3] = {0u, 0u, 0u};
+    struct Leaf { unsigned code, code2; double sg; int aa, mult; };
+    auto make_leaf = [&](const uint16_t* codes, int nf, int aa, int mult) {
+        unsigned slot[4] = {ONE, ONE, ONE, ONE}, cj[4] = {0u, 0u, 0u, 0u};
         double sg = 1.0;
         unsigned k1 = 0;
         for (int f = 0; f < nf; ++f) {
@@ -285,46 +318,30 @@ static void upload_stream(aceb200_model* m)
         }
         Leaf L;
         L.code = slot[0] | (k1 << 15) | (slot[1] << 16) | (cj[1] << 31);   // flipIm = conj of the whole product
-        L.code3 = slot[2] | (cj[2] << 31);
-        L.w = sg * w;
+        L.code2 = slot[2] | (cj[2] << 15) | (slot[3] << 16) | (cj[3] << 31);
+        L.sg = sg; L.aa = aa; L.mult = mult;
         return L;
     };
-    struct Sub { std::vector<uint32_t> blocks, ctl, tinfo; };
-    auto put_f64 = [](std::vector<uint32_t>& v, double x) { uint64_t b; memcpy(&b, &x, 8); v.push_back((uint32_t)(b & 0xffffffffu)); v.push_back((uint32_t)(b >> 32)); };
-    auto emit_block = [&](Sub& S, const std::vector<Leaf>& leaves, size_t i0, unsigned flags, int target, double invnu) {
-        Leaf L[kBlkLeaves];
+    // The block structure (codes, ctl, which target a tinfo record belongs to) is the same for every pass;
+    // only the weights differ.  Build the structure once per sub-stream, then emit the passes.
+    struct BlockRef { Leaf L[kBlkLeaves]; int nleaf; unsigned flags; int target; double invnu; };
+    std::vector<std::vector<BlockRef>> perslot(T.nS);
+    auto add_block = [&](std::vector<BlockRef>& v, const std::vector<Leaf>* leaves, size_t i0, unsigned flags, int target, double invnu) {
+        BlockRef b;
+        b.nleaf = 0; b.flags = flags; b.target = target; b.invnu = invnu;
         for (int k = 0; k < kBlkLeaves; ++k) {
-            if (i0 + k < leaves.size()) L[k] = leaves[i0 + k];
-            else { L[k].code = ONE | (ONE << 16); L[k].code3 = ONE; L[k].w = 0.0; }
+            if (leaves && i0 + k < leaves->size()) { b.L[k] = (*leaves)[i0 + k]; b.nleaf = k + 1; }
+            else { b.L[k].code = ONE | (ONE << 16); b.L[k].code2 = ONE | (ONE << 16); b.L[k].sg = 0.0; b.L[k].aa = -1; b.L[k].mult = 0; }
         }
-        for (int k = 0; k < kBlkLeaves; ++k) S.blocks.push_back(L[k].code);
-        if (NF == 3) for (int k = 0; k < kBlkLeaves; ++k) S.blocks.push_back(L[k].code3);
-        for (int k = 0; k < kBlkLeaves; ++k) put_f64(S.blocks, L[k].w);
-        S.ctl.push_back(flags);
-        if (flags) {
-            unsigned toff = ONE * 512u, mx = 0u, my = 0u;
-            double w1 = 0.0;
-            if (target >= 0) {
-                const unsigned c = (unsigned)T.iA_code[target];
-                toff = (c >> 2) * 512u;
-                mx = (c & 2u) ? 0x80000000u : 0u;
-                my = ((c & 1u) && !(c & 2u)) ? 0x80000000u : 0u;
-                if (T.aa1_of_target[target] >= 0) w1 = ceff[T.aa1_of_target[target]];
-            }
-            S.tinfo.push_back(toff); S.tinfo.push_back(mx); S.tinfo.push_back(my); S.tinfo.push_back(0u);
-            put_f64(S.tinfo, w1); put_f64(S.tinfo, invnu);
-        }
+        v.push_back(b);
     };
-    const std::vector<Leaf> none;
-    // ---- one block list per slot, then an LPT split of the slots over the kStreamWarps sub-streams
-    std::vector<Sub> perslot(T.nS);
     for (int s = 0; s < T.nS; ++s) {
-        Sub& S = perslot[s];
+        std::vector<BlockRef>& S = perslot[s];
         const unsigned sbits = (unsigned)s << 8;
         int tg[2] = {T.slot_pos[s], T.slot_neg[s]};
         int last = -1;
         for (int k = 0; k < 2; ++k) if (tg[k] >= 0) last = k;
-        if (last < 0) { emit_block(S, none, 0, kSlotEnd | sbits, -1, 0.0); continue; }
+        if (last < 0) { add_block(S, nullptr, 0, kSlotEnd | sbits, -1, 0.0); continue; }
         for (int k = 0; k < 2; ++k) {
             const int a = tg[k];
             if (a < 0) continue;
@@ -337,11 +354,11 @@ static void upload_stream(aceb200_model* m)
                 const Tree& tr = T.trees[nu];
                 for (int i = tr.ptr[a]; i < tr.ptr[a + 1]; ++i) {
                     if (!keep[tr.laa[i]]) continue;
-                    per[nu].push_back(make_leaf(&tr.codes[4 * (size_t)i], nu - 1, ceff[tr.laa[i]] * (double)tr.lmult[i]));
+                    per[nu].push_back(make_leaf(&tr.codes[4 * (size_t)i], nu - 1, tr.laa[i], tr.lmult[i]));
                 }
                 if (!per[nu].empty()) lastnu = nu;
             }
-            if (lastnu == 0) { emit_block(S, none, 0, tflags, a, 0.0); continue; }
+            if (lastnu == 0) { add_block(S, nullptr, 0, tflags, a, 0.0); continue; }
             for (int nu = 2; nu <= T.maxord; ++nu) {
                 const std::vector<Leaf>& lv = per[nu];
                 for (size_t i = 0; i < lv.size(); i += kBlkLeaves) {
@@ -350,49 +367,104 @@ static void upload_stream(aceb200_model* m)
                         flags = (unsigned)nu | kSegEnd | (tflags & (kTgtNeg | kTgtOdd));
                         if (nu == lastnu) flags |= tflags;
                     }
-                    emit_block(S, lv, i, flags, a, 1.0 / nu);
+                    add_block(S, &lv, i, flags, a, 1.0 / nu);
                 }
             }
         }
     }
+    // LPT split of the slots over the kStreamWarps sub-streams
     std::vector<int> order(T.nS);
     for (int s = 0; s < T.nS; ++s) order[s] = s;
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return perslot[x].ctl.size() > perslot[y].ctl.size(); });
-    std::vector<Sub> sub(kStreamWarps);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return perslot[x].size() > perslot[y].size(); });
+    std::vector<std::vector<BlockRef>> sub(kStreamWarps);
     for (int s : order) {
         int best = 0;
-        for (int w = 1; w < kStreamWarps; ++w) if (sub[w].ctl.size() < sub[best].ctl.size()) best = w;
-        Sub& d = sub[best];
-        d.blocks.insert(d.blocks.end(), perslot[s].blocks.begin(), perslot[s].blocks.end());
-        d.ctl.insert(d.ctl.end(), perslot[s].ctl.begin(), perslot[s].ctl.end());
-        d.tinfo.insert(d.tinfo.end(), perslot[s].tinfo.begin(), perslot[s].tinfo.end());
+        for (int w = 1; w < kStreamWarps; ++w) if (sub[w].size() < sub[best].size()) best = w;
+        sub[best].insert(sub[best].end(), perslot[s].begin(), perslot[s].end());
     }
     size_t longest = 1, ntinfo = 1;
-    for (auto& v : sub) { longest = std::max(longest, v.ctl.size()); ntinfo = std::max(ntinfo, v.tinfo.size() / 8); }
-    const size_t nchunks = (longest + kChunkBlocks - 1) / kChunkBlocks;
-    std::vector<uint32_t> allb, allc, allt;
     for (auto& v : sub) {
-        while (v.ctl.size() < nchunks * kChunkBlocks) emit_block(v, none, 0, 0u, -1, 0.0);   // inert padding blocks
-        v.tinfo.resize(ntinfo * 8, 0u);
-        allb.insert(allb.end(), v.blocks.begin(), v.blocks.end());
-        allc.insert(allc.end(), v.ctl.begin(), v.ctl.end());
-        allt.insert(allt.end(), v.tinfo.begin(), v.tinfo.end());
+        longest = std::max(longest, v.size());
+        size_t nt = 0;
+        for (auto& b : v) nt += b.flags != 0;
+        ntinfo = std::max(ntinfo, nt);
     }
-    (void)Q;
-    m->d_stream.reserve(allb.size() * 4 + 4096);
-    m->d_ctl.reserve(allc.size() * 4 + 256);
-    m->d_tinfo.reserve(allt.size() * 4 + 256);
-    CU(cudaMemcpy(m->d_stream.p, allb.data(), allb.size() * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(m->d_ctl.p, allc.data(), allc.size() * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(m->d_tinfo.p, allt.data(), allt.size() * 4, cudaMemcpyHostToDevice));
+    const size_t nchunks = (longest + g.KB - 1) / g.KB;
+    for (auto& v : sub) while (v.size() < nchunks * g.KB) add_block(v, nullptr, 0, 0u, -1, 0.0);   // inert padding blocks
+
+    // ctl (shared by all passes)
+    std::vector<uint32_t> ctl;
+    for (auto& v : sub) for (auto& b : v) ctl.push_back(b.flags);
+    m->d_ctl.reserve(ctl.size() * 4 + 256);
+    CU(cudaMemcpy(m->d_ctl.p, ctl.data(), ctl.size() * 4, cudaMemcpyHostToDevice));
+
+    // passes
+    const int npass = (P + PB - 1) / PB;
+    m->passes.resize(npass);
+    for (int ps = 0; ps < npass; ++ps) {
+        const int pb0 = ps * PB;
+        std::vector<uint32_t> blocks((size_t)kStreamWarps * nchunks * g.CH * 4, 0u);
+        std::vector<uint32_t> tinfo((size_t)kStreamWarps * ntinfo * g.TIQ * 4, 0u);
+        auto chan = [&](int aa, int q) { return (aa >= 0 && pb0 + q < P) ? ceff[(size_t)aa * P + pb0 + q] : cplx(0, 0); };
+        for (int w = 0; w < kStreamWarps; ++w) {
+            size_t ti = 0;
+            for (size_t ib = 0; ib < sub[w].size(); ++ib) {
+                const BlockRef& b = sub[w][ib];
+                uint32_t* dst = &blocks[(((size_t)w * nchunks * g.KB) + ib) * g.QBP * 4];
+                for (int k = 0; k < kBlkLeaves; ++k) {
+                    dst[k] = b.L[k].code;
+                    if (g.CWORDS == 2) dst[4 + k] = b.L[k].code2;
+                }
+                double* wd = reinterpret_cast<double*>(dst + 4 * g.CWORDS);
+                for (int k = 0; k < kBlkLeaves; ++k)
+                    for (int q = 0; q < PB; ++q) {
+                        const cplx z = chan(b.L[k].aa, q) * (b.L[k].sg * (double)b.L[k].mult);
+                        if (CW) { wd[(k * PB + q) * 2] = z.real(); wd[(k * PB + q) * 2 + 1] = z.imag(); }
+                        else wd[k * PB + q] = z.real();
+                    }
+                if (b.flags) {
+                    uint32_t* t = &tinfo[(((size_t)w * ntinfo) + ti) * g.TIQ * 4];
+                    ++ti;
+                    unsigned toff = ONE * 512u, mx = 0u, my = 0u;
+                    int aa1 = -1;
+                    if (b.target >= 0) {
+                        const unsigned c = (unsigned)T.iA_code[b.target];
+                        toff = (c >> 2) * 512u;
+                        mx = (c & 2u) ? 0x80000000u : 0u;
+                        my = ((c & 1u) && !(c & 2u)) ? 0x80000000u : 0u;
+                        aa1 = T.aa1_of_target[b.target];
+                    }
+                    t[0] = toff; t[1] = mx; t[2] = my; t[3] = 0u;
+                    double* td = reinterpret_cast<double*>(t + 4);
+                    td[0] = b.invnu;
+                    for (int q = 0; q < PB; ++q) {
+                        const cplx z = chan(aa1, q);
+                        td[1 + q * g.CS] = z.real();
+                        if (CW) td[2 + q * g.CS] = z.imag();
+                    }
+                }
+            }
+        }
+        std::vector<double> w0((size_t)PB * g.CS, 0.0);
+        if (T.has_const) for (int q = 0; q < PB; ++q) { const cplx z = chan(0, q); w0[q * g.CS] = z.real(); if (CW) w0[q * g.CS + 1] = z.imag(); }
+        StreamPass& sp = m->passes[ps];
+        sp.blocks.reserve(blocks.size() * 4 + 4096);
+        sp.tinfo.reserve(tinfo.size() * 4 + 256);
+        sp.w0.reserve(w0.size() * 8 + 64);
+        CU(cudaMemcpy(sp.blocks.p, blocks.data(), blocks.size() * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(sp.tinfo.p, tinfo.data(), tinfo.size() * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(sp.w0.p, w0.data(), w0.size() * 8, cudaMemcpyHostToDevice));
+        sp.pb0 = pb0;
+    }
     m->stream_chunks = (int)nchunks;
     m->stream_ntinfo = (int)ntinfo;
     m->stream_nf = NF;
+    m->stream_pb = PB;
     if (getenv("ACEB200_VERBOSE")) {
         size_t kept = 0, total = 0;
         for (int i = 0; i < T.nAA; ++i) { total += T.orders[i] >= 2; kept += (T.orders[i] >= 2 && keep[i]); }
-        fprintf(stderr, "[aceb200] stream: %d sub-streams x %zu chunks of %d blocks (%d leaves per block), AA functions of order >= 2 kept %zu of %zu\n",
-                kStreamWarps, nchunks, kChunkBlocks, kBlkLeaves, kept, total);
+        fprintf(stderr, "[aceb200] stream: NF=%d PB=%d CW=%d passes=%d, %d sub-streams x %zu chunks of %d blocks, AA functions of order >= 2 kept %zu of %zu, smem %zu B\n",
+                NF, PB, (int)CW, npass, kStreamWarps, nchunks, g.KB, kept, total, stream_smem(T.nS, g));
     }
 }
 
@@ -575,33 +647,50 @@ static void launch_adjoint_t(aceb200_model* m, const AdjointParams& p, int grid,
     ACE_LAUNCH(kfn, dim3(grid), dim3(32), smem, m->cur->stream, p);
 }
 
-template <int NF>
+template <int NF, int PB, bool CW>
 static void launch_stream_t(aceb200_model* m, const StreamParams& p, int grid, size_t smem)
 {
-    auto kfn = k_adjoint_stream<NF>;
+    auto kfn = k_adjoint_stream<NF, PB, CW>;
     CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ACE_LAUNCH(kfn, dim3(grid), dim3(32 * kStreamWarps), smem, m->cur->stream, p);
+}
+
+template <int NF>
+static void launch_stream_nf(aceb200_model* m, const StreamParams& p, int grid, size_t smem)
+{
+    const bool cw = m->cw;
+#define ACE_S(PBV) { if (cw) launch_stream_t<NF, PBV, true>(m, p, grid, smem); else launch_stream_t<NF, PBV, false>(m, p, grid, smem); }
+    switch (m->stream_pb) {
+    case 1: ACE_S(1) break;
+    case 2: ACE_S(2) break;
+    case 4: ACE_S(4) break;
+    default: ACE_S(8) break;
+    }
+#undef ACE_S
 }
 
 static void launch_adjoint(aceb200_model* m, long long nenv, long long ldA, bool want_D)
 {
     HostTables& T = m->T;
-    if (m->stream_chunks > 0 && !getenv("ACEB200_NO_STREAM")) {
-        StreamParams p;
-        p.nS = T.nS; p.has_const = T.has_const; p.want_D = want_D ? 1 : 0; p.nchunks = m->stream_chunks;
-        p.stream = m->d_stream.as<uint4>(); p.ctl = m->d_ctl.as<unsigned>(); p.tinfo = m->d_tinfo.as<uint4>(); p.ntinfo = m->stream_ntinfo;
-        p.w0 = T.has_const ? m->ctilde[0].real() : 0.0;
-        p.Ac = m->cur->ws_Ac.as<c2>(); p.ldA = ldA; p.Dt = m->cur->ws_Dt.as<c2>(); p.E = m->cur->ws_E.as<double>(); p.nenv = nenv;
-        const size_t smem = (size_t)(T.nS + 1) * 32 * sizeof(c2) + (size_t)kStreamWarps * (2 * kChunkBlocks * (m->stream_nf == 2 ? 3 : 4) * sizeof(uint4) + 32 * sizeof(double));
-        if (smem <= (size_t)m->smem_optin) {
-            const long long ntiles = (nenv + 31) / 32;
-            const int per_sm = std::max<int>(1, std::min<int>(32, (int)((size_t)m->smem_optin / (smem + 1024))));
-            const int grid = (int)std::min<long long>(ntiles, (long long)m->sm_count * per_sm);
-            if (m->stream_nf == 2) launch_stream_t<2>(m, p, grid, smem); else launch_stream_t<3>(m, p, grid, smem);
+    if (m->stream_chunks > 0) {
+        const HostGeom g = stream_geom(m->stream_nf, m->stream_pb, m->cw);
+        const size_t smem = stream_smem(T.nS, g);
+        const long long ntiles = (nenv + 31) / 32;
+        const int per_sm = std::max<int>(1, std::min<int>(8, (int)((size_t)m->smem_optin / (smem + 1024))));
+        const int grid = (int)std::min<long long>(ntiles, (long long)m->sm_count * per_sm);
+        for (const StreamPass& sp : m->passes) {
+            StreamParams p;
+            p.nS = T.nS; p.has_const = T.has_const; p.want_D = want_D ? 1 : 0; p.nchunks = m->stream_chunks; p.ntinfo = m->stream_ntinfo;
+            p.P = T.P; p.pb0 = sp.pb0;
+            p.stream = sp.blocks.as<uint4>(); p.ctl = m->d_ctl.as<unsigned>(); p.tinfo = sp.tinfo.as<uint4>(); p.w0 = sp.w0.as<double>();
+            p.Ac = m->cur->ws_Ac.as<c2>(); p.ldA = ldA; p.Dt = m->cur->ws_Dt.as<c2>(); p.E = m->cur->ws_E.as<double>(); p.nenv = nenv;
+            if (m->stream_nf == 2) launch_stream_nf<2>(m, p, grid, smem);
+            else if (m->stream_nf == 3) launch_stream_nf<3>(m, p, grid, smem);
+            else launch_stream_nf<4>(m, p, grid, smem);
             CU(cudaGetLastError());
             m->launches++;
-            return;
         }
+        return;
     }
     AdjointParams p;
     memset(&p, 0, sizeof(p));
@@ -972,7 +1061,8 @@ int aceb200_model_destroy(aceb200_model* m)
     if (!m) return ACEB200_OK;
     cudaSetDevice(m->device);
     for (DevBuf& b : m->pool) b.release();
-    m->d_w0.release(); m->d_w1.release(); m->d_stream.release(); m->d_ctl.release(); m->d_tinfo.release(); m->ws_err.release();
+    m->d_w0.release(); m->d_w1.release(); m->d_ctl.release(); m->ws_err.release();
+    for (StreamPass& sp : m->passes) { sp.blocks.release(); sp.tinfo.release(); sp.w0.release(); }
     for (int nu = 0; nu <= kMaxOrdDev; ++nu) m->d_lw[nu].release();
     for (Lane& L : m->lanes) L.release();
     delete m;
