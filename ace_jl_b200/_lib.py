@@ -83,6 +83,7 @@ SYMBOLS = [
     ("aceb200_eval_dB", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p]),
     ("aceb200_energy", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
     ("aceb200_energy_forces", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p]),
+    ("aceb200_adjoint_eval_d", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p]),
     ("aceb200_model_sizes", C.c_int, [C.c_void_p, C.POINTER(Sizes)]),
     ("aceb200_last_kernel_ms", C.c_int, [C.c_void_p, c_double_p]),
     ("aceb200_last_stage_ms", C.c_int, [C.c_void_p, c_double_p]),

@@ -201,6 +201,18 @@ class Handle:
         self._call("aceb200_eval_dB", b, B, dB)
         return B, dB
 
+    def adjoint_eval_d(self, b: B200Batch, w):
+        """sum_j w_j . dB_k/dr_j, complex (nenv, nB, ncomp)."""
+        if b.device:
+            w = w.contiguous().to(torch.float64)
+        else:
+            w = np.ascontiguousarray(w, dtype=np.float64)
+        if tuple(w.shape) != (b.nJ, 3):
+            raise ValueError("w must have shape (sum J, 3)")
+        out = b.empty((b.nenv, self.s.nB, self.s.ncomp), True)
+        self._call("aceb200_adjoint_eval_d", b, w, out)
+        return out
+
     def energy(self, b: B200Batch):
         E = b.empty((b.nenv, self.s.nprop, self.s.ncomp), not self.s.symreal)
         self._call("aceb200_energy", b, E)
@@ -394,6 +406,15 @@ class LinearACEModel:
             G = G[:, 0]
         return self._shape_val(E, single), G
 
+    def adjoint_EVAL_D(self, cfg, w):
+        """src/linearmodel.jl:133-134 -> src/evaluator.jl:204-244: dB_k = sum_j w_j . dB_k/dr_j."""
+        b, single = _as_batch(self, cfg)
+        h = self.evaluator.handle
+        out = _squeeze_prop(h.adjoint_eval_d(b, w), h.s.ncomp)
+        if h.s.ncomp == 1:
+            out = out.real
+        return out[0] if single else out
+
     def grad_params(self, cfg):
         """src/linearmodel.jl:114-123: the basis values."""
         return evaluate(self.basis, cfg)
@@ -413,6 +434,10 @@ def grad_params(model: LinearACEModel, cfg):
 
 def grad_params_config(model: LinearACEModel, cfg):
     return model.grad_params_config(cfg)
+
+
+def adjoint_EVAL_D(model: LinearACEModel, cfg, w):
+    return model.adjoint_EVAL_D(cfg, w)
 
 
 def set_params(model: LinearACEModel, c):

@@ -766,6 +766,157 @@ __global__ void k_B(long long nenv, int nB, int nAA, int ncomp, const int* ptr, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// adjoint_EVAL_D (src/evaluator.jl:204-244): dB_k = sum_j w_j . dB_k/dr_j without forming any Jacobian
+// ------------------------------------------------------------------------------------------------
+// Step 1 pools  dAw_s = sum_j w_j . grad phi_s(r_j)  exactly like k_pool pools A: with
+//   w . grad(R_n Y_lm) = (R_n' w.rhat) Y_lm + R_n (w . grad Y_lm),   w . grad Y = ep (dP w_theta + i m Pt w_phi)
+// two radial and two angular rows are staged per neighbour.  w is real, so dAw has the same m -> -m symmetry as A
+// and lives in the same canonical slots.
+struct PoolWParams {
+    RadialParams rp;
+    AlpParams ap;
+    ColumnsDev C;
+    BatchDev B;
+    const double* W;        // [neighbour][3], indexed like R
+    c2* Aw;                 // [nS][ldA]
+    long long ldA;
+    int TE, nP;
+};
+
+template <int NMAX, bool SPECIES>
+__global__ void __launch_bounds__(kPoolThreads) k_pool_w(const PoolWParams p)
+{
+    ACE_DYN_SMEM(c2, smem);
+    c2* SY = smem;                                                             // [2 nP][129]: Y, w.grad Y
+    double* SR = reinterpret_cast<double*>(SY + (size_t)2 * p.nP * kPoolPitch); // [2 N][129]: R' w.rhat, R
+    int* sq = reinterpret_cast<int*>(SR + (size_t)2 * p.rp.N * kPoolPitch);
+    int* joff = sq + kPoolThreads;
+    const int tid = threadIdx.x;
+    const int N = p.rp.N, nS = p.C.nS, nP = p.nP;
+    const long long e0 = (long long)blockIdx.x * p.TE;
+    if (e0 >= p.B.nenv) return;
+    const int ne = (int)((p.B.nenv - e0) < p.TE ? (p.B.nenv - e0) : p.TE);
+    const long long jbeg = p.B.off[e0];
+    if (tid <= ne) joff[tid] = (int)(p.B.off[e0 + tid] - jbeg);
+    const double* Rb = p.B.R + 3 * (jbeg - p.B.jbase);
+    const double* Wb = p.W + 3 * (jbeg - p.B.jbase);
+    const int* spb = SPECIES ? p.B.species + (jbeg - p.B.jbase) : nullptr;
+    __syncthreads();
+    c2 acc[kPoolItems];
+#pragma unroll
+    for (int it = 0; it < kPoolItems; ++it) acc[it] = c2{0.0, 0.0};
+    int e = 0, j0 = 0;
+    while (e < ne) {
+        const int jend_e = joff[e + 1];
+        int e2 = e + 1, j1;
+        bool done_e;
+        if (j0 == joff[e] && jend_e - j0 <= kPoolThreads) {
+            while (e2 < ne && joff[e2 + 1] - j0 <= kPoolThreads && (e2 + 1 - e) * nS <= kPoolThreads * kPoolItems) ++e2;
+            j1 = joff[e2];
+            done_e = true;
+        } else {
+            j1 = (j0 + kPoolThreads < jend_e) ? j0 + kPoolThreads : jend_e;
+            done_e = (j1 == jend_e);
+        }
+        const int nrows = j1 - j0;
+        if (tid < nrows) {
+            const int j = j0 + tid;
+            const double x = Rb[3 * j], y = Rb[3 * j + 1], z = Rb[3 * j + 2];
+            const double wx = Wb[3 * j], wy = Wb[3 * j + 1], wz = Wb[3 * j + 2];
+            if (SPECIES) { int q = spb[j] - 1; if (q < 0 || q >= p.C.nQ) q = 0; sq[tid] = q; }
+            const Spher sp = cart2spher(x, y, z);
+            double Rn[NMAX], dRn[NMAX];
+            radial_ed<NMAX>(p.rp, sp.r, Rn, dRn);
+            const double wr = (wx * x + wy * y + wz * z) * sp.rinv;                                     // w . rhat
+            const double wphi = (-sp.sphi * wx + sp.cphi * wy) * sp.rinv;
+            const double wth = (sp.cphi * sp.cth * wx + sp.sphi * sp.cth * wy - sp.sth * wz) * sp.rinv;
+#pragma unroll
+            for (int n = 0; n < NMAX; ++n)
+                if (n < N) { SR[n * kPoolPitch + tid] = dRn[n] * wr; SR[(N + n) * kPoolPitch + tid] = Rn[n]; }
+            for_each_lm_ed(p.ap, sp, [&](int l, int m, double Pt, double dP, double epr, double epi) {
+                const int ip = index_p(l, m);
+                const double f0 = (m == 0) ? Pt : Pt * sp.sth;
+                SY[ip * kPoolPitch + tid] = c2{epr * f0, epi * f0};
+                const double gr = dP * wth, gi = (double)m * Pt * wphi;          // (gr + i gi) * ep
+                SY[(nP + ip) * kPoolPitch + tid] = c2{epr * gr - epi * gi, epr * gi + epi * gr};
+            });
+        }
+        __syncthreads();
+        const int nitems = (e2 - e) * nS;
+#pragma unroll
+        for (int it = 0; it < kPoolItems; ++it) {
+            const int idx = tid + it * kPoolThreads;
+            if (idx < nitems) {
+                const int el = idx / nS, s = idx - el * nS;
+                const int n = __ldg(p.C.slot_n + s), ip = __ldg(p.C.slot_ip + s), q = SPECIES ? __ldg(p.C.slot_q + s) : 0;
+                int ra = joff[e + el] - j0, rb = joff[e + el + 1] - j0;
+                if (ra < 0) ra = 0;
+                if (rb > nrows) rb = nrows;
+                const double* pr1 = SR + n * kPoolPitch; const double* pr2 = SR + (N + n) * kPoolPitch;
+                const c2* py1 = SY + ip * kPoolPitch; const c2* py2 = SY + (nP + ip) * kPoolPitch;
+                c2 a = acc[it];
+                for (int r = ra; r < rb; ++r) {
+                    if (SPECIES && sq[r] != q) continue;
+                    const double r1 = pr1[r], r2 = pr2[r];
+                    const c2 y1 = py1[r], y2 = py2[r];
+                    a.x += r1 * y1.x + r2 * y2.x;
+                    a.y += r1 * y1.y + r2 * y2.y;
+                }
+                if (done_e) { p.Aw[(size_t)s * p.ldA + (e0 + e + el)] = a; a = c2{0.0, 0.0}; }
+                acc[it] = a;
+            }
+        }
+        __syncthreads();
+        j0 = j1;
+        if (done_e) e = e2;
+    }
+}
+
+// dAAw[e][i] = real?( sum_t dAw[v_t] prod_{s != t} A[v_s] )   (src/evaluator.jl:228-235)
+__global__ void k_AAw(long long nenv, int nA, int nAA, int maxord, const int* orders, const int* spec,
+                      const c2* A, const c2* Aw, int symreal, double* out)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nenv * nAA) return;
+    const long long e = t / nAA;
+    const int i = (int)(t % nAA);
+    const c2* Ae = A + (size_t)e * nA;
+    const c2* We = Aw + (size_t)e * nA;
+    const int o = __ldg(orders + i);
+    int v[8];
+    c2 adj[8];
+    for (int k = 0; k < o; ++k) v[k] = __ldg(spec + (size_t)i * maxord + k);
+    c2 run = c2{1.0, 0.0};
+    for (int k = 0; k < o; ++k) { adj[k] = run; run = cmul(run, Ae[v[k]]); }
+    run = c2{1.0, 0.0};
+    for (int k = o - 1; k >= 0; --k) { adj[k] = cmul(adj[k], run); run = cmul(run, Ae[v[k]]); }
+    c2 acc = c2{0.0, 0.0};
+    for (int k = 0; k < o; ++k) { const c2 m = cmul(adj[k], We[v[k]]); acc.x += m.x; acc.y += m.y; }
+    if (symreal) acc.y = 0.0;
+    out[2 * t] = acc.x; out[2 * t + 1] = acc.y;
+}
+
+// out[e][row][c] = sum_k A2B[row,k][c] * dAAw[e][col_k]   (dB = A2Bmap * dAAw, src/evaluator.jl:237); complex
+__global__ void k_Bw(long long nenv, int nB, int nAA, int ncomp, const int* ptr, const int* col, const c2* val,
+                     const double* AAw, double* out)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nenv * nB * ncomp) return;
+    const int c = (int)(t % ncomp);
+    const int row = (int)((t / ncomp) % nB);
+    const long long e = t / ((long long)ncomp * nB);
+    double br = 0.0, bi = 0.0;
+    for (int k = __ldg(ptr + row); k < __ldg(ptr + row + 1); ++k) {
+        const c2 v = val[(size_t)k * ncomp + c];
+        const size_t ia = (size_t)e * nAA + __ldg(col + k);
+        const double ar = AAw[2 * ia], ai = AAw[2 * ia + 1];
+        br += v.x * ar - v.y * ai;
+        bi += v.x * ai + v.y * ar;
+    }
+    out[2 * t] = br; out[2 * t + 1] = bi;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Jacobian kernels (evaluate_d / evaluate_ed)
 // ------------------------------------------------------------------------------------------------
 struct dAParams {

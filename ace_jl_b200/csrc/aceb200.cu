@@ -72,7 +72,7 @@ constexpr int kLanes = 3;
 
 struct Lane {
     DevBuf ws_Ac, ws_Dt, ws_E, ws_G, ws_A, ws_AA, ws_dA, ws_dAA, ws_out;
-    DevBuf in_off, in_R, in_sp;
+    DevBuf in_off, in_R, in_sp, in_w, ws_Aw, ws_A2;
     cudaStream_t stream = nullptr;       // the stream this lane currently launches on
     cudaStream_t own_stream = nullptr;   // private non-blocking stream (host-batch pipeline)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
@@ -80,7 +80,7 @@ struct Lane {
     bool timed_ef = false;
     void release()
     {
-        DevBuf* bufs[] = {&ws_Ac, &ws_Dt, &ws_E, &ws_G, &ws_A, &ws_AA, &ws_dA, &ws_dAA, &ws_out, &in_off, &in_R, &in_sp};
+        DevBuf* bufs[] = {&ws_Ac, &ws_Dt, &ws_E, &ws_G, &ws_A, &ws_AA, &ws_dA, &ws_dAA, &ws_out, &in_off, &in_R, &in_sp, &in_w, &ws_Aw, &ws_A2};
         for (DevBuf* b : bufs) b->release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -639,6 +639,42 @@ static void launch_pool(aceb200_model* m, const BatchDev& B, long long ldA)
     m->launches++;
 }
 
+template <int NMAX>
+static void launch_pool_w_t(aceb200_model* m, const PoolWParams& p, dim3 grid, size_t smem)
+{
+    if (p.B.species) {
+        auto kfn = k_pool_w<NMAX, true>;
+        CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ACE_LAUNCH(kfn, grid, dim3(kPoolThreads), smem, m->cur->stream, p);
+        return;
+    }
+    auto kfn = k_pool_w<NMAX, false>;
+    CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ACE_LAUNCH(kfn, grid, dim3(kPoolThreads), smem, m->cur->stream, p);
+}
+
+static void launch_pool_w(aceb200_model* m, const BatchDev& B, const double* W, long long ldA)
+{
+    HostTables& T = m->T;
+    PoolWParams p;
+    p.rp = m->rp; p.ap = m->ap; p.C = m->C; p.B = B; p.W = W;
+    p.Aw = m->cur->ws_Aw.as<c2>(); p.ldA = ldA; p.TE = 8;
+    p.nP = (T.Lused + 1) * (T.Lused + 2) / 2;
+    const size_t smem = (size_t)2 * kPoolPitch * (p.nP * sizeof(c2) + m->rp.N * sizeof(double)) + (kPoolThreads + kPoolTEmax + 1) * sizeof(int);
+    dim3 grid((unsigned)((B.nenv + p.TE - 1) / p.TE));
+    switch (m->NMAX) {
+    case 4: launch_pool_w_t<4>(m, p, grid, smem); break;
+    case 8: launch_pool_w_t<8>(m, p, grid, smem); break;
+    case 12: launch_pool_w_t<12>(m, p, grid, smem); break;
+    case 16: launch_pool_w_t<16>(m, p, grid, smem); break;
+    case 20: launch_pool_w_t<20>(m, p, grid, smem); break;
+    case 24: launch_pool_w_t<24>(m, p, grid, smem); break;
+    default: launch_pool_w_t<32>(m, p, grid, smem); break;
+    }
+    CU(cudaGetLastError());
+    m->launches++;
+}
+
 template <int PB, bool CW>
 static void launch_adjoint_t(aceb200_model* m, const AdjointParams& p, int grid, size_t smem)
 {
@@ -802,9 +838,11 @@ static void deliver(aceb200_model* m, const aceb200_batch* b, void* user, const 
 // ----------------------------------------------------------------------------------------------
 // the evaluation driver
 // ----------------------------------------------------------------------------------------------
-enum Want { W_A = 1, W_AA = 2, W_B = 4, W_dA = 8, W_dAA = 16, W_dB = 32, W_E = 64, W_G = 128 };
+enum Want { W_A = 1, W_AA = 2, W_B = 4, W_dA = 8, W_dAA = 16, W_dB = 32, W_E = 64, W_G = 128, W_ADJ = 256 };
 
 struct Outputs {
+    const double* w = nullptr;      // adjoint_EVAL_D: [sum J][3], same space as the batch
+    double* adj = nullptr;          // adjoint_EVAL_D: [nenv][nB][ncomp] complex
     double *A = nullptr, *AA = nullptr, *B = nullptr, *dA = nullptr, *dAA = nullptr, *dB = nullptr, *E = nullptr, *G = nullptr;
 };
 
@@ -837,7 +875,7 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
     std::lock_guard<std::mutex> lock(m->mu);
     const int P = T.P, nA = T.nA, nAA = T.nAA, nB = T.nB, ncomp = T.ncomp;
     const int ca = T.pireal ? 1 : 2, cs = T.symreal ? 1 : 2;
-    const bool need_full_A = want & (W_A | W_AA | W_B | W_dA | W_dAA | W_dB);
+    const bool need_full_A = want & (W_A | W_AA | W_B | W_dA | W_dAA | W_dB | W_ADJ);
     const bool need_AA = want & (W_AA | W_B | W_dAA | W_dB);
     const bool need_dA = want & (W_dA | W_dAA | W_dB);
     const bool need_dAA = want & (W_dAA | W_dB);
@@ -861,6 +899,7 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
     if (need_dA) per_env += (size_t)(Jav * nA * 48.0);
     if (need_dAA) per_env += (size_t)(Jav * nAA * 24.0 * ca);
     if (want & W_dB) per_env += (size_t)(Jav * nB * 24.0 * ncomp * cs);
+    if (want & W_ADJ) per_env += (size_t)T.nS * 16 + (size_t)nA * 16 + (size_t)nAA * 16 + (size_t)nB * ncomp * 16 + (size_t)(Jav * 24.0);
     if (host) per_env += (size_t)(Jav * 28.0) + 8;
     long long step = chunk_envs(b->nenv, per_env, (size_t)8 << 30);
     if (host) {
@@ -920,6 +959,36 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
             { auto kfn = k_expand_A;
               ACE_LAUNCH(kfn, dim3(blocks_for(ne * nA, 256)), dim3(256), 0, L.stream, ne, nA, m->d_code, L.ws_Ac.as<c2>(), ldA, L.ws_A.as<c2>());
               CU(cudaGetLastError()); m->launches++; }
+            if (want & W_ADJ) {
+                // adjoint_EVAL_D: pool dAw like A, contract through the product basis, apply A2Bmap
+                const double* Wdev = nullptr;
+                if (!host) Wdev = o.w + 3 * c.j0;
+                else {
+                    L.in_w.reserve(std::max<long long>(nj, 1) * 3 * sizeof(double));
+                    if (nj > 0) CU(cudaMemcpyAsync(L.in_w.p, o.w + 3 * c.j0, nj * 3 * sizeof(double), cudaMemcpyHostToDevice, L.stream));
+                    Wdev = L.in_w.as<double>();
+                }
+                L.ws_Aw.reserve((size_t)T.nS * ldA * sizeof(c2));
+                L.ws_A2.reserve((size_t)ne * nA * sizeof(c2));
+                L.ws_AA.reserve((size_t)ne * nAA * 16);
+                L.ws_out.reserve((size_t)ne * nB * ncomp * 16);
+                launch_pool_w(m, B, Wdev, ldA);
+                { auto kfn = k_expand_A;
+                  ACE_LAUNCH(kfn, dim3(blocks_for(ne * nA, 256)), dim3(256), 0, L.stream, ne, nA, m->d_code, (const c2*)L.ws_Aw.as<c2>(), ldA, L.ws_A2.as<c2>());
+                  CU(cudaGetLastError()); m->launches++; }
+                { auto kfn = k_AAw;
+                  ACE_LAUNCH(kfn, dim3(blocks_for(ne * nAA, 128)), dim3(128), 0, L.stream, ne, nA, nAA, std::max(1, T.maxord), m->d_orders, m->d_spec,
+                             (const c2*)L.ws_A.as<c2>(), (const c2*)L.ws_A2.as<c2>(), T.symreal, L.ws_AA.as<double>());
+                  CU(cudaGetLastError()); m->launches++; }
+                if (nB > 0) { auto kfn = k_Bw;
+                  ACE_LAUNCH(kfn, dim3(blocks_for(ne * nB * ncomp, 256)), dim3(256), 0, L.stream, ne, nB, nAA, ncomp, m->d_csr_ptr, m->d_csr_col, m->d_csr_val,
+                             (const double*)L.ws_AA.as<double>(), L.ws_out.as<double>());
+                  CU(cudaGetLastError()); m->launches++; }
+                CU(cudaEventRecord(L.ev1, L.stream));
+                deliver(m, b, o.adj + (size_t)c.e0 * nB * ncomp * 2, L.ws_out.p, (size_t)ne * nB * ncomp * 16);
+                L.busy = true;
+                continue;
+            }
             if (need_AA) {
                 L.ws_AA.reserve((size_t)ne * nAA * 8 * ca);
                 AA_dev = L.ws_AA.as<double>();
@@ -1168,6 +1237,9 @@ int aceb200_eval_dAA(aceb200_model* m, const aceb200_batch* b, double* AA, doubl
 
 int aceb200_eval_dB(aceb200_model* m, const aceb200_batch* b, double* B, double* dB)
 { API_BEGIN NEED(m, b); Outputs o; o.B = B; o.dB = dB; run(m, b, W_dB | (B ? W_B : 0), o); API_END }
+
+int aceb200_adjoint_eval_d(aceb200_model* m, const aceb200_batch* b, const double* w, double* out)
+{ API_BEGIN NEED(m, b); if (!w || !out) throw ModelError(ACEB200_EDESC, "null argument"); Outputs o; o.w = w; o.adj = out; run(m, b, W_ADJ, o); API_END }
 
 int aceb200_energy(aceb200_model* m, const aceb200_batch* b, double* E)
 { API_BEGIN NEED(m, b); Outputs o; o.E = E; run(m, b, W_E, o); API_END }

@@ -173,6 +173,11 @@ int aceb200_energy(aceb200_model *m, const aceb200_batch *b, double *E);
  * real if symreal else complex; E may be NULL */
 int aceb200_energy_forces(aceb200_model *m, const aceb200_batch *b, double *E, double *G);
 /* grad_params(m, cfg) (src/linearmodel.jl:114-123) is eval_B; grad_params_config (:127) is eval_dB. */
+/* adjoint_EVAL_D(m, cfg, w) (src/evaluator.jl:204-244; src/linearmodel.jl:133-134):
+ * out_k = A2Bmap * real?( sum_t (sum_j w_j . grad phi_{v_t}(r_j)) prod_{s != t} A_{v_s} ), i.e. sum_j w_j . dB_k/dr_j
+ * without forming a Jacobian.  w: [sum J][3] real (DState rr per neighbour), in the batch's memory space;
+ * out: [nenv][nB][ncomp] complex. */
+int aceb200_adjoint_eval_d(aceb200_model *m, const aceb200_batch *b, const double *w, double *out);
 
 /* ---- introspection (sizes the host needs to allocate outputs) ------------------------------ */
 typedef struct aceb200_sizes {

@@ -810,6 +810,42 @@ int oracle_naive_energy_forces(const aceb200_desc *d, const aceb200_batch *b, co
     OMP_ENV_LOOP_END
 }
 
+/* adjoint_EVAL_D(m, V::ProductEvaluator, cfg, w), src/evaluator.jl:204-244.
+ * w: [neighbour][3] real; out: [nenv][nB][ncomp] complex */
+int oracle_adjoint_eval_d(const aceb200_desc *d, const aceb200_batch *b, const double *w, double *out)
+{
+    OMP_ENV_LOOP_BEGIN
+        int J = (int)(b->offsets[e + 1] - b->offsets[e]);
+        scratch_need_dA(&s, d, J);
+        rc = eval_A_dA_env(d, &s, b, e, s.A, s.dA);           /* [1] */
+        if (!rc) {
+            cplx *dAw = (cplx *)calloc(d->nA, sizeof(cplx));
+            cplx *dAAw = (cplx *)calloc(d->nAA, sizeof(cplx));
+            const double *we = w + 3 * b->offsets[e];
+            for (int k = 0; k < d->nA; k++)
+                for (int j = 0; j < J; j++)
+                    for (int x = 0; x < 3; x++) dAw[k] += we[3 * j + x] * s.dA[3 * ((size_t)d->nA * j + k) + x];   /* contract: no conjugation */
+            int i0 = (d->nAA > 0 && d->orders[0] == 0) ? 1 : 0;    /* [2] */
+            for (int i = i0; i < d->nAA; i++) {
+                int ord = d->orders[i];
+                AA_local_adjoints(d, s.A, i, ord, s.dAAdA);
+                for (int t = 0; t < ord; t++) {
+                    cplx v = dAw[IAA(d, i, t) - 1] * s.dAAdA[t];
+                    dAAw[i] += d->symreal ? (cplx)creal(v) : v;
+                }
+            }
+            const cplx *nz = (const cplx *)d->nzval;              /* [3] dB = A2Bmap * dAAw */
+            cplx *o = (cplx *)out + (size_t)e * d->nB * d->ncomp;
+            for (size_t k = 0; k < (size_t)d->nB * d->ncomp; k++) o[k] = 0;
+            for (int col = 0; col < d->nAA; col++)
+                for (int k = d->colptr[col] - 1; k < d->colptr[col + 1] - 1; k++)
+                    for (int c = 0; c < d->ncomp; c++)
+                        o[(size_t)(d->rowval[k] - 1) * d->ncomp + c] += nz[(size_t)k * d->ncomp + c] * dAAw[col];
+            free(dAw); free(dAAw);
+        }
+    OMP_ENV_LOOP_END
+}
+
 void oracle_set_threads(int n)
 {
 #ifdef _OPENMP

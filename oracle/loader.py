@@ -184,6 +184,13 @@ class Oracle:
                    E.ctypes.data_as(C.c_void_p), G.ctypes.data_as(C.c_void_p))
         return E, G
 
+    def adjoint_eval_d(self, R, offsets, w, species=None):
+        b, keep = self._batch(R, offsets, species)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        out = np.zeros((b.nenv, self.d.nB, self.d.ncomp), dtype=np.complex128)
+        self._call("oracle_adjoint_eval_d", C.byref(self.d), C.byref(b), _dp(w), out.ctypes.data_as(C.c_void_p))
+        return out
+
     def naive_energy_forces(self, R, offsets, species=None):
         b, keep = self._batch(R, offsets, species)
         nj = int(keep[1][-1])

@@ -34,6 +34,8 @@ def compare_all(basis, nprop, Js, seed=7, jacobians=True, tol=TOL):
     Eo, Go = o.energy_forces(R, off, sp)
     errs["E"], errs["G"] = relerr(E, Eo), relerr(G, Go)
     errs["E_only"] = relerr(h.energy(b), Eo)
+    w = rng.standard_normal((len(R), 3))
+    errs["adjoint_EVAL_D"] = relerr(h.adjoint_eval_d(b, w), o.adjoint_eval_d(R, off, w, sp))
     if jacobians:
         A, dA = h.eval_dA(b)
         Ao, dAo = o.eval_dA(R, off, sp)

@@ -108,6 +108,18 @@ def test_reference_api_surface():
     assert relerr(model.evaluator.coeffs, Oracle(basis_descriptor(basis, c2.reshape(-1, 1))).eff_coeffs()) < 1e-14
 
 
+def test_adjoint_eval_d_api():
+    """adjoint_EVAL_D(model, cfg, w) (src/linearmodel.jl:133-134): equals sum_j w_j . dB_k/dr_j for an invariant model."""
+    basis = make_basis("inv_simple_3_6")
+    rng = philox(36)
+    model = ace.LinearACEModel(basis, rng.random(len(basis)) - 0.5)
+    R, off, _ = rand_envs(rng, rn_of(basis), 1, 14)
+    w = rng.standard_normal((14, 3))
+    got = ace.adjoint_EVAL_D(model, ace.ACEConfig(R), w)
+    dB = ace.evaluate_d(basis, ace.ACEConfig(R))                       # (J, nB, 3)
+    assert got.shape == (len(basis),) and relerr(got, np.einsum("jx,jkx->k", w, dB)) < 1e-11
+
+
 def test_multiproperty_matches_single_property_models():
     """property i of an N-property model == the single-property model with c[:, i] (test_multiprop.jl:24-92)."""
     for kind in ("inv_simple_3_6", "euclvec_3_5"):

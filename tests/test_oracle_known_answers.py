@@ -228,3 +228,22 @@ def test_equivariance(kind, zoo):
             M = np.einsum("ai,enab,bj->enij", Q, M, Q)
             back = M.transpose(0, 1, 3, 2).reshape(Bq.shape)
         assert relerr(back, B) < 1e-10
+
+
+@pytest.mark.parametrize("kind", ["inv_simple_3_6", "species_3_5", "inv_sparse_4_8"])
+def test_adjoint_eval_d_equals_contracted_jacobian(kind, zoo):
+    """adjoint_EVAL_D(w)_k = sum_j w_j . dB_k/dr_j: the product-evaluator shortcut equals the naive evaluator's
+    formula (src/linearmodel.jl:160-169; test/test_admodel.jl uses it through the rrule).  Invariant properties only:
+    the reference takes the real part *before* applying a complex A2Bmap (src/evaluator.jl:233), so for equivariant
+    properties its two evaluators are not the same function; the GPU path follows the product evaluator."""
+    basis = zoo(kind)
+    o = Oracle(basis_descriptor(basis, None))
+    rng = philox(12)
+    R, off, sp = rand_envs(rng, rn_of(basis), 3, [4, 11, 19], nspecies_of(basis))
+    w = rng.standard_normal((len(R), 3))
+    adj = o.adjoint_eval_d(R, off, w, sp)
+    _, dB = o.eval_dB(R, off, sp)                       # (sum J, nB, 3, ncomp)
+    for e in range(3):
+        ref = np.einsum("jx,jkxc->kc", w[off[e]:off[e + 1]], dB[off[e]:off[e + 1]])
+        got = adj[e].real if basis.real else adj[e]
+        assert relerr(got, ref) < 1e-11
