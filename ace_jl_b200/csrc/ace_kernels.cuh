@@ -636,7 +636,7 @@ __device__ __forceinline__ void column_dot(const c2* D, int cnt, const double (&
 // ([slot][channel][local env]) together with the (species, l, m) -> column table and the environments'
 // neighbour offsets, then runs one thread per neighbour of those environments.
 template <int NMAX, int PB, bool SPECIES>
-__global__ void __launch_bounds__(kForceThreads) k_forces(const ForceParams p)
+__global__ void __launch_bounds__(kForceThreads, 5) k_forces(const ForceParams p)
 {
     ACE_DYN_SMEM(c2, Ds);   // [nS][PB][kForceTE], then int colinfo[nQ * nPused], int joff[kForceTE + 1]
     constexpr int TE = kForceTE;

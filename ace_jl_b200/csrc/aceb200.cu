@@ -68,7 +68,7 @@ static T* upload(std::vector<DevBuf>& pool, const std::vector<T>& v)
 // ----------------------------------------------------------------------------------------------
 // the model handle
 // ----------------------------------------------------------------------------------------------
-constexpr int kLanes = 3;
+constexpr int kLanes = 4;
 
 struct Lane {
     DevBuf ws_Ac, ws_Dt, ws_E, ws_G, ws_A, ws_AA, ws_dA, ws_dAA, ws_out;
@@ -882,7 +882,8 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
     const bool host = b->space == ACEB200_HOST;
 
     // lanes: a device-resident batch runs on the caller's stream; a host-resident batch is pipelined
-    const int nlanes = host ? kLanes : 1;
+    int nlanes = host ? kLanes : 1;
+    if (host) if (const char* ov = getenv("ACEB200_LANES")) nlanes = std::max(1, std::min(kLanes, atoi(ov)));
     for (int l = 0; l < kLanes; ++l) { m->lanes[l].stream = host ? m->lanes[l].own_stream : m->user_stream; m->lanes[l].busy = false; }
     m->cur = &m->lanes[0];
 
@@ -904,7 +905,9 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
     long long step = chunk_envs(b->nenv, per_env, (size_t)8 << 30);
     if (host) {
         // pipeline granularity: a few MiB of positions per chunk, at least ~6 chunks when the batch is large
-        long long pipe = std::max<long long>(4096, (long long)((32.0 * 1048576.0) / (24.0 * Jav)));
+        double pipe_mb = 16.0;
+        if (const char* ov = getenv("ACEB200_PIPE_MB")) pipe_mb = std::max(1.0, atof(ov));
+        long long pipe = std::max<long long>(4096, (long long)((pipe_mb * 1048576.0) / (24.0 * Jav)));
         pipe = std::min<long long>(pipe, std::max<long long>(4096, (b->nenv + 5) / 6));
         step = std::min<long long>(step, ((pipe + 31) / 32) * 32);
     }

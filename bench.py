@@ -255,7 +255,7 @@ def main():
     Eh = torch.empty((nenv, 1, 1), dtype=torch.float64).pin_memory()
     Gh = torch.empty((nenv * J, 1, 3, 1), dtype=torch.float64).pin_memory()
     hb = ace.B200Batch(Rh.numpy(), offh.numpy())
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(args.steps, 10))
     h.energy_forces(hb, Eh.numpy(), Gh.numpy())
     barrier()
     t0 = time.perf_counter()
@@ -282,6 +282,15 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/), per launch
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            kname = {"pool": "k_pool", "adjoint": "k_adjoint_stream", "forces": "k_forces"}[dom]
+            t = tr[kname]
+            traffic = (t["dram_read_bytes"] + t["dram_write_bytes"]) * nenv / t["envs_per_launch"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -290,7 +299,9 @@ def main():
             "roofline": {
                 "bound": "fp64", "kernel": {"pool": "k_pool", "adjoint": "k_adjoint", "forces": "k_forces"}[dom],
                 "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak if fp64_peak else None,
-                "traffic": None,
+                "traffic": traffic,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/r1_traffic.json (includes the "
+                                  "[slot][env] workspace the three kernels exchange: 1.2 KB/env each way)",
                 "peak_source": "FP64 FMA probe run in this process (MEASURED_PEAKS.json holds no FP64 figure)",
                 "algorithmic_flops_per_env": flops, "ms_per_launch": per_launch_ms,
                 "whole_step_tflops": tot_flops * nenv / (total_ms / args.steps * 1e-3) / 1e12,

@@ -60,6 +60,8 @@ def make_basis(kind: str):
         RnYlm = RnYlm_1pbasis(maxdeg=5, maxL=4)
         B1p = ace.Product1pBasis((ace.Categorical1pBasis(["a", "b", "c", "d"], varsym="mu", idxsym="q"),) + RnYlm.bases)
         return ace.SymmetricBasis(ace.Invariant(), B1p, Bsel)
+    if kind == "inv_complexB_2_5":       # SymmetricBasis(...; isreal = false): B, dB stay complex (symmbasis.jl:84-86)
+        return ace.SymmetricBasis(ace.Invariant(), RnYlm_1pbasis(maxdeg=5), ace.SimpleSparseBasis(2, 5), isreal=False)
     if kind == "inv_morse_2_6":
         return ace.SymmetricBasis(ace.Invariant(), RnYlm_1pbasis(maxdeg=6, trans=ace.morsetransform(1.3, 1.1), pin=2),
                                   ace.SimpleSparseBasis(2, 6))

@@ -34,6 +34,7 @@ CASES = [
     ("species_3_5", 16, [5, 40, 33, 130]),                  # config 5's family: 16 properties, 4 species
     ("inv_morse_2_6", 1, [6, 20]),
     ("inv_agnesi_2_6", 1, [6, 20]),
+    ("inv_complexB_2_5", 1, [6, 20, 33]),                   # complex B / dB outputs (symreal = false)
 ]
 
 
@@ -171,6 +172,27 @@ def test_edge_cases():
         hs.energy(ace.B200Batch(R, off, np.array([1, 2, 3, 4, 5, 1], dtype=np.int32)))
     assert ei.value.code == -6
     assert h.launch_count() > 0 and h.last_kernel_ms() >= 0.0
+
+
+def test_concurrent_calls_on_one_handle():
+    """Several host threads may evaluate on one handle (the reference's per-thread pools, src/utils/pools.jl:44-75)."""
+    import threading
+    basis = make_basis("inv_sparse_3_10")
+    rng = philox(37)
+    h = ace.LinearACEModel(basis, rng.random(len(basis)) - 0.5).evaluator.handle
+    batches = [rand_envs(rng, rn_of(basis), 500 + 37 * k, 20 + k)[:2] for k in range(6)]
+    ref = [h.energy_forces(ace.B200Batch(R, off)) for R, off in batches]
+    out = [None] * len(batches)
+
+    def work(k):
+        for _ in range(5):
+            out[k] = h.energy_forces(ace.B200Batch(*batches[k]))
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(len(batches))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for k in range(len(batches)):
+        assert np.array_equal(out[k][0], ref[k][0]) and np.array_equal(out[k][1], ref[k][1])
 
 
 def test_finite_difference_forces():
