@@ -432,28 +432,37 @@ __device__ __forceinline__ double xor_hi(double v, unsigned mask)
 #endif
 }
 
-// One CTA = kStreamWarps warps sharing one shared-memory tile of A (32 environments, one per lane).  The
+// One CTA = kStreamWarps warps sharing one shared-memory tile of A (32 * EPL environments, EPL per lane).  The
 // host splits the targets into kStreamWarps balanced sub-streams; warp w walks sub-stream w.  More warps
-// per byte of shared memory is what hides the FP64 and shared-memory latencies of the leaf products.
-template <int NF, int PB, bool CW>
+// per byte of shared memory is what hides the FP64 and shared-memory latencies of the leaf products; EPL = 2
+// amortises the (warp-uniform) record decode over two environments and doubles the independent work per lane.
+template <int NF, int PB, bool CW, int EPL>
 __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const StreamParams p)
 {
     typedef StreamGeom<NF, PB, CW> G;
     constexpr int CS = G::CS, CH = G::CH, QBP = G::QBP, KB = G::KB, LPC = G::LPC, TIQ = G::TIQ;
-    ACE_DYN_SMEM(c2, As);                                       // [nS + 1][32]; slot nS holds 1
-    uint4* rings = reinterpret_cast<uint4*>(As + (size_t)(p.nS + 1) * 32);   // [kStreamWarps][2][CH]
+    constexpr int TW = 32 * EPL;                                // environments per tile
+    constexpr int RSH = (EPL == 1) ? 9 : 10;                    // log2 of the tile row pitch in bytes
+    ACE_DYN_SMEM(c2, As);                                       // [nS + 1][TW]; slot nS holds 1
+    uint4* rings = reinterpret_cast<uint4*>(As + (size_t)(p.nS + 1) * TW);   // [kStreamWarps][2][CH]
     double* Epart = reinterpret_cast<double*>(rings);            // aliases the rings once the stream is consumed
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4* ring = rings + warp * 2 * CH;
     const uint4* stream = p.stream + (size_t)warp * p.nchunks * CH;
     const unsigned* ctl = p.ctl + (size_t)warp * p.nchunks * KB;
     const uint4* tinfo = p.tinfo + (size_t)warp * p.ntinfo * TIQ;
-    const unsigned char* Ab = reinterpret_cast<const unsigned char*>(As) + lane * 16;   // this lane's column
-    const long long ntiles = (p.nenv + 31) / 32;
+    const unsigned char* Ab = reinterpret_cast<const unsigned char*>(As) + lane * 16;   // this lane's first column
+    const long long ntiles = (p.nenv + TW - 1) / TW;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long e = tile * 32 + lane;
-        for (int s = warp; s < p.nS; s += kStreamWarps) As[s * 32 + lane] = p.Ac[(size_t)s * p.ldA + e];
-        if (warp == 0) As[p.nS * 32 + lane] = c2{1.0, 0.0};
+        const long long e = tile * TW + lane;                   // environments e, e + 32, ...
+        for (int s = warp; s < p.nS; s += kStreamWarps) {
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) As[s * TW + lane + 32 * j] = p.Ac[(size_t)s * p.ldA + e + 32 * j];
+        }
+        if (warp == 0) {
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) As[p.nS * TW + lane + 32 * j] = c2{1.0, 0.0};
+        }
 #pragma unroll
         for (int k = 0; k < LPC; ++k) ring[k * 32 + lane] = __ldg(stream + k * 32 + lane);
         if (p.nchunks > 1) {
@@ -461,13 +470,15 @@ __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const Stre
             for (int k = 0; k < LPC; ++k) ring[CH + k * 32 + lane] = __ldg(stream + CH + k * 32 + lane);
         }
         __syncthreads();
-        double E[PB];
-        c2 D[PB], S[PB];
+        double E[PB][EPL];
+        c2 D[PB][EPL], S[PB][EPL];
 #pragma unroll
-        for (int q = 0; q < PB; ++q) {
-            E[q] = (p.has_const && warp == 0) ? __ldg(p.w0 + q * CS) : 0.0;
-            D[q] = c2{0.0, 0.0}; S[q] = c2{0.0, 0.0};
-        }
+        for (int q = 0; q < PB; ++q)
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) {
+                E[q][j] = (p.has_const && warp == 0) ? __ldg(p.w0 + q * CS) : 0.0;
+                D[q][j] = c2{0.0, 0.0}; S[q][j] = c2{0.0, 0.0};
+            }
         int ti = 0;
         for (int ch = 0; ch < p.nchunks; ++ch) {
             const bool havepre = ch + 2 < p.nchunks;
@@ -489,80 +500,101 @@ __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const Stre
                 unsigned code2[4] = {0u, 0u, 0u, 0u};
                 if (NF > 2) { const uint4 c3 = blk[1]; code2[0] = c3.x; code2[1] = c3.y; code2[2] = c3.z; code2[3] = c3.w; }
                 const double* wb = reinterpret_cast<const double*>(blk + G::CWORDS);     // [4][PB][CS]
-                c2 acc1 = c2{0.0, 0.0};          // second accumulator (PB == 1 only): halves the dependent chain
-                c2 a1 = c2{0.0, 0.0};
+                c2 acc1[EPL];                    // second accumulator (PB == 1 only): halves the dependent chain
+                c2 a1[EPL];
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) { acc1[j] = c2{0.0, 0.0}; a1[j] = c2{0.0, 0.0}; }
                 unsigned s1prev = 0xffffffffu;
 #pragma unroll
                 for (int k = 0; k < kBlkLeaves; ++k) {
                     const unsigned c = code[k];
                     const unsigned s1 = c & 0x3fffu;
-                    // leaves are sorted by their first factor: re-fetch it only when it changes (warp-uniform)
-                    lds_c2_if(a1, Ab, s1 << 9, s1 != s1prev);
+                    const unsigned o1 = s1 << RSH, o2 = ((c >> 16) & 0x3fffu) << RSH;
+                    const unsigned m2 = c & 0x80000000u, mf = (c & 0x8000u) << 16;
+                    c2 X[EPL];
+#pragma unroll
+                    for (int j = 0; j < EPL; ++j) {
+                        // leaves are sorted by their first factor: re-fetch it only when it changes (warp-uniform)
+                        lds_c2_if(a1[j], Ab + 512 * j, o1, s1 != s1prev);
+                        c2 a2 = lds_c2(Ab + 512 * j, o2);
+                        a2.y = xor_hi(a2.y, m2);
+                        X[j] = cmul(a1[j], a2);
+                    }
                     s1prev = s1;
-                    c2 a2 = lds_c2(Ab, ((c >> 16) & 0x3fffu) << 9);
-                    a2.y = xor_hi(a2.y, c & 0x80000000u);
-                    c2 X = cmul(a1, a2);
                     if (NF > 2) {
-                        c2 a3 = lds_c2(Ab, (code2[k] & 0x3fffu) << 9);
-                        a3.y = xor_hi(a3.y, (code2[k] & 0x8000u) << 16);
-                        X = cmul(X, a3);
+                        const unsigned o3 = (code2[k] & 0x3fffu) << RSH, m3 = (code2[k] & 0x8000u) << 16;
+#pragma unroll
+                        for (int j = 0; j < EPL; ++j) { c2 a3 = lds_c2(Ab + 512 * j, o3); a3.y = xor_hi(a3.y, m3); X[j] = cmul(X[j], a3); }
                     }
                     if (NF > 3) {
-                        c2 a4 = lds_c2(Ab, ((code2[k] >> 16) & 0x3fffu) << 9);
-                        a4.y = xor_hi(a4.y, code2[k] & 0x80000000u);
-                        X = cmul(X, a4);
+                        const unsigned o4 = ((code2[k] >> 16) & 0x3fffu) << RSH, m4 = code2[k] & 0x80000000u;
+#pragma unroll
+                        for (int j = 0; j < EPL; ++j) { c2 a4 = lds_c2(Ab + 512 * j, o4); a4.y = xor_hi(a4.y, m4); X[j] = cmul(X[j], a4); }
                     }
-                    X.y = xor_hi(X.y, (c & 0x8000u) << 16);
+#pragma unroll
+                    for (int j = 0; j < EPL; ++j) X[j].y = xor_hi(X[j].y, mf);
 #pragma unroll
                     for (int q = 0; q < PB; ++q) {
                         if (CW) {
                             const double wr = wb[(k * PB + q) * 2], wi = wb[(k * PB + q) * 2 + 1];
-                            S[q].x += wr * X.x - wi * X.y;
-                            S[q].y += wr * X.y + wi * X.x;
+#pragma unroll
+                            for (int j = 0; j < EPL; ++j) {
+                                S[q][j].x += wr * X[j].x - wi * X[j].y;
+                                S[q][j].y += wr * X[j].y + wi * X[j].x;
+                            }
                         } else {
                             const double w = wb[k * PB + q];
-                            if (PB == 1 && (k & 1)) { acc1.x += w * X.x; acc1.y += w * X.y; }
-                            else { S[q].x += w * X.x; S[q].y += w * X.y; }
+#pragma unroll
+                            for (int j = 0; j < EPL; ++j) {
+                                if (PB == 1 && (k & 1)) { acc1[j].x += w * X[j].x; acc1[j].y += w * X[j].y; }
+                                else { S[q][j].x += w * X[j].x; S[q][j].y += w * X[j].y; }
+                            }
                         }
                     }
                 }
-                if (PB == 1 && !CW) { S[0].x += acc1.x; S[0].y += acc1.y; }
+                if (PB == 1 && !CW) {
+#pragma unroll
+                    for (int j = 0; j < EPL; ++j) { S[0][j].x += acc1[j].x; S[0][j].y += acc1[j].y; }
+                }
                 if (flags) {
                     const uint4 t0 = __ldg(tinfo + (size_t)ti * TIQ);
                     const double* td = reinterpret_cast<const double*>(tinfo + (size_t)ti * TIQ + 1);   // scale, w1[PB][CS]
                     ++ti;
-                    c2 Aa = lds_c2(Ab, t0.x);
-                    Aa.x = xor_hi(Aa.x, t0.y);
-                    Aa.y = xor_hi(Aa.y, t0.z);
                     const bool neg = (flags & kTgtNeg) != 0u, odd = (flags & kTgtOdd) != 0u;
                     // fold onto the m >= 0 slot: Re(D- grad(phi_-m)) = Re((-1)^m conj(D-) grad(phi_m))
                     const double fx = (neg && odd) ? -1.0 : 1.0, fy = neg ? (odd ? 1.0 : -1.0) : 1.0;
-                    if (flags & kSegEnd) {
-                        const double scale = __ldg(td);
+                    const double scale = __ldg(td);
 #pragma unroll
-                        for (int q = 0; q < PB; ++q) {
-                            E[q] += (Aa.x * S[q].x - Aa.y * S[q].y) * scale;
-                            D[q].x += fx * S[q].x;
-                            D[q].y += fy * S[q].y;
-                            S[q] = c2{0.0, 0.0};
+                    for (int j = 0; j < EPL; ++j) {
+                        c2 Aa = lds_c2(Ab + 512 * j, EPL == 1 ? t0.x : t0.x * 2u);
+                        Aa.x = xor_hi(Aa.x, t0.y);
+                        Aa.y = xor_hi(Aa.y, t0.z);
+                        if (flags & kSegEnd) {
+#pragma unroll
+                            for (int q = 0; q < PB; ++q) {
+                                E[q][j] += (Aa.x * S[q][j].x - Aa.y * S[q][j].y) * scale;
+                                D[q][j].x += fx * S[q][j].x;
+                                D[q][j].y += fy * S[q][j].y;
+                                S[q][j] = c2{0.0, 0.0};
+                            }
                         }
-                    }
-                    if (flags & kTgtEnd) {
-                        // order-1 term of this target: dE/dA_a += c~, E += Re(A_a c~)
+                        if (flags & kTgtEnd) {
+                            // order-1 term of this target: dE/dA_a += c~, E += Re(A_a c~)
 #pragma unroll
-                        for (int q = 0; q < PB; ++q) {
-                            const double wr = __ldg(td + 1 + q * CS), wi = CW ? __ldg(td + 2 + q * CS) : 0.0;
-                            E[q] += Aa.x * wr - Aa.y * wi;
-                            D[q].x += fx * wr;
-                            D[q].y += fy * wi;
+                            for (int q = 0; q < PB; ++q) {
+                                const double wr = __ldg(td + 1 + q * CS), wi = CW ? __ldg(td + 2 + q * CS) : 0.0;
+                                E[q][j] += Aa.x * wr - Aa.y * wi;
+                                D[q][j].x += fx * wr;
+                                D[q][j].y += fy * wi;
+                            }
                         }
-                    }
-                    if (flags & kSlotEnd) {
+                        if (flags & kSlotEnd) {
 #pragma unroll
-                        for (int q = 0; q < PB; ++q) {
-                            if (p.want_D && e < p.nenv && p.pb0 + q < p.P)
-                                p.Dt[((size_t)(flags >> 8) * p.P + p.pb0 + q) * p.ldA + e] = D[q];
-                            D[q] = c2{0.0, 0.0};
+                            for (int q = 0; q < PB; ++q) {
+                                if (p.want_D && e + 32 * j < p.nenv && p.pb0 + q < p.P)
+                                    p.Dt[((size_t)(flags >> 8) * p.P + p.pb0 + q) * p.ldA + e + 32 * j] = D[q][j];
+                                D[q][j] = c2{0.0, 0.0};
+                            }
                         }
                     }
                 }
@@ -576,18 +608,22 @@ __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const Stre
         }
         __syncthreads();             // all warps are done with their rings: reuse them for the energy partials
 #pragma unroll
-        for (int q = 0; q < PB; ++q) Epart[(warp * PB + q) * 32 + lane] = E[q];
+        for (int q = 0; q < PB; ++q)
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) Epart[((warp * PB + q) * EPL + j) * 32 + lane] = E[q][j];
         __syncthreads();
-        if (warp == 0 && e < p.nenv) {
+        if (warp == 0) {
 #pragma unroll
-            for (int q = 0; q < PB; ++q) {
-                if (p.pb0 + q < p.P) {
-                    double Et = 0.0;
+            for (int q = 0; q < PB; ++q)
 #pragma unroll
-                    for (int w = 0; w < kStreamWarps; ++w) Et += Epart[(w * PB + q) * 32 + lane];
-                    p.E[(size_t)e * p.P + p.pb0 + q] = Et;
+                for (int j = 0; j < EPL; ++j) {
+                    if (p.pb0 + q < p.P && e + 32 * j < p.nenv) {
+                        double Et = 0.0;
+#pragma unroll
+                        for (int w = 0; w < kStreamWarps; ++w) Et += Epart[((w * PB + q) * EPL + j) * 32 + lane];
+                        p.E[(size_t)(e + 32 * j) * p.P + p.pb0 + q] = Et;
+                    }
                 }
-            }
         }
         __syncthreads();
     }

@@ -112,7 +112,7 @@ struct aceb200_model {
     DevBuf d_lw[kMaxOrdDev + 1];
     DevBuf d_ctl;                      // k_adjoint_stream control words (shared by all passes)
     std::vector<StreamPass> passes;    // per-pass leaf blocks and target records (PB channels each)
-    int stream_chunks = 0, stream_nf = 0, stream_ntinfo = 0, stream_pb = 1;   // 0 chunks: use the generic k_adjoint
+    int stream_chunks = 0, stream_nf = 0, stream_ntinfo = 0, stream_pb = 1, stream_epl = 1;   // 0 chunks: use the generic k_adjoint
     // per-call workspace (guarded by mu).  Three lanes: device-resident batches use lane 0 on the caller's
     // stream; host-resident batches are pipelined chunk by chunk over all lanes (H2D copy, kernels and D2H
     // copy of consecutive chunks overlap on the lanes' private streams).
@@ -228,9 +228,9 @@ static HostGeom stream_geom(int NF, int PB, bool CW)
     return g;
 }
 
-static size_t stream_smem(int nS, const HostGeom& g)
+static size_t stream_smem(int nS, const HostGeom& g, int epl = 1)
 {
-    return (size_t)(nS + 1) * 32 * sizeof(c2) + (size_t)kStreamWarps * 2 * g.CH * sizeof(uint4);
+    return (size_t)(nS + 1) * 32 * epl * sizeof(c2) + (size_t)kStreamWarps * 2 * g.CH * sizeof(uint4);
 }
 
 // Flatten the adjoint lists into the streams k_adjoint_stream consumes (layout: ace_kernels.cuh).
@@ -460,6 +460,9 @@ static void upload_stream(aceb200_model* m)
     m->stream_ntinfo = (int)ntinfo;
     m->stream_nf = NF;
     m->stream_pb = PB;
+    // two environments per lane for the single-channel real path when two such CTAs still fit on an SM
+    m->stream_epl = (PB == 1 && !CW && 2 * (stream_smem(T.nS, g, 2) + 1024) <= (size_t)m->smem_optin) ? 2 : 1;
+    if (const char* ov = getenv("ACEB200_EPL")) m->stream_epl = (atoi(ov) == 2 && PB == 1 && !CW && stream_smem(T.nS, g, 2) <= (size_t)m->smem_optin) ? 2 : 1;
     if (getenv("ACEB200_VERBOSE")) {
         size_t kept = 0, total = 0;
         for (int i = 0; i < T.nAA; ++i) { total += T.orders[i] >= 2; kept += (T.orders[i] >= 2 && keep[i]); }
@@ -683,10 +686,10 @@ static void launch_adjoint_t(aceb200_model* m, const AdjointParams& p, int grid,
     ACE_LAUNCH(kfn, dim3(grid), dim3(32), smem, m->cur->stream, p);
 }
 
-template <int NF, int PB, bool CW>
+template <int NF, int PB, bool CW, int EPL = 1>
 static void launch_stream_t(aceb200_model* m, const StreamParams& p, int grid, size_t smem)
 {
-    auto kfn = k_adjoint_stream<NF, PB, CW>;
+    auto kfn = k_adjoint_stream<NF, PB, CW, EPL>;
     CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ACE_LAUNCH(kfn, dim3(grid), dim3(32 * kStreamWarps), smem, m->cur->stream, p);
 }
@@ -697,7 +700,10 @@ static void launch_stream_nf(aceb200_model* m, const StreamParams& p, int grid, 
     const bool cw = m->cw;
 #define ACE_S(PBV) { if (cw) launch_stream_t<NF, PBV, true>(m, p, grid, smem); else launch_stream_t<NF, PBV, false>(m, p, grid, smem); }
     switch (m->stream_pb) {
-    case 1: ACE_S(1) break;
+    case 1:
+        if (!cw && m->stream_epl == 2) launch_stream_t<NF, 1, false, 2>(m, p, grid, smem);
+        else ACE_S(1)
+        break;
     case 2: ACE_S(2) break;
     case 4: ACE_S(4) break;
     default: ACE_S(8) break;
@@ -710,8 +716,8 @@ static void launch_adjoint(aceb200_model* m, long long nenv, long long ldA, bool
     HostTables& T = m->T;
     if (m->stream_chunks > 0) {
         const HostGeom g = stream_geom(m->stream_nf, m->stream_pb, m->cw);
-        const size_t smem = stream_smem(T.nS, g);
-        const long long ntiles = (nenv + 31) / 32;
+        const size_t smem = stream_smem(T.nS, g, m->stream_epl);
+        const long long ntiles = (nenv + 32 * m->stream_epl - 1) / (32 * m->stream_epl);
         const int per_sm = std::max<int>(1, std::min<int>(8, (int)((size_t)m->smem_optin / (smem + 1024))));
         const int grid = (int)std::min<long long>(ntiles, (long long)m->sm_count * per_sm);
         for (const StreamPass& sp : m->passes) {
@@ -930,7 +936,7 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
         Chunk c;
         c.e0 = ic * step; c.e1 = std::min<long long>(b->nenv, c.e0 + step); c.j0 = bo[ic]; c.j1 = bo[ic + 1];
         const long long ne = c.e1 - c.e0, nj = c.j1 - c.j0;
-        const long long ldA = ((ne + 31) / 32) * 32;
+        const long long ldA = ((ne + 63) / 64) * 64;
         Staged st = stage_chunk(m, b, c);
         BatchDev B = batch_dev(st, c);
         L.ws_Ac.reserve((size_t)T.nS * ldA * sizeof(c2));
