@@ -432,6 +432,43 @@ __device__ __forceinline__ double xor_hi(double v, unsigned mask)
 #endif
 }
 
+
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on mbarriers: how the A tile and the stream
+// chunks reach shared memory without passing through registers.  The emulated test build uses plain loads.
+#if !defined(ACEB200_EMU) && !defined(ACEB200_NO_TMA)
+#define ACEB200_TMA 1
+#else
+#define ACEB200_TMA 0
+#endif
+#if ACEB200_TMA
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity)
+{
+    unsigned ok = 0;
+    int spins = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+        if (!ok && ++spins > (1 << 22)) __trap();      // a lost transaction must fail loudly, never hang the GPU
+    } while (!ok);
+}
+#endif
+
 // One CTA = kStreamWarps warps sharing one shared-memory tile of A (32 * EPL environments, EPL per lane).  The
 // host splits the targets into kStreamWarps balanced sub-streams; warp w walks sub-stream w.  More warps
 // per byte of shared memory is what hides the FP64 and shared-memory latencies of the leaf products; EPL = 2
@@ -445,9 +482,24 @@ __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const Stre
     constexpr int RSH = (EPL == 1) ? 9 : 10;                    // log2 of the tile row pitch in bytes
     ACE_DYN_SMEM(c2, As);                                       // [nS + 1][TW]; slot nS holds 1
     uint4* rings = reinterpret_cast<uint4*>(As + (size_t)(p.nS + 1) * TW);   // [kStreamWarps][2][CH]
-    double* Epart = reinterpret_cast<double*>(rings);            // aliases the rings once the stream is consumed
+    double* Epart = reinterpret_cast<double*>(rings + kStreamWarps * 2 * CH); // [kStreamWarps][PB][EPL][32]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4* ring = rings + warp * 2 * CH;
+#if ACEB200_TMA
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(Epart + kStreamWarps * PB * EPL * 32);   // [1 + 2 kStreamWarps]
+    unsigned long long* barA = bars;
+    unsigned long long* barR = bars + 1 + 2 * warp;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 1 + 2 * kStreamWarps; ++i) mbar_init(bars + i, 1);
+        fence_barrier_init();
+    }
+    unsigned phA = 0, phR0 = 0, phR1 = 0;
+#endif
+    if (warp == 0) {
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) As[p.nS * TW + lane + 32 * j] = c2{1.0, 0.0};
+    }
+    __syncthreads();
     const uint4* stream = p.stream + (size_t)warp * p.nchunks * CH;
     const unsigned* ctl = p.ctl + (size_t)warp * p.nchunks * KB;
     const uint4* tinfo = p.tinfo + (size_t)warp * p.ntinfo * TIQ;
@@ -455,13 +507,29 @@ __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const Stre
     const long long ntiles = (p.nenv + TW - 1) / TW;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long e = tile * TW + lane;                   // environments e, e + 32, ...
+#if ACEB200_TMA
+        // one thread arms the tile barrier and issues one bulk copy per slot row (TW * 16 contiguous bytes each);
+        // lane 0 of every warp primes its two ring slots
+        if (threadIdx.x == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(barA, (unsigned)(p.nS * TW * sizeof(c2)));
+            for (int s = 0; s < p.nS; ++s) bulk_g2s(As + s * TW, p.Ac + (size_t)s * p.ldA + tile * TW, TW * sizeof(c2), barA);
+        }
+        if (lane == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(barR, CH * sizeof(uint4));
+            bulk_g2s(ring, stream, CH * sizeof(uint4), barR);
+            if (p.nchunks > 1) {
+                mbar_expect_tx(barR + 1, CH * sizeof(uint4));
+                bulk_g2s(ring + CH, stream + CH, CH * sizeof(uint4), barR + 1);
+            }
+        }
+        mbar_wait(barA, phA);
+        phA ^= 1u;
+#else
         for (int s = warp; s < p.nS; s += kStreamWarps) {
 #pragma unroll
             for (int j = 0; j < EPL; ++j) As[s * TW + lane + 32 * j] = p.Ac[(size_t)s * p.ldA + e + 32 * j];
-        }
-        if (warp == 0) {
-#pragma unroll
-            for (int j = 0; j < EPL; ++j) As[p.nS * TW + lane + 32 * j] = c2{1.0, 0.0};
         }
 #pragma unroll
         for (int k = 0; k < LPC; ++k) ring[k * 32 + lane] = __ldg(stream + k * 32 + lane);
@@ -470,6 +538,7 @@ __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const Stre
             for (int k = 0; k < LPC; ++k) ring[CH + k * 32 + lane] = __ldg(stream + CH + k * 32 + lane);
         }
         __syncthreads();
+#endif
         double E[PB][EPL];
         c2 D[PB][EPL], S[PB][EPL];
 #pragma unroll
@@ -482,6 +551,10 @@ __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const Stre
         int ti = 0;
         for (int ch = 0; ch < p.nchunks; ++ch) {
             const bool havepre = ch + 2 < p.nchunks;
+#if ACEB200_TMA
+            if (ch & 1) { mbar_wait(barR + 1, phR1); phR1 ^= 1u; }
+            else { mbar_wait(barR, phR0); phR0 ^= 1u; }
+#else
             uint4 pre[LPC];
 #pragma unroll
             for (int k = 0; k < LPC; ++k) pre[k] = uint4{0u, 0u, 0u, 0u};
@@ -489,6 +562,7 @@ __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const Stre
 #pragma unroll
                 for (int k = 0; k < LPC; ++k) pre[k] = __ldg(stream + (size_t)(ch + 2) * CH + k * 32 + lane);
             }
+#endif
             const uint4* rb = ring + (ch & 1) * CH;
             const unsigned* cb = ctl + (size_t)ch * KB;
 #pragma unroll 4
@@ -600,13 +674,20 @@ __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const Stre
                 }
             }
             __syncwarp();            // every lane is done reading this ring slot
+#if ACEB200_TMA
+            if (havepre && lane == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(barR + (ch & 1), CH * sizeof(uint4));
+                bulk_g2s(ring + (ch & 1) * CH, stream + (size_t)(ch + 2) * CH, CH * sizeof(uint4), barR + (ch & 1));
+            }
+#else
             if (havepre) {
 #pragma unroll
                 for (int k = 0; k < LPC; ++k) ring[(ch & 1) * CH + k * 32 + lane] = pre[k];
             }
             __syncwarp();
+#endif
         }
-        __syncthreads();             // all warps are done with their rings: reuse them for the energy partials
 #pragma unroll
         for (int q = 0; q < PB; ++q)
 #pragma unroll

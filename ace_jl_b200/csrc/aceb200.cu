@@ -228,9 +228,12 @@ static HostGeom stream_geom(int NF, int PB, bool CW)
     return g;
 }
 
-static size_t stream_smem(int nS, const HostGeom& g, int epl = 1)
+static size_t stream_smem(int nS, const HostGeom& g, int pb, int epl = 1)
 {
-    return (size_t)(nS + 1) * 32 * epl * sizeof(c2) + (size_t)kStreamWarps * 2 * g.CH * sizeof(uint4);
+    return (size_t)(nS + 1) * 32 * epl * sizeof(c2)                // A tile (+ the row of ones)
+         + (size_t)kStreamWarps * 2 * g.CH * sizeof(uint4)          // per-warp stream rings
+         + (size_t)kStreamWarps * pb * epl * 32 * sizeof(double)    // per-warp energy partials
+         + (size_t)(1 + 2 * kStreamWarps) * 8;                      // mbarriers
 }
 
 // Flatten the adjoint lists into the streams k_adjoint_stream consumes (layout: ace_kernels.cuh).
@@ -254,9 +257,9 @@ static void upload_stream(aceb200_model* m)
     // channels per pass: the largest power of two <= 8 whose ring still fits next to the A tile
     int PB = 1;
     while (PB < P && PB < 8) PB *= 2;
-    while (PB > 1 && stream_smem(T.nS, stream_geom(NF, PB, CW)) > (size_t)m->smem_optin) PB /= 2;
+    while (PB > 1 && stream_smem(T.nS, stream_geom(NF, PB, CW), PB) > (size_t)m->smem_optin) PB /= 2;
     const HostGeom g = stream_geom(NF, PB, CW);
-    if (stream_smem(T.nS, g) > (size_t)m->smem_optin) return;    // falls back to the list kernel
+    if (stream_smem(T.nS, g, PB) > (size_t)m->smem_optin) return;    // falls back to the list kernel
     const bool fold = !getenv("ACEB200_NO_MIRROR_FOLD");
 
     // ---- effective (mirror-folded) coefficients; non-canonical partners are dropped
@@ -461,13 +464,13 @@ static void upload_stream(aceb200_model* m)
     m->stream_nf = NF;
     m->stream_pb = PB;
     // two environments per lane for the single-channel real path when two such CTAs still fit on an SM
-    m->stream_epl = (PB == 1 && !CW && 2 * (stream_smem(T.nS, g, 2) + 1024) <= (size_t)m->smem_optin) ? 2 : 1;
-    if (const char* ov = getenv("ACEB200_EPL")) m->stream_epl = (atoi(ov) == 2 && PB == 1 && !CW && stream_smem(T.nS, g, 2) <= (size_t)m->smem_optin) ? 2 : 1;
+    m->stream_epl = (PB == 1 && !CW && 2 * (stream_smem(T.nS, g, PB, 2) + 1024) <= (size_t)m->smem_optin) ? 2 : 1;
+    if (const char* ov = getenv("ACEB200_EPL")) m->stream_epl = (atoi(ov) == 2 && PB == 1 && !CW && stream_smem(T.nS, g, PB, 2) <= (size_t)m->smem_optin) ? 2 : 1;
     if (getenv("ACEB200_VERBOSE")) {
         size_t kept = 0, total = 0;
         for (int i = 0; i < T.nAA; ++i) { total += T.orders[i] >= 2; kept += (T.orders[i] >= 2 && keep[i]); }
         fprintf(stderr, "[aceb200] stream: NF=%d PB=%d CW=%d passes=%d, %d sub-streams x %zu chunks of %d blocks, AA functions of order >= 2 kept %zu of %zu, smem %zu B\n",
-                NF, PB, (int)CW, npass, kStreamWarps, nchunks, g.KB, kept, total, stream_smem(T.nS, g));
+                NF, PB, (int)CW, npass, kStreamWarps, nchunks, g.KB, kept, total, stream_smem(T.nS, g, PB, m->stream_epl));
     }
 }
 
@@ -716,7 +719,7 @@ static void launch_adjoint(aceb200_model* m, long long nenv, long long ldA, bool
     HostTables& T = m->T;
     if (m->stream_chunks > 0) {
         const HostGeom g = stream_geom(m->stream_nf, m->stream_pb, m->cw);
-        const size_t smem = stream_smem(T.nS, g, m->stream_epl);
+        const size_t smem = stream_smem(T.nS, g, m->stream_pb, m->stream_epl);
         const long long ntiles = (nenv + 32 * m->stream_epl - 1) / (32 * m->stream_epl);
         const int per_sm = std::max<int>(1, std::min<int>(8, (int)((size_t)m->smem_optin / (smem + 1024))));
         const int grid = (int)std::min<long long>(ntiles, (long long)m->sm_count * per_sm);
