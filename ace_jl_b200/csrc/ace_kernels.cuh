@@ -100,9 +100,13 @@ struct PoolParams {
     int* errflag;           // set to ACEB200_EEMPTY / ACEB200_ECATEGORY on bad input
     int TE;                 // environments per CTA (<= kPoolTEmax)
     int nP;                 // harmonics staged per neighbour: sizeP(L)
+    const int4* blk;        // [nblk] 2 x 2 register blocks of slots (two radial indices x two columns of one species):
+    int nblk;               //   x = n0 | n1 << 8 | q << 16,  y = ip0 | ip1 << 16,
+                            //   z = slot(n0, col0) | slot(n1, col0) << 16,  w = slot(n0, col1) | slot(n1, col1) << 16  (0xffff: none)
 };
 
 constexpr int kPoolThreads = 128;
+constexpr int kPoolBItems = 2;      // (environment, slot block) items a thread can own per sub-tile of k_pool
 constexpr int kPoolItems = 4;       // (environment, slot) items a thread can own per sub-tile
 constexpr int kPoolPitch = 129;     // staging row pitch (elements)
 constexpr int kPoolTEmax = 16;
@@ -116,7 +120,7 @@ __global__ void __launch_bounds__(kPoolThreads) k_pool(const PoolParams p)
     int* sq = reinterpret_cast<int*>(SR + (size_t)p.rp.N * kPoolPitch);        // [128] species of the staged neighbour
     int* joff = sq + kPoolThreads;                                             // [TE + 1] neighbour offsets relative to the CTA's first
     const int tid = threadIdx.x;
-    const int N = p.rp.N, nS = p.C.nS;
+    const int N = p.rp.N, nblk = p.nblk;
     const long long e0 = (long long)blockIdx.x * p.TE;
     if (e0 >= p.B.nenv) return;
     const int ne = (int)((p.B.nenv - e0) < p.TE ? (p.B.nenv - e0) : p.TE);
@@ -126,9 +130,11 @@ __global__ void __launch_bounds__(kPoolThreads) k_pool(const PoolParams p)
     const int* spb = SPECIES ? p.B.species + (jbeg - p.B.jbase) : nullptr;
     __syncthreads();
 
-    c2 acc[kPoolItems];
+    c2 acc[kPoolBItems][4];
 #pragma unroll
-    for (int it = 0; it < kPoolItems; ++it) acc[it] = c2{0.0, 0.0};
+    for (int it = 0; it < kPoolBItems; ++it)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[it][k] = c2{0.0, 0.0};
 
     int e = 0, j0 = 0;
     while (e < ne) {
@@ -137,7 +143,7 @@ __global__ void __launch_bounds__(kPoolThreads) k_pool(const PoolParams p)
         int e2 = e + 1, j1;
         bool done_e;                      // the environments of this sub-tile are complete after it
         if (j0 == joff[e] && jend_e - j0 <= kPoolThreads) {
-            while (e2 < ne && joff[e2 + 1] - j0 <= kPoolThreads && (e2 + 1 - e) * nS <= kPoolThreads * kPoolItems) ++e2;
+            while (e2 < ne && joff[e2 + 1] - j0 <= kPoolThreads && (e2 + 1 - e) * nblk <= kPoolThreads * kPoolBItems) ++e2;
             j1 = joff[e2];
             done_e = true;
         } else {
@@ -166,42 +172,64 @@ __global__ void __launch_bounds__(kPoolThreads) k_pool(const PoolParams p)
         }
         __syncthreads();
 
-        // ---- phase b
-        const int nitems = (e2 - e) * nS;
+        // ---- phase b: one (environment, 2 x 2 slot block) item accumulates r_{n0,n1}[j] * y_{col0,col1}[j] over
+        // the environment's staged rows: four shared-memory loads feed eight FP64 FMAs
+        const int nitems = (e2 - e) * nblk;
 #pragma unroll
-        for (int it = 0; it < kPoolItems; ++it) {
+        for (int it = 0; it < kPoolBItems; ++it) {
             const int idx = tid + it * kPoolThreads;
             if (idx < nitems) {
-                const int el = idx / nS, s = idx - el * nS;
-                const int n = __ldg(p.C.slot_n + s), ip = __ldg(p.C.slot_ip + s);
+                const int el = idx / nblk, b = idx - el * nblk;
+                const int4 d = __ldg(p.blk + b);
                 int ra = joff[e + el] - j0, rb = joff[e + el + 1] - j0;
-                if (ra == rb && s == 0) atomicMax(p.errflag, 5);          // EEMPTY (src/product_1pbasis.jl:124)
+                if (ra == rb && b == 0) atomicMax(p.errflag, 5);          // EEMPTY (src/product_1pbasis.jl:124)
                 if (ra < 0) ra = 0;
                 if (rb > nrows) rb = nrows;
-                const double* pr = SR + n * kPoolPitch;
-                const c2* py = SY + ip * kPoolPitch;
-                c2 a = acc[it], a2 = c2{0.0, 0.0};
+                const double* pr0 = SR + (d.x & 0xff) * kPoolPitch + ra;
+                const double* pr1 = SR + ((d.x >> 8) & 0xff) * kPoolPitch + ra;
+                const c2* py0 = SY + (d.y & 0xffff) * kPoolPitch + ra;
+                const c2* py1 = SY + ((d.y >> 16) & 0xffff) * kPoolPitch + ra;
+                c2 a00 = acc[it][0], a10 = acc[it][1], a01 = acc[it][2], a11 = acc[it][3];
+                const int nr = rb - ra;
                 if (SPECIES) {
-                    const int q = __ldg(p.C.slot_q + s);
-                    for (int r = ra; r < rb; ++r) {
-                        const double rn = (sq[r] == q) ? pr[r] : 0.0;
-                        const c2 yv = py[r];
-                        a.x += rn * yv.x; a.y += rn * yv.y;
+                    const int q = (d.x >> 16) & 0xffff;
+                    const int* ps = sq + ra;
+                    for (int r = 0; r < nr; ++r) {
+                        const bool on = ps[r] == q;
+                        const double r0 = on ? pr0[r] : 0.0, r1 = on ? pr1[r] : 0.0;
+                        const c2 y0 = py0[r], y1 = py1[r];
+                        a00.x += r0 * y0.x; a00.y += r0 * y0.y; a10.x += r1 * y0.x; a10.y += r1 * y0.y;
+                        a01.x += r0 * y1.x; a01.y += r0 * y1.y; a11.x += r1 * y1.x; a11.y += r1 * y1.y;
                     }
                 } else {
-                    int r = ra;
-#pragma unroll 2
-                    for (; r + 1 < rb; r += 2) {
-                        const double r0 = pr[r], r1 = pr[r + 1];
-                        const c2 y0 = py[r], y1 = py[r + 1];
-                        a.x += r0 * y0.x; a.y += r0 * y0.y;
-                        a2.x += r1 * y1.x; a2.y += r1 * y1.y;
+                    int r = 0;
+                    for (; r + 1 < nr; r += 2) {
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const double r0 = pr0[u], r1 = pr1[u];
+                            const c2 y0 = py0[u], y1 = py1[u];
+                            a00.x += r0 * y0.x; a00.y += r0 * y0.y; a10.x += r1 * y0.x; a10.y += r1 * y0.y;
+                            a01.x += r0 * y1.x; a01.y += r0 * y1.y; a11.x += r1 * y1.x; a11.y += r1 * y1.y;
+                        }
+                        pr0 += 2; pr1 += 2; py0 += 2; py1 += 2;
                     }
-                    if (r < rb) { const double r0 = pr[r]; const c2 y0 = py[r]; a.x += r0 * y0.x; a.y += r0 * y0.y; }
+                    if (r < nr) {
+                        const double r0 = pr0[0], r1 = pr1[0];
+                        const c2 y0 = py0[0], y1 = py1[0];
+                        a00.x += r0 * y0.x; a00.y += r0 * y0.y; a10.x += r1 * y0.x; a10.y += r1 * y0.y;
+                        a01.x += r0 * y1.x; a01.y += r0 * y1.y; a11.x += r1 * y1.x; a11.y += r1 * y1.y;
+                    }
                 }
-                a.x += a2.x; a.y += a2.y;
-                if (done_e) { p.Ac[(size_t)s * p.ldA + (e0 + e + el)] = a; a = c2{0.0, 0.0}; }
-                acc[it] = a;
+                if (done_e) {
+                    c2* out = p.Ac + (e0 + e + el);
+                    const int s00 = d.z & 0xffff, s10 = (d.z >> 16) & 0xffff, s01 = d.w & 0xffff, s11 = (d.w >> 16) & 0xffff;
+                    if (s00 != 0xffff) out[(size_t)s00 * p.ldA] = a00;
+                    if (s10 != 0xffff) out[(size_t)s10 * p.ldA] = a10;
+                    if (s01 != 0xffff) out[(size_t)s01 * p.ldA] = a01;
+                    if (s11 != 0xffff) out[(size_t)s11 * p.ldA] = a11;
+                    a00 = a10 = a01 = a11 = c2{0.0, 0.0};
+                }
+                acc[it][0] = a00; acc[it][1] = a10; acc[it][2] = a01; acc[it][3] = a11;
             }
         }
         __syncthreads();
@@ -898,15 +926,17 @@ struct PoolWParams {
     c2* Aw;                 // [nS][ldA]
     long long ldA;
     int TE, nP;
+    int rows;               // neighbours staged per sub-tile: 128 unless the staging would not fit in shared memory
 };
 
 template <int NMAX, bool SPECIES>
 __global__ void __launch_bounds__(kPoolThreads) k_pool_w(const PoolWParams p)
 {
     ACE_DYN_SMEM(c2, smem);
+    const int rows = p.rows, pitch = p.rows + 1;   // staged rows per sub-tile (<= kPoolThreads) and the row pitch
     c2* SY = smem;                                                             // [2 nP][129]: Y, w.grad Y
-    double* SR = reinterpret_cast<double*>(SY + (size_t)2 * p.nP * kPoolPitch); // [2 N][129]: R' w.rhat, R
-    int* sq = reinterpret_cast<int*>(SR + (size_t)2 * p.rp.N * kPoolPitch);
+    double* SR = reinterpret_cast<double*>(SY + (size_t)2 * p.nP * pitch); // [2 N][129]: R' w.rhat, R
+    int* sq = reinterpret_cast<int*>(SR + (size_t)2 * p.rp.N * pitch);
     int* joff = sq + kPoolThreads;
     const int tid = threadIdx.x;
     const int N = p.rp.N, nS = p.C.nS, nP = p.nP;
@@ -927,12 +957,12 @@ __global__ void __launch_bounds__(kPoolThreads) k_pool_w(const PoolWParams p)
         const int jend_e = joff[e + 1];
         int e2 = e + 1, j1;
         bool done_e;
-        if (j0 == joff[e] && jend_e - j0 <= kPoolThreads) {
-            while (e2 < ne && joff[e2 + 1] - j0 <= kPoolThreads && (e2 + 1 - e) * nS <= kPoolThreads * kPoolItems) ++e2;
+        if (j0 == joff[e] && jend_e - j0 <= rows) {
+            while (e2 < ne && joff[e2 + 1] - j0 <= rows && (e2 + 1 - e) * nS <= kPoolThreads * kPoolItems) ++e2;
             j1 = joff[e2];
             done_e = true;
         } else {
-            j1 = (j0 + kPoolThreads < jend_e) ? j0 + kPoolThreads : jend_e;
+            j1 = (j0 + rows < jend_e) ? j0 + rows : jend_e;
             done_e = (j1 == jend_e);
         }
         const int nrows = j1 - j0;
@@ -949,13 +979,13 @@ __global__ void __launch_bounds__(kPoolThreads) k_pool_w(const PoolWParams p)
             const double wth = (sp.cphi * sp.cth * wx + sp.sphi * sp.cth * wy - sp.sth * wz) * sp.rinv;
 #pragma unroll
             for (int n = 0; n < NMAX; ++n)
-                if (n < N) { SR[n * kPoolPitch + tid] = dRn[n] * wr; SR[(N + n) * kPoolPitch + tid] = Rn[n]; }
+                if (n < N) { SR[n * pitch + tid] = dRn[n] * wr; SR[(N + n) * pitch + tid] = Rn[n]; }
             for_each_lm_ed(p.ap, sp, [&](int l, int m, double Pt, double dP, double epr, double epi) {
                 const int ip = index_p(l, m);
                 const double f0 = (m == 0) ? Pt : Pt * sp.sth;
-                SY[ip * kPoolPitch + tid] = c2{epr * f0, epi * f0};
+                SY[ip * pitch + tid] = c2{epr * f0, epi * f0};
                 const double gr = dP * wth, gi = (double)m * Pt * wphi;          // (gr + i gi) * ep
-                SY[(nP + ip) * kPoolPitch + tid] = c2{epr * gr - epi * gi, epr * gi + epi * gr};
+                SY[(nP + ip) * pitch + tid] = c2{epr * gr - epi * gi, epr * gi + epi * gr};
             });
         }
         __syncthreads();
@@ -969,8 +999,8 @@ __global__ void __launch_bounds__(kPoolThreads) k_pool_w(const PoolWParams p)
                 int ra = joff[e + el] - j0, rb = joff[e + el + 1] - j0;
                 if (ra < 0) ra = 0;
                 if (rb > nrows) rb = nrows;
-                const double* pr1 = SR + n * kPoolPitch; const double* pr2 = SR + (N + n) * kPoolPitch;
-                const c2* py1 = SY + ip * kPoolPitch; const c2* py2 = SY + (nP + ip) * kPoolPitch;
+                const double* pr1 = SR + n * pitch; const double* pr2 = SR + (N + n) * pitch;
+                const c2* py1 = SY + ip * pitch; const c2* py2 = SY + (nP + ip) * pitch;
                 c2 a = acc[it];
                 for (int r = ra; r < rb; ++r) {
                     if (SPECIES && sq[r] != q) continue;

@@ -169,6 +169,11 @@ ACE_HD inline Spher cart2spher(double x, double y, double z)
 //   ep = exp(i m phi) / sqrt(2)  (:385-393),  so that  Y_l^m = ep * Pv  and  Y_l^{-m} = (-1)^m conj(Y_l^m).
 // The coefficient tables hold A_{m+1}^m = sqrt(2m+3), B_{m+1}^m = 0 (:179, :191) so that one recurrence
 // serves every l > m and the callback is instantiated once.
+// Up to kStaticL the walk is fully unrolled behind warp-uniform `l <= L` exits: (l, m) are then compile-time
+// constants in the callback, and the recursion coefficients become constant-bank operands of the FP64
+// instructions instead of indexed loads.  Models referencing a higher l take the rolled loop.
+constexpr int kStaticL = 6;
+
 template <class F>
 ACE_HD inline void for_each_lm(const AlpParams& ap, const Spher& S, F&& f)
 {
@@ -177,6 +182,30 @@ ACE_HD inline void for_each_lm(const AlpParams& ap, const Spher& S, F&& f)
     const double is2 = 0.70710678118654752;   // 1/sqrt(2)
     double dg = P00;                          // P_m^m
     double epr = is2, epi = 0.0;
+    if (L <= kStaticL) {
+#pragma unroll
+        for (int m = 0; m <= kStaticL; ++m) {
+            if (m > L) break;
+            if (m > 0) {
+                dg = -ap.diagc[m] * S.sth * dg;
+                const double nr = epr * S.cphi - epi * S.sphi;
+                epi = epr * S.sphi + epi * S.cphi;
+                epr = nr;
+            }
+            double p2 = 0.0, p1 = dg;
+#pragma unroll
+            for (int l = m; l <= kStaticL; ++l) {
+                if (l > L) break;
+                if (l > m) {
+                    const double p = (l == m + 1) ? ap.A[index_p(l, m)] * (S.cth * p1)
+                                                  : ap.A[index_p(l, m)] * (S.cth * p1 + ap.B[index_p(l, m)] * p2);
+                    p2 = p1; p1 = p;
+                }
+                f(l, m, p1, epr, epi);
+            }
+        }
+        return;
+    }
     for (int m = 0; m <= L; ++m) {
         if (m > 0) {
             dg = -ap.diagc[m] * S.sth * dg;   // :180, :192
@@ -209,6 +238,45 @@ ACE_HD inline void for_each_lm_ed(const AlpParams& ap, const Spher& S, F&& f)
     double dgt = P00, dgd = 0.0;              // diagonal Pt_m^m, dP_m^m (temp1, temp_d of :229-263)
     double epr = is2, epi = 0.0;
     const double s2 = S.sth * S.sth;
+    if (L <= kStaticL) {
+#pragma unroll
+        for (int m = 0; m <= kStaticL; ++m) {
+            if (m > L) break;
+            const double sfac = (m == 0) ? S.sth : s2;
+            if (m == 1) {
+                dgd = -ap.diagc[1] * (S.cth * dgt + S.sth * dgd);
+                dgt = -ap.diagc[1] * dgt;
+            } else if (m > 1) {
+                const double nd = -ap.diagc[m] * (S.cth * dgt * S.sth + S.sth * dgd);
+                dgt = -ap.diagc[m] * S.sth * dgt;
+                dgd = nd;
+            }
+            if (m > 0) {
+                const double nr = epr * S.cphi - epi * S.sphi;
+                epi = epr * S.sphi + epi * S.cphi;
+                epr = nr;
+            }
+            double p2 = 0.0, d2 = 0.0, p1 = dgt, d1 = dgd;
+#pragma unroll
+            for (int l = m; l <= kStaticL; ++l) {
+                if (l > L) break;
+                if (l > m) {
+                    const int ip = index_p(l, m);
+                    double p, d;
+                    if (l == m + 1) {     // B_{m+1}^m = 0
+                        p = ap.A[ip] * (S.cth * p1);
+                        d = ap.A[ip] * (-sfac * p1 + S.cth * d1);
+                    } else {
+                        p = ap.A[ip] * (S.cth * p1 + ap.B[ip] * p2);
+                        d = ap.A[ip] * (-sfac * p1 + S.cth * d1 + ap.B[ip] * d2);
+                    }
+                    p2 = p1; d2 = d1; p1 = p; d1 = d;
+                }
+                f(l, m, p1, d1, epr, epi);
+            }
+        }
+        return;
+    }
     for (int m = 0; m <= L; ++m) {
         const double sfac = (m == 0) ? S.sth : s2;   // -sin th P (m = 0, :241) vs -sin^2 th Pt (:251)
         if (m == 1) {

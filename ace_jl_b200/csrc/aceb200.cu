@@ -104,6 +104,8 @@ struct aceb200_model {
     std::vector<DevBuf> pool;
     ColumnsDev C;
     const int *d_slot_pos = nullptr, *d_slot_neg = nullptr, *d_code = nullptr;
+    const int4* d_pool_blk = nullptr;
+    int n_pool_blk = 0;
     const int *d_orders = nullptr, *d_spec = nullptr;
     const int *d_csr_ptr = nullptr, *d_csr_col = nullptr;
     const c2* d_csr_val = nullptr;
@@ -490,6 +492,32 @@ static void upload_tables(aceb200_model* m)
             for (int n = 0; n < c.cnt; ++n) { sn[c.base + n] = n; sip[c.base + n] = c.ip; sqv[c.base + n] = c.q; }
         C.slot_n = upload(m->pool, sn); C.slot_ip = upload(m->pool, sip); C.slot_q = upload(m->pool, sqv);
     }
+    {
+        // 2 x 2 slot blocks for k_pool: per species, columns sorted by length and paired; a block is two
+        // consecutive radial indices of such a pair (missing corners carry slot 0xffff and are never written)
+        std::vector<int4> blk;
+        for (int q = 0; q < T.nQ; ++q) {
+            std::vector<const Column*> cs;
+            for (const Column& c : T.cols) if (c.q == q) cs.push_back(&c);
+            std::stable_sort(cs.begin(), cs.end(), [](const Column* a, const Column* b) { return a->cnt > b->cnt; });
+            for (size_t i = 0; i < cs.size(); i += 2) {
+                const Column* a = cs[i];
+                const Column* b = i + 1 < cs.size() ? cs[i + 1] : nullptr;
+                for (int n0 = 0; n0 < a->cnt; n0 += 2) {
+                    const int n1 = n0 + 1 < a->cnt ? n0 + 1 : n0;
+                    auto slot = [&](const Column* c, int n, bool ok) { return (c && ok && n < c->cnt) ? c->base + n : 0xffff; };
+                    int4 d;
+                    d.x = n0 | (n1 << 8) | (q << 16);
+                    d.y = a->ip | ((b ? b->ip : a->ip) << 16);
+                    d.z = slot(a, n0, true) | (slot(a, n1, n1 != n0) << 16);
+                    d.w = slot(b, n0, true) | (slot(b, n1, n1 != n0) << 16);
+                    blk.push_back(d);
+                }
+            }
+        }
+        m->n_pool_blk = (int)blk.size();
+        m->d_pool_blk = upload(m->pool, blk);
+    }
     m->d_slot_pos = upload(m->pool, T.slot_pos);
     m->d_slot_neg = upload(m->pool, T.slot_neg);
     m->d_code = upload(m->pool, T.iA_code);
@@ -626,8 +654,9 @@ static void launch_pool(aceb200_model* m, const BatchDev& B, long long ldA)
     PoolParams p;
     p.rp = m->rp; p.ap = m->ap; p.C = m->C; p.B = B;
     p.Ac = m->cur->ws_Ac.as<c2>(); p.ldA = ldA; p.errflag = m->ws_err.as<int>();
-    if (T.nS > kPoolThreads * kPoolItems)
-        throw ModelError(ACEB200_EUNSUPPORTED, "one-particle basis too large for k_pool (more than 512 canonical slots)");
+    if (m->n_pool_blk > kPoolThreads * kPoolBItems || T.nS >= 0xffff || T.nQ > 0xffff)
+        throw ModelError(ACEB200_EUNSUPPORTED, "one-particle basis too large for k_pool (more than 256 slot blocks)");
+    p.blk = m->d_pool_blk; p.nblk = m->n_pool_blk;
     p.TE = 8;
     p.nP = (T.Lused + 1) * (T.Lused + 2) / 2;
     const size_t smem = (size_t)kPoolPitch * (p.nP * sizeof(c2) + m->rp.N * sizeof(double)) + (kPoolThreads + kPoolTEmax + 1) * sizeof(int);
@@ -666,7 +695,12 @@ static void launch_pool_w(aceb200_model* m, const BatchDev& B, const double* W, 
     p.rp = m->rp; p.ap = m->ap; p.C = m->C; p.B = B; p.W = W;
     p.Aw = m->cur->ws_Aw.as<c2>(); p.ldA = ldA; p.TE = 8;
     p.nP = (T.Lused + 1) * (T.Lused + 2) / 2;
-    const size_t smem = (size_t)2 * kPoolPitch * (p.nP * sizeof(c2) + m->rp.N * sizeof(double)) + (kPoolThreads + kPoolTEmax + 1) * sizeof(int);
+    const size_t rowbytes = (size_t)2 * (p.nP * sizeof(c2) + m->rp.N * sizeof(double)), misc = (kPoolThreads + kPoolTEmax + 1) * sizeof(int);
+    p.rows = kPoolThreads;
+    if ((p.rows + 1) * rowbytes + misc > (size_t)m->smem_optin) p.rows = (int)(((size_t)m->smem_optin - misc) / rowbytes) - 1;
+    if (p.rows < 8) throw ModelError(ACEB200_EUNSUPPORTED, "one-particle basis too large for the shared-memory staging of k_pool_w");
+    if (p.rows & 1) p.rows -= 1;             // an odd pitch (rows + 1) keeps the staging rows conflict-free
+    const size_t smem = (size_t)(p.rows + 1) * rowbytes + misc;
     dim3 grid((unsigned)((B.nenv + p.TE - 1) / p.TE));
     switch (m->NMAX) {
     case 4: launch_pool_w_t<4>(m, p, grid, smem); break;

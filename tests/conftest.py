@@ -68,6 +68,9 @@ def make_basis(kind: str):
     if kind == "inv_agnesi_2_6":
         return ace.SymmetricBasis(ace.Invariant(), RnYlm_1pbasis(maxdeg=6, trans=ace.agnesitransform(1.0, 3)),
                                   ace.SimpleSparseBasis(2, 6))
+    if kind == "inv_highL_2_12":         # l up to 10: beyond the statically unrolled harmonics walk (ace_math.cuh kStaticL)
+        Bsel = ace.SparseBasis(maxorder=2, p=1, default_maxdeg=12, weight={"n": 1.0, "l": 0.6})
+        return ace.SymmetricBasis(ace.Invariant(), RnYlm_1pbasis(maxdeg=12, maxL=10, Bsel=Bsel), Bsel)
     raise KeyError(kind)
 
 

@@ -35,6 +35,7 @@ struct dim3 {
 struct double2 { double x, y; };
 struct uint2 { unsigned x, y; };
 struct uint4 { unsigned x, y, z, w; };
+struct int4 { int x, y, z, w; };
 inline int __double2hiint(double v) { union { double d; unsigned long long u; } w; w.d = v; return (int)(w.u >> 32); }
 inline int __double2loint(double v) { union { double d; unsigned long long u; } w; w.d = v; return (int)(w.u & 0xffffffffu); }
 inline double __hiloint2double(int hi, int lo) { union { double d; unsigned long long u; } w; w.u = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo; return w.d; }

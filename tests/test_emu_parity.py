@@ -38,6 +38,7 @@ def emu():
     ("species_3_5", 2, [5, 12, 33, 130]),                 # categorical component
     ("inv_morse_2_6", 1, [6, 20]),
     ("inv_agnesi_2_6", 1, [6, 20]),
+    ("inv_highL_2_12", 1, [5, 17]),
     ("inv_complexB_2_5", 1, [6, 20]),                     # complex B / dB outputs (symreal = false)
 ])
 def test_emulated_kernels_match_oracle(emu, kind, nprop, Js):

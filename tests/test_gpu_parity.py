@@ -34,6 +34,7 @@ CASES = [
     ("species_3_5", 16, [5, 40, 33, 130]),                  # config 5's family: 16 properties, 4 species
     ("inv_morse_2_6", 1, [6, 20]),
     ("inv_agnesi_2_6", 1, [6, 20]),
+    ("inv_highL_2_12", 1, [5, 17]),
     ("inv_complexB_2_5", 1, [6, 20, 33]),                   # complex B / dB outputs (symreal = false)
 ]
 
