@@ -397,6 +397,12 @@ __global__ void __launch_bounds__(32) k_adjoint(const AdjointParams p)
 //     A~ are the canonical (m >= 0) slots; unused factors point at an extra slot that holds 1; the conjugation
 //     of the first operand and all (-1)^m signs are folded into flipIm / w by the host:
 //       prod_k (s_k cj^{k_k} A~_k) = (prod s_k) cj^{k_1}( A~_1 prod_{k>1} cj^{k_k xor k_1} A~_k ).
+//   Grouped form (one real channel, PB == 1 && !CW): within a segment the host greedily groups the leaves that
+//   share a factor, makes that factor the first one, and marks each group's last leaf (kGroupEnd).  The kernel
+//   accumulates  T += w * cj^{k_2}(A~[slot2]) (* ...)  per leaf (two FMAs instead of a complex product plus two
+//   FMAs) and multiplies by the shared factor once per group:  S += cj^{k_1}(A~[slot1]) * T.  Bit 15 is then the
+//   conjugation of the first factor alone, the other conj bits apply to their own factor, and w carries the
+//   (-1)^m signs.  Order-2 leaves (one other factor) form a single group whose first factor is the slot of ones.
 //   ctl[block]  (u32, global)  0 for most blocks; else flags | order | slot<<8: end of segment / target / slot
 //   tinfo[k]    (global) consumed in order, one per non-zero ctl: target slot + masks, 1/order, order-1 weights
 // The leaf blocks are read strictly sequentially and identically by every lane, so the warp fetches them
@@ -405,6 +411,7 @@ __global__ void __launch_bounds__(32) k_adjoint(const AdjointParams p)
 // warp-uniform branch on ctl.  The energy falls out of the same pass by Euler's identity
 // sum_a A_a dF_nu/dA_a = nu F_nu.
 constexpr unsigned kSegEnd = 8, kTgtEnd = 16, kTgtNeg = 32, kTgtOdd = 64, kSlotEnd = 128;
+constexpr unsigned kGroupEnd = 0x4000u;     // leaf code bit 14 (grouped form)
 constexpr int kBlkLeaves = 4;               // leaves per block
 constexpr int kStreamWarps = 8;             // warps per CTA; each walks its own sub-stream over the same A tile
 
@@ -423,6 +430,7 @@ struct StreamGeom {
 struct StreamParams {
     int nS, has_const, want_D, nchunks, ntinfo;
     int P, pb0;                              // channels [pb0, pb0 + PB) of P are computed by this launch
+    int nblk[8];                             // [kStreamWarps] blocks of each sub-stream before its inert padding
     const uint4* stream;                     // [kStreamWarps][nchunks][CH]
     const unsigned* ctl;                     // [kStreamWarps][nchunks * KB]
     const uint4* tinfo;                      // [kStreamWarps][ntinfo][TIQ]
@@ -528,6 +536,9 @@ __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const Stre
         for (int j = 0; j < EPL; ++j) As[p.nS * TW + lane + 32 * j] = c2{1.0, 0.0};
     }
     __syncthreads();
+    constexpr bool GR = (PB == 1 && !CW);                       // grouped leaves (see the stream layout above)
+    const int nblkw = p.nblk[warp];                             // this warp's sub-stream stops at its last real block
+    const int nchw = (nblkw + KB - 1) / KB;
     const uint4* stream = p.stream + (size_t)warp * p.nchunks * CH;
     const unsigned* ctl = p.ctl + (size_t)warp * p.nchunks * KB;
     const uint4* tinfo = p.tinfo + (size_t)warp * p.ntinfo * TIQ;
@@ -543,11 +554,11 @@ __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const Stre
             mbar_expect_tx(barA, (unsigned)(p.nS * TW * sizeof(c2)));
             for (int s = 0; s < p.nS; ++s) bulk_g2s(As + s * TW, p.Ac + (size_t)s * p.ldA + tile * TW, TW * sizeof(c2), barA);
         }
-        if (lane == 0) {
+        if (lane == 0 && nchw > 0) {
             fence_proxy_async();
             mbar_expect_tx(barR, CH * sizeof(uint4));
             bulk_g2s(ring, stream, CH * sizeof(uint4), barR);
-            if (p.nchunks > 1) {
+            if (nchw > 1) {
                 mbar_expect_tx(barR + 1, CH * sizeof(uint4));
                 bulk_g2s(ring + CH, stream + CH, CH * sizeof(uint4), barR + 1);
             }
@@ -559,9 +570,11 @@ __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const Stre
 #pragma unroll
             for (int j = 0; j < EPL; ++j) As[s * TW + lane + 32 * j] = p.Ac[(size_t)s * p.ldA + e + 32 * j];
         }
+        if (nchw > 0) {
 #pragma unroll
-        for (int k = 0; k < LPC; ++k) ring[k * 32 + lane] = __ldg(stream + k * 32 + lane);
-        if (p.nchunks > 1) {
+            for (int k = 0; k < LPC; ++k) ring[k * 32 + lane] = __ldg(stream + k * 32 + lane);
+        }
+        if (nchw > 1) {
 #pragma unroll
             for (int k = 0; k < LPC; ++k) ring[CH + k * 32 + lane] = __ldg(stream + CH + k * 32 + lane);
         }
@@ -569,6 +582,9 @@ __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const Stre
 #endif
         double E[PB][EPL];
         c2 D[PB][EPL], S[PB][EPL];
+        c2 Tg[EPL];                      // GR: sum of w * (other factors) over the current group
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) Tg[j] = c2{0.0, 0.0};
 #pragma unroll
         for (int q = 0; q < PB; ++q)
 #pragma unroll
@@ -577,8 +593,8 @@ __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const Stre
                 D[q][j] = c2{0.0, 0.0}; S[q][j] = c2{0.0, 0.0};
             }
         int ti = 0;
-        for (int ch = 0; ch < p.nchunks; ++ch) {
-            const bool havepre = ch + 2 < p.nchunks;
+        for (int ch = 0; ch < nchw; ++ch) {
+            const bool havepre = ch + 2 < nchw;
 #if ACEB200_TMA
             if (ch & 1) { mbar_wait(barR + 1, phR1); phR1 ^= 1u; }
             else { mbar_wait(barR, phR0); phR0 ^= 1u; }
@@ -593,8 +609,9 @@ __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const Stre
 #endif
             const uint4* rb = ring + (ch & 1) * CH;
             const unsigned* cb = ctl + (size_t)ch * KB;
+            const int nb = (nblkw - ch * KB < KB) ? nblkw - ch * KB : KB;
 #pragma unroll 4
-            for (int b = 0; b < KB; ++b) {
+            for (int b = 0; b < nb; ++b) {
                 const uint4* blk = rb + b * QBP;
                 const unsigned flags = __ldg(cb + b);
                 const uint4 cw = blk[0];
@@ -610,6 +627,38 @@ __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const Stre
 #pragma unroll
                 for (int k = 0; k < kBlkLeaves; ++k) {
                     const unsigned c = code[k];
+                    if (GR) {
+                        // T += w * a2^{c2} [* a3^{c3} * a4^{c4}];  at the group's last leaf  S += a1^{c1} * T
+                        const unsigned o2 = ((c >> 16) & 0x3fffu) << RSH, m2 = c & 0x80000000u;
+                        c2 X[EPL];
+#pragma unroll
+                        for (int j = 0; j < EPL; ++j) { X[j] = lds_c2(Ab + 512 * j, o2); X[j].y = xor_hi(X[j].y, m2); }
+                        if (NF > 2) {
+                            const unsigned o3 = (code2[k] & 0x3fffu) << RSH, m3 = (code2[k] & 0x8000u) << 16;
+#pragma unroll
+                            for (int j = 0; j < EPL; ++j) { c2 a3 = lds_c2(Ab + 512 * j, o3); a3.y = xor_hi(a3.y, m3); X[j] = cmul(X[j], a3); }
+                        }
+                        if (NF > 3) {
+                            const unsigned o4 = ((code2[k] >> 16) & 0x3fffu) << RSH, m4 = code2[k] & 0x80000000u;
+#pragma unroll
+                            for (int j = 0; j < EPL; ++j) { c2 a4 = lds_c2(Ab + 512 * j, o4); a4.y = xor_hi(a4.y, m4); X[j] = cmul(X[j], a4); }
+                        }
+                        const double w = wb[k];
+#pragma unroll
+                        for (int j = 0; j < EPL; ++j) { Tg[j].x += w * X[j].x; Tg[j].y += w * X[j].y; }
+                        if (c & kGroupEnd) {
+                            const unsigned o1 = (c & 0x3fffu) << RSH, m1 = (c & 0x8000u) << 16;
+#pragma unroll
+                            for (int j = 0; j < EPL; ++j) {
+                                c2 a = lds_c2(Ab + 512 * j, o1);
+                                a.y = xor_hi(a.y, m1);
+                                S[0][j].x += a.x * Tg[j].x - a.y * Tg[j].y;
+                                S[0][j].y += a.x * Tg[j].y + a.y * Tg[j].x;
+                                Tg[j] = c2{0.0, 0.0};
+                            }
+                        }
+                        continue;
+                    }
                     const unsigned s1 = c & 0x3fffu;
                     const unsigned o1 = s1 << RSH, o2 = ((c >> 16) & 0x3fffu) << RSH;
                     const unsigned m2 = c & 0x80000000u, mf = (c & 0x8000u) << 16;
@@ -654,7 +703,7 @@ __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const Stre
                         }
                     }
                 }
-                if (PB == 1 && !CW) {
+                if (PB == 1 && !CW && !GR) {
 #pragma unroll
                     for (int j = 0; j < EPL; ++j) { S[0][j].x += acc1[j].x; S[0][j].y += acc1[j].y; }
                 }
@@ -748,24 +797,31 @@ struct ForceParams {
     BatchDev B;
     const c2* Dt; long long ldA;
     int P, nprop, ncomp;
+    int TE, dpitch;          // environments per CTA; c2 elements per staged environment (odd: conflict-free broadcasts)
     double* G;               // [neighbour][nprop][3][ncomp], chunk-relative
 };
 
+#ifndef ACE_FORCE_MINB
+#define ACE_FORCE_MINB 5      // resident CTAs per SM the register allocation of k_forces is held to
+#endif
 constexpr int kForceThreads = 128;
-constexpr int kForceTE = 8;          // environments per CTA (compile-time: staging strides become immediates)
+constexpr int kForceTEmax = 32;      // environments per CTA (ForceParams::TE), chosen by the host so that the CTA's
+                                     // neighbours fill whole passes of kForceThreads
 
 // u += D[n] R[n], v += D[n] dR[n] for n < cnt, with n a compile-time register index: a fall-through
-// switch on the (warp-uniform) column length replaces a per-n predicate.
+// switch on the (warp-uniform) column length replaces a per-n predicate.  R_n lives in registers; dR_n/dr is
+// parked in shared memory ([n][thread]) so that the register budget allows ACE_FORCE_MINB resident CTAs.
 template <int NMAX, int STRIDE>
-__device__ __forceinline__ void column_dot(const c2* D, int cnt, const double (&Rn)[NMAX], const double (&dRn)[NMAX],
+__device__ __forceinline__ void column_dot(const c2* D, int cnt, const double (&Rn)[NMAX], const double* dRs,
                                            double& ur, double& ui, double& vr, double& vi)
 {
 #define ACE_TERM(n)                                                                      \
     case (n) + 1:                                                                        \
         if ((n) < NMAX) {                                                                \
             const c2 d = D[(size_t)(n) * STRIDE];                                        \
+            const double dr = dRs[(n) * kForceThreads];                                  \
             ur += d.x * Rn[(n) < NMAX ? (n) : 0]; ui += d.y * Rn[(n) < NMAX ? (n) : 0];      \
-            vr += d.x * dRn[(n) < NMAX ? (n) : 0]; vi += d.y * dRn[(n) < NMAX ? (n) : 0];    \
+            vr += d.x * dr; vi += d.y * dr;                                              \
         }
     switch (cnt) {
         ACE_TERM(31) ACE_TERM(30) ACE_TERM(29) ACE_TERM(28) ACE_TERM(27) ACE_TERM(26) ACE_TERM(25) ACE_TERM(24)
@@ -777,21 +833,23 @@ __device__ __forceinline__ void column_dot(const c2* D, int cnt, const double (&
 #undef ACE_TERM
 }
 
-// A CTA owns kForceTE consecutive environments: it stages their folded adjoints D~ in shared memory
-// ([slot][channel][local env]) together with the (species, l, m) -> column table and the environments'
-// neighbour offsets, then runs one thread per neighbour of those environments.
+// A CTA owns TE consecutive environments: it stages their folded adjoints D~ in shared memory
+// ([local env][slot][channel]: the slots of a column are a compile-time stride apart) together with the
+// (species, l, m) -> column table and the environments' neighbour offsets, then runs one thread per neighbour
+// of those environments.
 template <int NMAX, int PB, bool SPECIES>
-__global__ void __launch_bounds__(kForceThreads, 5) k_forces(const ForceParams p)
+__global__ void __launch_bounds__(kForceThreads, ACE_FORCE_MINB) k_forces(const ForceParams p)
 {
-    ACE_DYN_SMEM(c2, Ds);   // [nS][PB][kForceTE], then int colinfo[nQ * nPused], int joff[kForceTE + 1]
-    constexpr int TE = kForceTE;
+    ACE_DYN_SMEM(c2, Ds);   // [TE][dpitch >= nS * PB], double dR[NMAX][kForceThreads], int colinfo[nQ * nPused], int joff[TE + 1]
+    const int TE = p.TE, dpitch = p.dpitch;
     const int tid = threadIdx.x;
     const long long e0 = (long long)blockIdx.x * TE;
     if (e0 >= p.B.nenv) return;
     const int ne = (int)((p.B.nenv - e0) < TE ? (p.B.nenv - e0) : TE);
     const long long jbeg = p.B.off[e0];
     const int nS = p.C.nS, ncol = p.C.nQ * p.C.nPused;
-    int* colinfo = reinterpret_cast<int*>(Ds + (size_t)nS * PB * TE);
+    double* dRs = reinterpret_cast<double*>(Ds + (size_t)TE * dpitch) + tid;   // [NMAX][kForceThreads]
+    int* colinfo = reinterpret_cast<int*>(dRs - tid + NMAX * kForceThreads);
     int* joff = colinfo + ncol;
     for (int i = tid; i < ncol; i += kForceThreads) {
         const int col = __ldg(p.C.colmap + i);
@@ -806,7 +864,7 @@ __global__ void __launch_bounds__(kForceThreads, 5) k_forces(const ForceParams p
         __syncthreads();
         for (int idx = tid; idx < nS * PB * TE; idx += kForceThreads) {
             const int el = idx % TE, sc = idx / TE, c = sc % PB, s = sc / PB;
-            Ds[idx] = (pb + c < p.P && el < ne) ? p.Dt[((size_t)s * p.P + pb + c) * p.ldA + e0 + el] : c2{0.0, 0.0};
+            Ds[el * dpitch + sc] = (pb + c < p.P && el < ne) ? p.Dt[((size_t)s * p.P + pb + c) * p.ldA + e0 + el] : c2{0.0, 0.0};
         }
         __syncthreads();
         const int nj = joff[ne];
@@ -817,10 +875,10 @@ __global__ void __launch_bounds__(kForceThreads, 5) k_forces(const ForceParams p
             int q = 0;
             if (SPECIES) { q = spb[j] - 1; if (q < 0 || q >= p.C.nQ) q = 0; }
             const Spher sp = cart2spher(x, y, z);
-            double Rn[NMAX], dRn[NMAX];
-            radial_ed<NMAX>(p.rp, sp.r, Rn, dRn);
+            double Rn[NMAX];
+            radial_ed_park<NMAX>(p.rp, sp.r, Rn, dRs, kForceThreads);
             const int* cinfo = colinfo + (SPECIES ? q * p.C.nPused : 0);
-            const c2* Dj = Ds + el;
+            const c2* Dj = Ds + el * dpitch;
             double S0[PB], S1[PB], S2[PB];
 #pragma unroll
             for (int c = 0; c < PB; ++c) { S0[c] = 0.0; S1[c] = 0.0; S2[c] = 0.0; }
@@ -833,10 +891,11 @@ __global__ void __launch_bounds__(kForceThreads, 5) k_forces(const ForceParams p
 #pragma unroll
                 for (int c = 0; c < PB; ++c) {
                     double ur = 0.0, ui = 0.0, vr = 0.0, vi = 0.0;
-                    column_dot<NMAX, PB * TE>(Dj + ((size_t)base * PB + c) * TE, cnt, Rn, dRn, ur, ui, vr, vi);
-                    // z = u * ep ;  Re(v * ep)
-                    const double zr = ur * epr - ui * epi, zi = ur * epi + ui * epr;
-                    const double ve = vr * epr - vi * epi;
+                    column_dot<NMAX, PB>(Dj + base * PB + c, cnt, Rn, dRs, ur, ui, vr, vi);
+                    // z = u * ep ;  Re(v * ep)   (ep is real for m = 0)
+                    const double zr = (m == 0) ? ur * epr : ur * epr - ui * epi;
+                    const double zi = (m == 0) ? ui * epr : ur * epi + ui * epr;
+                    const double ve = (m == 0) ? vr * epr : vr * epr - vi * epi;
                     S0[c] += f0 * ve;          // radial:   rhat * Re(v Y)
                     S1[c] += f1 * zi;          // azimuth:  m Pt Im(u ep)
                     S2[c] += dP * zr;          // polar:    dP Re(u ep)

@@ -131,6 +131,35 @@ ACE_HD inline void radial_ed(const RadialParams& rp, double r, double (&R)[NMAX]
     for (int n = 0; n < NMAX; ++n) dR[n] *= dt;
 }
 
+// radial_ed with dR_n/dr written to dRs[n * stride] as soon as it is formed (two rolling registers instead of
+// an NMAX-register array): k_forces parks the derivatives in shared memory.
+template <int NMAX>
+ACE_HD inline void radial_ed_park(const RadialParams& rp, double r, double (&R)[NMAX], double* dRs, int stride)
+{
+    double t, dt, f, df;
+    transform_ed(rp, r, t, dt);
+    envelope_ed(rp, t, f, df);
+    R[0] = rp.A[0] * f;
+    double d2 = rp.A[0] * df, d1 = 0.0;      // dP_{n-2}/dt, dP_{n-1}/dt
+    dRs[0] = d2 * dt;
+    if (NMAX > 1) {
+        const double al = rp.A[1] * t + rp.B[1];
+        R[1] = al * R[0];
+        d1 = al * d2 + rp.A[1] * R[0];
+        dRs[stride] = d1 * dt;
+    }
+#pragma unroll
+    for (int n = 2; n < NMAX; ++n) {
+        if (n < rp.N) {
+            const double al = rp.A[n] * t + rp.B[n];
+            R[n] = al * R[n - 1] + rp.C[n] * R[n - 2];
+            const double d = al * d1 + rp.C[n] * d2 + rp.A[n] * R[n - 1];
+            d2 = d1; d1 = d;
+            dRs[n * stride] = d * dt;
+        } else { R[n] = 0.0; dRs[n * stride] = 0.0; }
+    }
+}
+
 // Spherical coordinates of a neighbour (src/polynomials/sphericalharmonics.jl:43-51).  The reference
 // goes through atan + sincos; x/rho, y/rho are the same numbers to round-off, with the rho = 0
 // convention atan(0, 0) = 0 kept (cos = 1, sin = 0).

@@ -114,6 +114,7 @@ struct aceb200_model {
     DevBuf d_lw[kMaxOrdDev + 1];
     DevBuf d_ctl;                      // k_adjoint_stream control words (shared by all passes)
     std::vector<StreamPass> passes;    // per-pass leaf blocks and target records (PB channels each)
+    int stream_nblk[kStreamWarps] = {0};
     int stream_chunks = 0, stream_nf = 0, stream_ntinfo = 0, stream_pb = 1, stream_epl = 1;   // 0 chunks: use the generic k_adjoint
     // per-call workspace (guarded by mu).  Three lanes: device-resident batches use lane 0 on the caller's
     // stream; host-resident batches are pipelined chunk by chunk over all lanes (H2D copy, kernels and D2H
@@ -327,6 +328,24 @@ static void upload_stream(aceb200_model* m)
         L.sg = sg; L.aa = aa; L.mult = mult;
         return L;
     };
+    // grouped form: `first` is the A-code of the group's shared factor (-1: the slot of ones), `others` the rest
+    const bool GR = (PB == 1 && !CW);
+    auto make_leaf_gr = [&](int first, const uint16_t* others, int no, int aa, int mult, bool gend) {
+        unsigned slot[4] = {ONE, ONE, ONE, ONE}, cj[4] = {0u, 0u, 0u, 0u};
+        double sg = 1.0;
+        auto put = [&](int f, unsigned c) {
+            const unsigned neg = c & 1u, odd = (c >> 1) & 1u;
+            if (neg && odd) sg = -sg;
+            slot[f] = c >> 2; cj[f] = neg;
+        };
+        if (first >= 0) put(0, (unsigned)first);
+        for (int f = 0; f < no; ++f) put(1 + f, others[f]);
+        Leaf L;
+        L.code = slot[0] | (gend ? kGroupEnd : 0u) | (cj[0] << 15) | (slot[1] << 16) | (cj[1] << 31);
+        L.code2 = slot[2] | (cj[2] << 15) | (slot[3] << 16) | (cj[3] << 31);
+        L.sg = sg; L.aa = aa; L.mult = mult;
+        return L;
+    };
     // The block structure (codes, ctl, which target a tinfo record belongs to) is the same for every pass;
     // only the weights differ.  Build the structure once per sub-stream, then emit the passes.
     struct BlockRef { Leaf L[kBlkLeaves]; int nleaf; unsigned flags; int target; double invnu; };
@@ -357,9 +376,54 @@ static void upload_stream(aceb200_model* m)
             int lastnu = 0;
             for (int nu = 2; nu <= T.maxord; ++nu) {
                 const Tree& tr = T.trees[nu];
-                for (int i = tr.ptr[a]; i < tr.ptr[a + 1]; ++i) {
-                    if (!keep[tr.laa[i]]) continue;
-                    per[nu].push_back(make_leaf(&tr.codes[4 * (size_t)i], nu - 1, tr.laa[i], tr.lmult[i]));
+                if (!GR) {
+                    for (int i = tr.ptr[a]; i < tr.ptr[a + 1]; ++i) {
+                        if (!keep[tr.laa[i]]) continue;
+                        per[nu].push_back(make_leaf(&tr.codes[4 * (size_t)i], nu - 1, tr.laa[i], tr.lmult[i]));
+                    }
+                } else {
+                    // greedy grouping: repeatedly take the factor shared by the most remaining leaves
+                    std::vector<int> rest;
+                    for (int i = tr.ptr[a]; i < tr.ptr[a + 1]; ++i) if (keep[tr.laa[i]]) rest.push_back(i);
+                    const int nf = nu - 1;
+                    while (!rest.empty()) {
+                        int key = -1;
+                        std::vector<int> grp;
+                        if (nf == 1) grp.swap(rest);          // order 2: one group behind the slot of ones
+                        else {
+                            std::map<int, int> cnt;
+                            for (int i : rest) {
+                                const uint16_t* cd = &tr.codes[4 * (size_t)i];
+                                for (int f = 0; f < nf; ++f) {
+                                    bool seen = false;
+                                    for (int f2 = 0; f2 < f; ++f2) seen |= cd[f2] == cd[f];
+                                    if (!seen) cnt[cd[f]]++;
+                                }
+                            }
+                            int bestc = 0;
+                            for (auto& kv : cnt) if (kv.second > bestc) { bestc = kv.second; key = kv.first; }
+                            std::vector<int> keepv;
+                            for (int i : rest) {
+                                const uint16_t* cd = &tr.codes[4 * (size_t)i];
+                                bool has = false;
+                                for (int f = 0; f < nf; ++f) has |= cd[f] == key;
+                                (has ? grp : keepv).push_back(i);
+                            }
+                            rest.swap(keepv);
+                        }
+                        for (size_t gi = 0; gi < grp.size(); ++gi) {
+                            const int i = grp[gi];
+                            const uint16_t* cd = &tr.codes[4 * (size_t)i];
+                            uint16_t ord[4] = {0, 0, 0, 0};
+                            int no = 0;
+                            bool taken = false;
+                            for (int f = 0; f < nf; ++f) {
+                                if (key >= 0 && !taken && cd[f] == key) { taken = true; continue; }
+                                ord[no++] = cd[f];
+                            }
+                            per[nu].push_back(make_leaf_gr(key, ord, no, tr.laa[i], tr.lmult[i], gi + 1 == grp.size()));
+                        }
+                    }
                 }
                 if (!per[nu].empty()) lastnu = nu;
             }
@@ -395,6 +459,7 @@ static void upload_stream(aceb200_model* m)
         ntinfo = std::max(ntinfo, nt);
     }
     const size_t nchunks = (longest + g.KB - 1) / g.KB;
+    for (int w = 0; w < kStreamWarps; ++w) m->stream_nblk[w] = (int)sub[w].size();
     for (auto& v : sub) while (v.size() < nchunks * g.KB) add_block(v, nullptr, 0, 0u, -1, 0.0);   // inert padding blocks
 
     // ctl (shared by all passes)
@@ -648,7 +713,7 @@ static void launch_pool_t(aceb200_model* m, const PoolParams& p, dim3 grid, size
     ACE_LAUNCH(kfn, grid, dim3(kPoolThreads), smem, m->cur->stream, p);
 }
 
-static void launch_pool(aceb200_model* m, const BatchDev& B, long long ldA)
+static void launch_pool(aceb200_model* m, const BatchDev& B, long long nJ, long long ldA)
 {
     HostTables& T = m->T;
     PoolParams p;
@@ -657,7 +722,15 @@ static void launch_pool(aceb200_model* m, const BatchDev& B, long long ldA)
     if (m->n_pool_blk > kPoolThreads * kPoolBItems || T.nS >= 0xffff || T.nQ > 0xffff)
         throw ModelError(ACEB200_EUNSUPPORTED, "one-particle basis too large for k_pool (more than 256 slot blocks)");
     p.blk = m->d_pool_blk; p.nblk = m->n_pool_blk;
-    p.TE = 8;
+    // environments per CTA: a multiple of the whole environments one 128-row sub-tile holds, so that the last
+    // sub-tile of a CTA is as full as the others
+    {
+        const double Jbar = std::max(1.0, (double)nJ / (double)std::max<long long>(1, B.nenv));
+        int k = (int)(kPoolThreads / Jbar);
+        k = std::max(1, std::min(k, kPoolThreads * kPoolBItems / std::max(1, p.nblk)));
+        p.TE = k >= 8 ? std::min(k, kPoolTEmax) : k * ((8 + k - 1) / k);
+        if (p.TE > kPoolTEmax) p.TE = (kPoolTEmax / k) * k;
+    }
     p.nP = (T.Lused + 1) * (T.Lused + 2) / 2;
     const size_t smem = (size_t)kPoolPitch * (p.nP * sizeof(c2) + m->rp.N * sizeof(double)) + (kPoolThreads + kPoolTEmax + 1) * sizeof(int);
     dim3 grid((unsigned)((B.nenv + p.TE - 1) / p.TE));
@@ -760,6 +833,7 @@ static void launch_adjoint(aceb200_model* m, long long nenv, long long ldA, bool
         for (const StreamPass& sp : m->passes) {
             StreamParams p;
             p.nS = T.nS; p.has_const = T.has_const; p.want_D = want_D ? 1 : 0; p.nchunks = m->stream_chunks; p.ntinfo = m->stream_ntinfo;
+            for (int w = 0; w < kStreamWarps; ++w) p.nblk[w] = m->stream_nblk[w];
             p.P = T.P; p.pb0 = sp.pb0;
             p.stream = sp.blocks.as<uint4>(); p.ctl = m->d_ctl.as<unsigned>(); p.tinfo = sp.tinfo.as<uint4>(); p.w0 = sp.w0.as<double>();
             p.Ac = m->cur->ws_Ac.as<c2>(); p.ldA = ldA; p.Dt = m->cur->ws_Dt.as<c2>(); p.E = m->cur->ws_E.as<double>(); p.nenv = nenv;
@@ -812,11 +886,25 @@ static void launch_forces(aceb200_model* m, const BatchDev& B, long long nJ, lon
     p.rp = m->rp; p.ap = m->ap; p.C = m->C; p.B = B;
     p.Dt = m->cur->ws_Dt.as<c2>(); p.ldA = ldA; p.P = m->T.P; p.nprop = m->T.nprop; p.ncomp = m->T.ncomp; p.G = G;
     const int pb = m->PB == 1 ? 1 : (m->PB == 3 ? 3 : 2);
-    const size_t smem = (size_t)m->T.nS * pb * kForceTE * sizeof(c2) + ((size_t)m->C.nQ * m->C.nPused + kForceTE + 1) * sizeof(int);
+    p.dpitch = (m->T.nS * pb) | 1;
+    // environments per CTA: the largest TE (within shared memory for 5 CTAs per SM, and leaving two waves of
+    // CTAs) whose neighbours waste the fewest lanes of the last pass over kForceThreads
+    const size_t misc = ((size_t)m->C.nQ * m->C.nPused + kForceTEmax + 1) * sizeof(int) + (size_t)m->NMAX * kForceThreads * sizeof(double);
+    const double Jbar = (double)nJ / (double)B.nenv;
+    int best = 1;
+    double besteff = 0.0;
+    for (int te = 1; te <= kForceTEmax; ++te) {
+        const size_t sm = (size_t)te * p.dpitch * sizeof(c2) + misc;
+        if (te > 1 && (sm > (size_t)m->smem_optin / ACE_FORCE_MINB - 1024 || (B.nenv + te - 1) / te < 2LL * 5 * m->sm_count)) break;
+        const double rows = te * Jbar, eff = rows / (kForceThreads * ceil(rows / kForceThreads));
+        if (eff >= besteff - 1e-9) { besteff = eff; best = te; }
+    }
+    p.TE = best;
+    const size_t smem = (size_t)p.TE * p.dpitch * sizeof(c2) + misc;
     const bool sp = B.species != nullptr;
     if (smem > (size_t)m->smem_optin)
         throw ModelError(ACEB200_EUNSUPPORTED, "one-particle basis too large for the shared-memory staging of k_forces");
-    const unsigned grid = (unsigned)((B.nenv + kForceTE - 1) / kForceTE);
+    const unsigned grid = (unsigned)((B.nenv + p.TE - 1) / p.TE);
 #define ACE_F2(NM, PBV) { if (sp) launch_forces_t<NM, PBV, true>(m, p, grid, smem); else launch_forces_t<NM, PBV, false>(m, p, grid, smem); }
 #define ACE_F(NM) { if (pb == 1) ACE_F2(NM, 1) else if (pb == 3) ACE_F2(NM, 3) else ACE_F2(NM, 2) }
     switch (m->NMAX) {
@@ -979,7 +1067,7 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
         L.ws_Ac.reserve((size_t)T.nS * ldA * sizeof(c2));
         if (want & W_G) L.ws_Dt.reserve((size_t)T.nS * P * ldA * sizeof(c2));
         CU(cudaEventRecord(L.ev0, L.stream));
-        launch_pool(m, B, ldA);
+        launch_pool(m, B, nj, ldA);
         L.timed_ef = (want & (W_E | W_G)) != 0;
 
         if (want & (W_E | W_G)) {

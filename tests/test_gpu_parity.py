@@ -35,6 +35,7 @@ CASES = [
     ("inv_morse_2_6", 1, [6, 20]),
     ("inv_agnesi_2_6", 1, [6, 20]),
     ("inv_highL_2_12", 1, [5, 17]),
+    ("inv_sparse_4_8", 1, [7, 21]),                       # order 4 through the grouped single-channel stream
     ("inv_complexB_2_5", 1, [6, 20, 33]),                   # complex B / dB outputs (symreal = false)
 ]
 
