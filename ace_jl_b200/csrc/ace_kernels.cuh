@@ -111,7 +111,7 @@ constexpr int kPoolItems = 4;       // (environment, slot) items a thread can ow
 constexpr int kPoolPitch = 129;     // staging row pitch (elements)
 constexpr int kPoolTEmax = 16;
 
-template <int NMAX, bool SPECIES>
+template <int NMAX, bool SPECIES, int WALK>
 __global__ void __launch_bounds__(kPoolThreads) k_pool(const PoolParams p)
 {
     ACE_DYN_SMEM(c2, smem);
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kPoolThreads) k_pool(const PoolParams p)
             radial_e<NMAX>(p.rp, sp.r, Rn);
 #pragma unroll
             for (int n = 0; n < NMAX; ++n) if (n < N) SR[n * kPoolPitch + tid] = Rn[n];
-            for_each_lm(p.ap, sp, [&](int l, int m, double Pv, double epr, double epi) {
+            for_each_lm<WALK>(p.ap, sp, [&](int l, int m, double Pv, double epr, double epi) {
                 SY[index_p(l, m) * kPoolPitch + tid] = c2{epr * Pv, epi * Pv};
             });
         }
@@ -837,7 +837,7 @@ __device__ __forceinline__ void column_dot(const c2* D, int cnt, const double (&
 // ([local env][slot][channel]: the slots of a column are a compile-time stride apart) together with the
 // (species, l, m) -> column table and the environments' neighbour offsets, then runs one thread per neighbour
 // of those environments.
-template <int NMAX, int PB, bool SPECIES>
+template <int NMAX, int PB, bool SPECIES, int WALK>
 __global__ void __launch_bounds__(kForceThreads, ACE_FORCE_MINB) k_forces(const ForceParams p)
 {
     ACE_DYN_SMEM(c2, Ds);   // [TE][dpitch >= nS * PB], double dR[NMAX][kForceThreads], int colinfo[nQ * nPused], int joff[TE + 1]
@@ -882,7 +882,7 @@ __global__ void __launch_bounds__(kForceThreads, ACE_FORCE_MINB) k_forces(const 
             double S0[PB], S1[PB], S2[PB];
 #pragma unroll
             for (int c = 0; c < PB; ++c) { S0[c] = 0.0; S1[c] = 0.0; S2[c] = 0.0; }
-            for_each_lm_ed(p.ap, sp, [&](int l, int m, double Pt, double dP, double epr, double epi) {
+            for_each_lm_ed<WALK>(p.ap, sp, [&](int l, int m, double Pt, double dP, double epr, double epi) {
                 const int ci = cinfo[index_p(l, m)];
                 if (ci < 0) return;
                 const int cnt = ci >> 16, base = ci & 0xffff;
@@ -902,7 +902,7 @@ __global__ void __launch_bounds__(kForceThreads, ACE_FORCE_MINB) k_forces(const 
                 }
             });
             // g = rhat S0 + (1/r) [ sphi S1 + cphi cth S2,  -cphi S1 + sphi cth S2,  -sth S2 ]
-            const double rx = x * sp.rinv, ry = y * sp.rinv, rz = z * sp.rinv;
+            const double rx = sp.sth * sp.cphi, ry = sp.sth * sp.sphi, rz = sp.cth;   // rhat (x, y, z need not stay live)
 #pragma unroll
             for (int c = 0; c < PB; ++c) {
                 if (pb + c >= p.P) break;
@@ -922,7 +922,7 @@ __global__ void __launch_bounds__(kForceThreads, ACE_FORCE_MINB) k_forces(const 
 // ------------------------------------------------------------------------------------------------
 
 // canonical slots -> the reference's A vector: A[e][iA] (src/product_1pbasis.jl:123-134)
-__global__ void k_expand_A(long long nenv, int nA, const int* code, const c2* Ac, long long ldA, c2* A)
+static __global__ void k_expand_A(long long nenv, int nA, const int* code, const c2* Ac, long long ldA, c2* A)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nenv * nA) return;
@@ -933,7 +933,7 @@ __global__ void k_expand_A(long long nenv, int nA, const int* code, const c2* Ac
 }
 
 // AA[e][i] = real?(prod_t A[e][spec[i][t]])  (src/pibasis.jl:265-275)
-__global__ void k_AA(long long nenv, int nA, int nAA, int maxord, const int* orders, const int* spec,
+static __global__ void k_AA(long long nenv, int nA, int nAA, int maxord, const int* orders, const int* spec,
                      const c2* A, int pireal, double* AA)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -949,7 +949,7 @@ __global__ void k_AA(long long nenv, int nA, int nAA, int maxord, const int* ord
 }
 
 // B[e][row][c] = real?(sum_k A2B[row,k][c] * AA[e][col_k])  (src/symmbasis.jl:248-264, 312-316), row-parallel CSR
-__global__ void k_B(long long nenv, int nB, int nAA, int ncomp, const int* ptr, const int* col, const c2* val,
+static __global__ void k_B(long long nenv, int nB, int nAA, int ncomp, const int* ptr, const int* col, const c2* val,
                     const double* AA, int pireal, int symreal, double* B)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1079,7 +1079,7 @@ __global__ void __launch_bounds__(kPoolThreads) k_pool_w(const PoolWParams p)
 }
 
 // dAAw[e][i] = real?( sum_t dAw[v_t] prod_{s != t} A[v_s] )   (src/evaluator.jl:228-235)
-__global__ void k_AAw(long long nenv, int nA, int nAA, int maxord, const int* orders, const int* spec,
+static __global__ void k_AAw(long long nenv, int nA, int nAA, int maxord, const int* orders, const int* spec,
                       const c2* A, const c2* Aw, int symreal, double* out)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1103,7 +1103,7 @@ __global__ void k_AAw(long long nenv, int nA, int nAA, int maxord, const int* or
 }
 
 // out[e][row][c] = sum_k A2B[row,k][c] * dAAw[e][col_k]   (dB = A2Bmap * dAAw, src/evaluator.jl:237); complex
-__global__ void k_Bw(long long nenv, int nB, int nAA, int ncomp, const int* ptr, const int* col, const c2* val,
+static __global__ void k_Bw(long long nenv, int nB, int nAA, int ncomp, const int* ptr, const int* col, const c2* val,
                      const double* AAw, double* out)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1189,7 +1189,7 @@ __global__ void __launch_bounds__(128) k_dA(const dAParams p)
 
 // dAA[j][i][:] = real?(sum_t (prod_{s != t} A_{v_s}) dA[j][v_t][:])  (src/pibasis.jl:402-432)
 constexpr int kMaxOrdDevK = 8;
-__global__ void k_dAA(long long nenv, const long long* off, int nA, int nAA, int maxord, const int* orders, const int* spec,
+static __global__ void k_dAA(long long nenv, const long long* off, int nA, int nAA, int maxord, const int* orders, const int* spec,
                       const c2* A, const c2* dA, int pireal, double* dAA)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1223,7 +1223,7 @@ __global__ void k_dAA(long long nenv, const long long* off, int nA, int nAA, int
 }
 
 // dB[j][row][xyz][c] = real?(sum_k A2B[row,k][c] * dAA[j][col_k][xyz])  (src/symmbasis.jl:330-334, src/properties.jl:53-59)
-__global__ void k_dB(long long nJ, int nB, int nAA, int ncomp, const int* ptr, const int* col, const c2* val,
+static __global__ void k_dB(long long nJ, int nB, int nAA, int ncomp, const int* ptr, const int* col, const c2* val,
                      const double* dAA, int pireal, int symreal, double* dB)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -1,0 +1,54 @@
+// ace_launch.h -- the two large kernel families (k_pool, k_forces) are instantiated in one translation unit per
+// radial bound NMAX (inst_NN.cu, generated from inst_template.cuh) so that the library builds in parallel.
+#pragma once
+
+#include <stdexcept>
+#include <string>
+
+#include "../../include/aceb200.h"
+#include "ace_kernels.cuh"
+#include "ace_tables.h"
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t err__ = (call);                                                               \
+        if (err__ != cudaSuccess)                                                                 \
+            throw ModelError(err__ == cudaErrorMemoryAllocation ? ACEB200_ENOMEM : ACEB200_ECUDA, \
+                             std::string(#call) + ": " + cudaGetErrorString(err__));              \
+    } while (0)
+
+namespace aceb200 {
+
+#define ACE_INST_DECL(N)                                                                                                    \
+    void forces_inst_##N(int pb, bool species, bool staticL, const ForceParams& p, unsigned grid, size_t smem, cudaStream_t st); \
+    void pool_inst_##N(bool species, bool staticL, const PoolParams& p, unsigned grid, size_t smem, cudaStream_t st);
+ACE_INST_DECL(4) ACE_INST_DECL(8) ACE_INST_DECL(12) ACE_INST_DECL(16) ACE_INST_DECL(20) ACE_INST_DECL(24) ACE_INST_DECL(32)
+#undef ACE_INST_DECL
+
+inline void launch_forces_inst(int nmax, int pb, bool species, bool staticL, const ForceParams& p, unsigned grid, size_t smem, cudaStream_t st)
+{
+    switch (nmax) {
+    case 4: forces_inst_4(pb, species, staticL, p, grid, smem, st); break;
+    case 8: forces_inst_8(pb, species, staticL, p, grid, smem, st); break;
+    case 12: forces_inst_12(pb, species, staticL, p, grid, smem, st); break;
+    case 16: forces_inst_16(pb, species, staticL, p, grid, smem, st); break;
+    case 20: forces_inst_20(pb, species, staticL, p, grid, smem, st); break;
+    case 24: forces_inst_24(pb, species, staticL, p, grid, smem, st); break;
+    default: forces_inst_32(pb, species, staticL, p, grid, smem, st); break;
+    }
+}
+
+inline void launch_pool_inst(int nmax, bool species, bool staticL, const PoolParams& p, unsigned grid, size_t smem, cudaStream_t st)
+{
+    switch (nmax) {
+    case 4: pool_inst_4(species, staticL, p, grid, smem, st); break;
+    case 8: pool_inst_8(species, staticL, p, grid, smem, st); break;
+    case 12: pool_inst_12(species, staticL, p, grid, smem, st); break;
+    case 16: pool_inst_16(species, staticL, p, grid, smem, st); break;
+    case 20: pool_inst_20(species, staticL, p, grid, smem, st); break;
+    case 24: pool_inst_24(species, staticL, p, grid, smem, st); break;
+    default: pool_inst_32(species, staticL, p, grid, smem, st); break;
+    }
+}
+
+}  // namespace aceb200

@@ -203,7 +203,11 @@ ACE_HD inline Spher cart2spher(double x, double y, double z)
 // instructions instead of indexed loads.  Models referencing a higher l take the rolled loop.
 constexpr int kStaticL = 6;
 
-template <class F>
+// WALK selects the code that is generated: kWalkAny (both, chosen at run time), kWalkStatic (the model is known
+// to have L <= kStaticL), kWalkRolled.  The hot kernels are instantiated per walk so that each carries one copy.
+constexpr int kWalkAny = 0, kWalkStatic = 1, kWalkRolled = 2;
+
+template <int WALK = kWalkAny, class F>
 ACE_HD inline void for_each_lm(const AlpParams& ap, const Spher& S, F&& f)
 {
     const int L = ap.L;
@@ -211,7 +215,7 @@ ACE_HD inline void for_each_lm(const AlpParams& ap, const Spher& S, F&& f)
     const double is2 = 0.70710678118654752;   // 1/sqrt(2)
     double dg = P00;                          // P_m^m
     double epr = is2, epi = 0.0;
-    if (L <= kStaticL) {
+    if (WALK == kWalkStatic || (WALK == kWalkAny && L <= kStaticL)) {
 #pragma unroll
         for (int m = 0; m <= kStaticL; ++m) {
             if (m > L) break;
@@ -235,6 +239,7 @@ ACE_HD inline void for_each_lm(const AlpParams& ap, const Spher& S, F&& f)
         }
         return;
     }
+    if (WALK == kWalkStatic) return;
     for (int m = 0; m <= L; ++m) {
         if (m > 0) {
             dg = -ap.diagc[m] * S.sth * dg;   // :180, :192
@@ -258,7 +263,7 @@ ACE_HD inline void for_each_lm(const AlpParams& ap, const Spher& S, F&& f)
 //   Pt = P_l^m / sin th for m >= 1, P_l^0 for m = 0   (the pole-stable storage of :208-267)
 //   dP = d P_l^m / d theta
 // from which  Y_l^m = ep Pt sin th (m >= 1),  dY/dphi / sin th = i m ep Pt,  dY/dtheta = ep dP  (:410-443).
-template <class F>
+template <int WALK = kWalkAny, class F>
 ACE_HD inline void for_each_lm_ed(const AlpParams& ap, const Spher& S, F&& f)
 {
     const int L = ap.L;
@@ -267,7 +272,7 @@ ACE_HD inline void for_each_lm_ed(const AlpParams& ap, const Spher& S, F&& f)
     double dgt = P00, dgd = 0.0;              // diagonal Pt_m^m, dP_m^m (temp1, temp_d of :229-263)
     double epr = is2, epi = 0.0;
     const double s2 = S.sth * S.sth;
-    if (L <= kStaticL) {
+    if (WALK == kWalkStatic || (WALK == kWalkAny && L <= kStaticL)) {
 #pragma unroll
         for (int m = 0; m <= kStaticL; ++m) {
             if (m > L) break;
@@ -306,6 +311,7 @@ ACE_HD inline void for_each_lm_ed(const AlpParams& ap, const Spher& S, F&& f)
         }
         return;
     }
+    if (WALK == kWalkStatic) return;
     for (int m = 0; m <= L; ++m) {
         const double sfac = (m == 0) ? S.sth : s2;   // -sin th P (m = 0, :241) vs -sin^2 th Pt (:251)
         if (m == 1) {

@@ -18,6 +18,7 @@
 #include "ace_platform.cuh"
 #include "ace_kernels.cuh"
 #include "ace_tables.h"
+#include "ace_launch.h"
 
 using namespace aceb200;
 
@@ -29,13 +30,7 @@ static thread_local int g_device = 0;
 
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
-#define CU(call)                                                                                  \
-    do {                                                                                          \
-        cudaError_t err__ = (call);                                                               \
-        if (err__ != cudaSuccess)                                                                 \
-            throw ModelError(err__ == cudaErrorMemoryAllocation ? ACEB200_ENOMEM : ACEB200_ECUDA, \
-                             std::string(#call) + ": " + cudaGetErrorString(err__));              \
-    } while (0)
+// CU(call): throw ModelError on a CUDA error (ace_launch.h)
 
 // ----------------------------------------------------------------------------------------------
 // device buffers
@@ -699,20 +694,6 @@ static BatchDev batch_dev(const Staged& s, const Chunk& c)
 // ----------------------------------------------------------------------------------------------
 // kernel launch helpers
 // ----------------------------------------------------------------------------------------------
-template <int NMAX>
-static void launch_pool_t(aceb200_model* m, const PoolParams& p, dim3 grid, size_t smem)
-{
-    if (p.B.species) {
-        auto kfn = k_pool<NMAX, true>;
-        CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ACE_LAUNCH(kfn, grid, dim3(kPoolThreads), smem, m->cur->stream, p);
-        return;
-    }
-    auto kfn = k_pool<NMAX, false>;
-    CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ACE_LAUNCH(kfn, grid, dim3(kPoolThreads), smem, m->cur->stream, p);
-}
-
 static void launch_pool(aceb200_model* m, const BatchDev& B, long long nJ, long long ldA)
 {
     HostTables& T = m->T;
@@ -734,15 +715,7 @@ static void launch_pool(aceb200_model* m, const BatchDev& B, long long nJ, long 
     p.nP = (T.Lused + 1) * (T.Lused + 2) / 2;
     const size_t smem = (size_t)kPoolPitch * (p.nP * sizeof(c2) + m->rp.N * sizeof(double)) + (kPoolThreads + kPoolTEmax + 1) * sizeof(int);
     dim3 grid((unsigned)((B.nenv + p.TE - 1) / p.TE));
-    switch (m->NMAX) {
-    case 4: launch_pool_t<4>(m, p, grid, smem); break;
-    case 8: launch_pool_t<8>(m, p, grid, smem); break;
-    case 12: launch_pool_t<12>(m, p, grid, smem); break;
-    case 16: launch_pool_t<16>(m, p, grid, smem); break;
-    case 20: launch_pool_t<20>(m, p, grid, smem); break;
-    case 24: launch_pool_t<24>(m, p, grid, smem); break;
-    default: launch_pool_t<32>(m, p, grid, smem); break;
-    }
+    launch_pool_inst(m->NMAX, p.B.species != nullptr, p.ap.L <= kStaticL, p, grid.x, smem, m->cur->stream);
     CU(cudaGetLastError());
     m->launches++;
 }
@@ -871,14 +844,6 @@ static void launch_adjoint(aceb200_model* m, long long nenv, long long ldA, bool
     m->launches++;
 }
 
-template <int NMAX, int PB, bool SPECIES>
-static void launch_forces_t(aceb200_model* m, const ForceParams& p, unsigned grid, size_t smem)
-{
-    auto kfn = k_forces<NMAX, PB, SPECIES>;
-    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ACE_LAUNCH(kfn, dim3(grid), dim3(kForceThreads), smem, m->cur->stream, p);
-}
-
 static void launch_forces(aceb200_model* m, const BatchDev& B, long long nJ, long long ldA, double* G)
 {
     if (nJ == 0) return;
@@ -905,19 +870,7 @@ static void launch_forces(aceb200_model* m, const BatchDev& B, long long nJ, lon
     if (smem > (size_t)m->smem_optin)
         throw ModelError(ACEB200_EUNSUPPORTED, "one-particle basis too large for the shared-memory staging of k_forces");
     const unsigned grid = (unsigned)((B.nenv + p.TE - 1) / p.TE);
-#define ACE_F2(NM, PBV) { if (sp) launch_forces_t<NM, PBV, true>(m, p, grid, smem); else launch_forces_t<NM, PBV, false>(m, p, grid, smem); }
-#define ACE_F(NM) { if (pb == 1) ACE_F2(NM, 1) else if (pb == 3) ACE_F2(NM, 3) else ACE_F2(NM, 2) }
-    switch (m->NMAX) {
-    case 4: ACE_F(4) break;
-    case 8: ACE_F(8) break;
-    case 12: ACE_F(12) break;
-    case 16: ACE_F(16) break;
-    case 20: ACE_F(20) break;
-    case 24: ACE_F(24) break;
-    default: ACE_F(32) break;
-    }
-#undef ACE_F
-#undef ACE_F2
+    launch_forces_inst(m->NMAX, pb, sp, p.ap.L <= kStaticL, p, grid, smem, m->cur->stream);
     CU(cudaGetLastError());
     m->launches++;
 }
