@@ -101,8 +101,10 @@ struct PoolParams {
     int TE;                 // environments per CTA (<= kPoolTEmax)
     int nP;                 // harmonics staged per neighbour: sizeP(L)
     const int4* blk;        // [nblk] 2 x 2 register blocks of slots (two radial indices x two columns of one species):
-    int nblk;               //   x = n0 | n1 << 8 | q << 16,  y = ip0 | ip1 << 16,
+    int nblk, nbp;          //   x = n0 | n1 << 8 | q << 16,  y = ip0 | ip1 << 16,
                             //   z = slot(n0, col0) | slot(n1, col0) << 16,  w = slot(n0, col1) | slot(n1, col1) << 16  (0xffff: none)
+                            // nbp >= nblk: lanes reserved per environment in phase b (a power of two up to 32, or a multiple
+                            // of 32), so that the lanes that share a shared-memory wavefront belong to one environment
 };
 
 constexpr int kPoolThreads = 128;
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(kPoolThreads) k_pool(const PoolParams p)
     int* sq = reinterpret_cast<int*>(SR + (size_t)p.rp.N * kPoolPitch);        // [128] species of the staged neighbour
     int* joff = sq + kPoolThreads;                                             // [TE + 1] neighbour offsets relative to the CTA's first
     const int tid = threadIdx.x;
-    const int N = p.rp.N, nblk = p.nblk;
+    const int N = p.rp.N, nblk = p.nblk, nbp = p.nbp;
     const long long e0 = (long long)blockIdx.x * p.TE;
     if (e0 >= p.B.nenv) return;
     const int ne = (int)((p.B.nenv - e0) < p.TE ? (p.B.nenv - e0) : p.TE);
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(kPoolThreads) k_pool(const PoolParams p)
         int e2 = e + 1, j1;
         bool done_e;                      // the environments of this sub-tile are complete after it
         if (j0 == joff[e] && jend_e - j0 <= kPoolThreads) {
-            while (e2 < ne && joff[e2 + 1] - j0 <= kPoolThreads && (e2 + 1 - e) * nblk <= kPoolThreads * kPoolBItems) ++e2;
+            while (e2 < ne && joff[e2 + 1] - j0 <= kPoolThreads && (e2 + 1 - e) * nbp <= kPoolThreads * kPoolBItems) ++e2;
             j1 = joff[e2];
             done_e = true;
         } else {
@@ -174,12 +176,12 @@ __global__ void __launch_bounds__(kPoolThreads) k_pool(const PoolParams p)
 
         // ---- phase b: one (environment, 2 x 2 slot block) item accumulates r_{n0,n1}[j] * y_{col0,col1}[j] over
         // the environment's staged rows: four shared-memory loads feed eight FP64 FMAs
-        const int nitems = (e2 - e) * nblk;
+        const int nitems = (e2 - e) * nbp;
 #pragma unroll
         for (int it = 0; it < kPoolBItems; ++it) {
             const int idx = tid + it * kPoolThreads;
-            if (idx < nitems) {
-                const int el = idx / nblk, b = idx - el * nblk;
+            const int el = idx / nbp, b = idx - el * nbp;
+            if (idx < nitems && b < nblk) {
                 const int4 d = __ldg(p.blk + b);
                 int ra = joff[e + el] - j0, rb = joff[e + el + 1] - j0;
                 if (ra == rb && b == 0) atomicMax(p.errflag, 5);          // EEMPTY (src/product_1pbasis.jl:124)

@@ -703,12 +703,15 @@ static void launch_pool(aceb200_model* m, const BatchDev& B, long long nJ, long 
     if (m->n_pool_blk > kPoolThreads * kPoolBItems || T.nS >= 0xffff || T.nQ > 0xffff)
         throw ModelError(ACEB200_EUNSUPPORTED, "one-particle basis too large for k_pool (more than 256 slot blocks)");
     p.blk = m->d_pool_blk; p.nblk = m->n_pool_blk;
+    p.nbp = 1;
+    while (p.nbp < p.nblk && p.nbp < 32) p.nbp *= 2;
+    if (p.nblk > 32) p.nbp = ((p.nblk + 31) / 32) * 32;
     // environments per CTA: a multiple of the whole environments one 128-row sub-tile holds, so that the last
     // sub-tile of a CTA is as full as the others
     {
         const double Jbar = std::max(1.0, (double)nJ / (double)std::max<long long>(1, B.nenv));
         int k = (int)(kPoolThreads / Jbar);
-        k = std::max(1, std::min(k, kPoolThreads * kPoolBItems / std::max(1, p.nblk)));
+        k = std::max(1, std::min(k, kPoolThreads * kPoolBItems / std::max(1, p.nbp)));
         p.TE = k >= 8 ? std::min(k, kPoolTEmax) : k * ((8 + k - 1) / k);
         if (p.TE > kPoolTEmax) p.TE = (kPoolTEmax / k) * k;
     }
