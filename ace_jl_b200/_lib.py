@@ -51,6 +51,14 @@ class Batch(C.Structure):
     ]
 
 
+class Structure(C.Structure):
+    _fields_ = [
+        ("natoms", C.c_int64), ("npairs", C.c_int64), ("X", c_double_p), ("first", c_int64_p), ("nbr", c_int32_p),
+        ("image", C.POINTER(C.c_int8)), ("species", c_int32_p), ("rev", c_int32_p), ("cell", C.c_double * 9),
+        ("space", C.c_int32), ("_pad", C.c_int32),
+    ]
+
+
 class Sizes(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("nA", "nAA", "nB", "ncomp", "nprop", "maxord", "pireal", "symreal")]
 
@@ -84,6 +92,7 @@ SYMBOLS = [
     ("aceb200_energy", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
     ("aceb200_energy_forces", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p]),
     ("aceb200_adjoint_eval_d", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p]),
+    ("aceb200_structure_energy_forces", C.c_int, [C.c_void_p, C.POINTER(Structure), C.c_void_p, C.c_void_p, C.c_void_p]),
     ("aceb200_model_sizes", C.c_int, [C.c_void_p, C.POINTER(Sizes)]),
     ("aceb200_last_kernel_ms", C.c_int, [C.c_void_p, c_double_p]),
     ("aceb200_last_stage_ms", C.c_int, [C.c_void_p, c_double_p]),

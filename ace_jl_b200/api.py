@@ -227,6 +227,17 @@ class Handle:
         return E, G
 
 
+    def structure_energy_forces(self, st, virial: bool = True, E=None, F=None, W=None):
+        """aceb200_structure_energy_forces: (Esite [natoms][nprop][ncomp], F [natoms][nprop][3][ncomp], W [nprop][3][3] or None).
+        Pre-allocated (e.g. pinned) outputs may be passed in."""
+        E = st.empty((st.natoms, self.s.nprop, self.s.ncomp)) if E is None else E
+        F = st.empty((st.natoms, self.s.nprop, 3, self.s.ncomp)) if F is None else F
+        W = (st.empty((self.s.nprop, 3, 3)) if virial else None) if W is None else W
+        cs = st.c_struct()
+        L.check(self.lib.aceb200_structure_energy_forces(self.ptr, C.byref(cs), _out_ptr(E), _out_ptr(F), _out_ptr(W)))
+        return E, F, W
+
+
 def measure_fp64_tflops() -> float:
     v = C.c_double()
     L.check(L.load().aceb200_measure_fp64(C.byref(v)))
@@ -405,6 +416,16 @@ class LinearACEModel:
         if not self.multi:
             G = G[:, 0]
         return self._shape_val(E, single), G
+
+    def energy_forces_virial(self, st, virial: bool = True):
+        """JuLIP's energy / forces / virial of a whole structure (``B200Structure``) in one call: site energies
+        (natoms[, nprop]), forces (natoms[, nprop], 3), virial ([nprop, ]3, 3)."""
+        E, F, W = self.evaluator.handle.structure_energy_forces(st, virial)
+        if self.evaluator.handle.s.ncomp == 1:
+            E, F = E[..., 0], F[..., 0]
+        if not self.multi:
+            E, F, W = E[:, 0], F[:, 0], (None if W is None else W[0])
+        return E, F, W
 
     def adjoint_EVAL_D(self, cfg, w):
         """src/linearmodel.jl:133-134 -> src/evaluator.jl:204-244: dB_k = sum_j w_j . dB_k/dr_j."""

@@ -1249,4 +1249,129 @@ static __global__ void k_dB(long long nJ, int nB, int nAA, int ncomp, const int*
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// caller side of the path: an atomic structure + neighbour list in, site energies and
+// atomic forces out.  In the reference ecosystem this loop lives in JuLIP / ACEatoms.jl
+// (forces(V, at): for each centre i, dV = evaluate_d(V, Rs); frc[j] -= dV_j; frc[i] += dV_j), around the
+// per-environment calls of ACE.jl.  Doing it on the device removes the 24 B/pair each way that the
+// per-environment interface has to move over PCIe.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPairAtoms = 32;      // centres per CTA of k_build_pairs
+
+struct CellDev { double c[9]; };
+
+// R_p = X[nbr_p] + S_p . cell - X[i(p)],  species_p = species[nbr_p]   for the pairs of centres [a0, a0 + na)
+static __global__ void k_build_pairs(long long a0, long long na, long long natoms, const long long* first, const int* nbr,
+                                     const signed char* image, const CellDev cell, const double* X, const int* spc, double* R, int* sp,
+                                     int* errflag)
+{
+    ACE_DYN_SMEM(long long, f);                 // [kPairAtoms + 1]
+    const long long c0 = a0 + (long long)blockIdx.x * kPairAtoms;
+    if (c0 >= a0 + na) return;
+    const int nc = (int)((a0 + na - c0) < kPairAtoms ? (a0 + na - c0) : kPairAtoms);
+    if ((int)threadIdx.x <= nc) f[threadIdx.x] = first[c0 + threadIdx.x];
+    __syncthreads();
+    for (long long p = f[0] + threadIdx.x; p < f[nc]; p += blockDim.x) {
+        int lo = 0, hi = nc;                       // centre of pair p: the last c with f[c] <= p
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (f[mid] <= p) lo = mid; else hi = mid; }
+        const long long i = c0 + lo;
+        long long j = nbr[p];
+        if (j < 0 || j >= natoms) { atomicMax(errflag, 1); j = i; }
+        double x = X[3 * j] - X[3 * i], y = X[3 * j + 1] - X[3 * i + 1], z = X[3 * j + 2] - X[3 * i + 2];
+        if (image) {
+            const double s0 = (double)image[3 * p], s1 = (double)image[3 * p + 1], s2 = (double)image[3 * p + 2];
+            x += s0 * cell.c[0] + s1 * cell.c[3] + s2 * cell.c[6];
+            y += s0 * cell.c[1] + s1 * cell.c[4] + s2 * cell.c[7];
+            z += s0 * cell.c[2] + s1 * cell.c[5] + s2 * cell.c[8];
+        }
+        R[3 * p] = x; R[3 * p + 1] = y; R[3 * p + 2] = z;
+        if (sp) sp[p] = spc[j];
+    }
+}
+
+// rev[p] for the pairs of 32 centres per CTA: scan the pair list of j = nbr[p] for (neighbour i, image -S)
+static __global__ void k_find_rev(long long natoms, const long long* first, const int* nbr, const signed char* image, int* rev)
+{
+    ACE_DYN_SMEM(long long, f);                 // [kPairAtoms + 1]
+    const long long c0 = (long long)blockIdx.x * kPairAtoms;
+    if (c0 >= natoms) return;
+    const int nc = (int)((natoms - c0) < kPairAtoms ? (natoms - c0) : kPairAtoms);
+    if ((int)threadIdx.x <= nc) f[threadIdx.x] = first[c0 + threadIdx.x];
+    __syncthreads();
+    for (long long p = f[0] + threadIdx.x; p < f[nc]; p += blockDim.x) {
+        int lo = 0, hi = nc;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (f[mid] <= p) lo = mid; else hi = mid; }
+        const int i = (int)(c0 + lo);
+        const long long j = nbr[p];
+        int found = -1;
+        if (j >= 0 && j < natoms) {
+            int s0 = 0, s1 = 0, s2 = 0;
+            if (image) { s0 = -image[3 * p]; s1 = -image[3 * p + 1]; s2 = -image[3 * p + 2]; }
+            for (long long q = first[j]; q < first[j + 1]; ++q) {
+                if (nbr[q] != i) continue;
+                if (image && (image[3 * q] != s0 || image[3 * q + 1] != s1 || image[3 * q + 2] != s2)) continue;
+                found = (int)q;
+                break;
+            }
+        }
+        rev[p] = found;
+    }
+}
+
+// F_i[k] = sum_{p in env(i)} ( g_p[k] - g_{rev(p)}[k] ),  k over the K = nprop * 3 * ncomp components of a pair
+// gradient: a gather over the reverse-pair table, no atomics, fixed summation order.
+static __global__ void k_assemble_rev(long long natoms, int K, const long long* first, const int* rev, const double* G,
+                                      double* F, int* errflag, long long npairs)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= natoms * K) return;
+    const long long i = t / K;
+    const int k = (int)(t - i * K);
+    double acc = 0.0;
+    for (long long p = first[i]; p < first[i + 1]; ++p) {
+        const long long q = rev[p];
+        double v = G[(size_t)p * K + k];
+        if (q >= 0 && q < npairs) v -= G[(size_t)q * K + k];
+        else if (q >= npairs) atomicMax(errflag, 1);
+        acc += v;                                   // q < 0: the neighbour is not a centre (no reverse pair)
+    }
+    F[t] = acc;
+}
+
+// virial  W[prop][a][b] = - sum_p g_p[prop][a] R_p[b]  (JuLIP: site_virial = -sum dV_j (x) R_j), two deterministic stages
+constexpr int kVirThreads = 256;
+static __global__ void k_virial_partial(long long npairs, int nprop, const double* G, const double* R, double* part)
+{
+    ACE_DYN_SMEM(double, red);                  // [kVirThreads]
+    const int prop = blockIdx.y;
+    double w[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npairs; p += (long long)gridDim.x * blockDim.x) {
+        const double* g = G + ((size_t)p * nprop + prop) * 3;
+        const double* r = R + (size_t)p * 3;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) w[a * 3 + b] -= g[a] * r[b];
+    }
+    for (int c = 0; c < 9; ++c) {
+        red[threadIdx.x] = w[c];
+        __syncthreads();
+        for (int s = kVirThreads / 2; s > 0; s >>= 1) {
+            if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) part[((size_t)prop * gridDim.x + blockIdx.x) * 9 + c] = red[0];
+        __syncthreads();
+    }
+}
+
+static __global__ void k_virial_final(int nblocks, const double* part, double* W)
+{
+    const int prop = blockIdx.x, c = threadIdx.x;
+    if (c >= 9) return;
+    double acc = 0.0;
+    for (int b = 0; b < nblocks; ++b) acc += part[((size_t)prop * nblocks + b) * 9 + c];
+    W[prop * 9 + c] = acc;
+}
+
 }  // namespace aceb200

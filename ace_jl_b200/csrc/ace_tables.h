@@ -56,6 +56,7 @@ struct Tree {
 struct HostTables {
     // sizes and flags
     int nA = 0, nAA = 0, nB = 0, ncomp = 1, nprop = 1, P = 1, maxord = 0, nS = 0, ncols = 0, Lused = 0, nQ = 1;
+    bool has_cat = false;               // the one-particle basis has a Categorical1pBasis component
     int pireal = 0, symreal = 0, has_const = 0;
     bool cw = false;   // complex weights
     // one-particle decode
@@ -112,6 +113,7 @@ inline void build_tables(const aceb200_desc& d, HostTables& T)
     T.nA = d.nA; T.nAA = d.nAA; T.nB = d.nB; T.ncomp = d.ncomp; T.nprop = d.nprop; T.P = d.nprop * d.ncomp;
     T.maxord = d.maxord; T.pireal = d.pireal; T.symreal = d.symreal;
     T.nQ = ib_cat >= 0 ? d.n_cat : 1;
+    T.has_cat = ib_cat >= 0;
 
     // ---- decode the one-particle functions
     T.iA_q.resize(T.nA); T.iA_n.resize(T.nA); T.iA_l.resize(T.nA); T.iA_m.resize(T.nA);

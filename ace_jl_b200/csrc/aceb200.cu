@@ -118,6 +118,12 @@ struct aceb200_model {
     Lane lanes[kLanes];
     Lane* cur = nullptr;
     DevBuf ws_err;
+    // structure path (aceb200_structure_energy_forces): inputs are copied on copy_stream, chunk by chunk, while
+    // the evaluation of earlier chunks runs on the caller's stream
+    std::mutex mu_s;
+    DevBuf s_X, s_first, s_nbr, s_img, s_spc, s_rev, s_R, s_sp, s_G, s_E, s_F, s_W, s_part, s_err;
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> s_ev;
     cudaStream_t user_stream = nullptr;
     double last_ms = 0.0;
     double stage_ms[3] = {0.0, 0.0, 0.0};   // pool, adjoint, forces of the last energy(_forces) call
@@ -992,7 +998,7 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
     long long step = chunk_envs(b->nenv, per_env, (size_t)8 << 30);
     if (host) {
         // pipeline granularity: a few MiB of positions per chunk, at least ~6 chunks when the batch is large
-        double pipe_mb = 16.0;
+        double pipe_mb = 64.0;
         if (const char* ov = getenv("ACEB200_PIPE_MB")) pipe_mb = std::max(1.0, atof(ov));
         long long pipe = std::max<long long>(4096, (long long)((pipe_mb * 1048576.0) / (24.0 * Jav)));
         pipe = std::min<long long>(pipe, std::max<long long>(4096, (b->nenv + 5) / 6));
@@ -1135,6 +1141,144 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
     check_errflag(m);
 }
 
+// ----------------------------------------------------------------------------------------------
+// the structure driver: neighbour list in, site energies / atomic forces / virial out
+// ----------------------------------------------------------------------------------------------
+static void run_structure(aceb200_model* m, const aceb200_structure* s, double* Esite, double* F, double* W)
+{
+    if (!s) throw ModelError(ACEB200_EDESC, "null structure");
+    if (s->natoms < 0 || s->npairs < 0) throw ModelError(ACEB200_EDESC, "negative natoms / npairs");
+    if (s->space != ACEB200_HOST && s->space != ACEB200_DEVICE) throw ModelError(ACEB200_EDESC, "structure.space must be HOST or DEVICE");
+    HostTables& T = m->T;
+    if (!T.symreal) throw ModelError(ACEB200_EUNSUPPORTED, "structure forces need a real symmetric basis");
+    if (W && T.ncomp != 1) throw ModelError(ACEB200_EUNSUPPORTED, "the virial is defined for scalar (ncomp = 1) properties");
+    if (T.has_cat && !s->species) throw ModelError(ACEB200_EDESC, "the model has a categorical basis: structure.species is required");
+    if (s->npairs >= (1ll << 31)) throw ModelError(ACEB200_EUNSUPPORTED, "structure: npairs must be below 2^31");
+    if (s->natoms == 0) return;
+    if (!s->X || !s->first || (s->npairs > 0 && !s->nbr) || !F) throw ModelError(ACEB200_EDESC, "null X / first / nbr / F");
+    CU(cudaSetDevice(m->device));
+    std::lock_guard<std::mutex> lock(m->mu_s);
+    const bool host = s->space == ACEB200_HOST;
+    const long long na = s->natoms, np = s->npairs;
+    const int P = T.P, K = P * 3;
+    const bool species = T.has_cat;
+    cudaStream_t st = m->user_stream, cs = m->copy_stream;
+
+    // chunks of centres: ~32 MiB of pair tables each when the structure comes from the host (so that the copy
+    // of chunk k+1 overlaps the evaluation of chunk k); one chunk when it is already on the device
+    std::vector<long long> cut{0};
+    if (host) {
+        if (s->first[0] != 0 || s->first[na] != np) throw ModelError(ACEB200_EDESC, "first[0] must be 0 and first[natoms] = npairs");
+        const double pair_bytes = 4.0 + (s->image ? 3.0 : 0.0);
+        double chunk_mb = 64.0;
+        if (const char* ov = getenv("ACEB200_STRUCT_MB")) chunk_mb = std::max(0.001, atof(ov));
+        const long long ppc = std::max<long long>(1024, (long long)(chunk_mb * 1048576.0 / pair_bytes));
+        long long a = 0;
+        while (a < na) {
+            const long long target = s->first[a] + ppc;
+            long long b = std::upper_bound(s->first + a + 1, s->first + na + 1, target) - s->first - 1;   // last b with first[b] <= target
+            b = std::max(a + 1, std::min(b, na));
+            cut.push_back(b);
+            a = b;
+        }
+    } else cut.push_back(na);
+    const size_t nch = cut.size() - 1;
+    while (m->s_ev.size() < nch + 2) { cudaEvent_t e; CU(cudaEventCreate(&e)); m->s_ev.push_back(e); }
+
+    m->s_err.reserve(sizeof(int));
+    CU(cudaMemsetAsync(m->s_err.p, 0, sizeof(int), st));
+    m->s_R.reserve(std::max<long long>(np, 1) * 3 * sizeof(double));
+    m->s_G.reserve(std::max<long long>(np, 1) * (size_t)K * sizeof(double));
+    if (species) m->s_sp.reserve(std::max<long long>(np, 1) * sizeof(int));
+    if (host || !s->rev) m->s_rev.reserve(std::max<long long>(np, 1) * sizeof(int));
+    const double* dX; const long long* dfirst; const int* dnbr; const signed char* dimg; const int* dspc; const int* drev;
+    CellDev cell;
+    for (int i = 0; i < 9; ++i) cell.c[i] = s->image ? s->cell[i] : 0.0;
+    double *dE, *dF, *dW;
+    if (host) {
+        m->s_X.reserve(na * 3 * sizeof(double));
+        m->s_first.reserve((na + 1) * sizeof(long long));
+        m->s_nbr.reserve(std::max<long long>(np, 1) * sizeof(int));
+        if (s->image) m->s_img.reserve(std::max<long long>(np, 1) * 3);
+        if (species) m->s_spc.reserve(na * sizeof(int));
+
+        m->s_E.reserve((size_t)na * P * sizeof(double));
+        m->s_F.reserve((size_t)na * K * sizeof(double));
+        m->s_W.reserve((size_t)T.nprop * 9 * sizeof(double));
+        CU(cudaMemcpyAsync(m->s_X.p, s->X, na * 3 * sizeof(double), cudaMemcpyHostToDevice, cs));
+        CU(cudaMemcpyAsync(m->s_first.p, s->first, (na + 1) * sizeof(long long), cudaMemcpyHostToDevice, cs));
+        if (species) CU(cudaMemcpyAsync(m->s_spc.p, s->species, na * sizeof(int), cudaMemcpyHostToDevice, cs));
+        for (size_t k = 0; k < nch; ++k) {
+            const long long j0 = s->first[cut[k]], j1 = s->first[cut[k + 1]];
+            if (j1 > j0) {
+                CU(cudaMemcpyAsync(m->s_nbr.as<int>() + j0, s->nbr + j0, (j1 - j0) * sizeof(int), cudaMemcpyHostToDevice, cs));
+                if (s->image) CU(cudaMemcpyAsync(m->s_img.as<signed char>() + 3 * j0, s->image + 3 * j0, (j1 - j0) * 3, cudaMemcpyHostToDevice, cs));
+            }
+            CU(cudaEventRecord(m->s_ev[k], cs));
+        }
+        if (s->rev && np > 0) CU(cudaMemcpyAsync(m->s_rev.p, s->rev, np * sizeof(int), cudaMemcpyHostToDevice, cs));
+        CU(cudaEventRecord(m->s_ev[nch], cs));
+        dX = m->s_X.as<double>(); dfirst = m->s_first.as<long long>(); dnbr = m->s_nbr.as<int>();
+        dimg = s->image ? m->s_img.as<signed char>() : nullptr; dspc = species ? m->s_spc.as<int>() : nullptr;
+        drev = s->rev ? m->s_rev.as<int>() : nullptr;
+        dE = m->s_E.as<double>(); dF = m->s_F.as<double>(); dW = m->s_W.as<double>();
+    } else {
+        dX = s->X; dfirst = reinterpret_cast<const long long*>(s->first); dnbr = s->nbr; dimg = reinterpret_cast<const signed char*>(s->image);
+        dspc = species ? s->species : nullptr; drev = s->rev;
+        if (!Esite) m->s_E.reserve((size_t)na * P * sizeof(double));
+        dE = Esite ? Esite : m->s_E.as<double>(); dF = F; dW = W;
+    }
+
+    double kernel_ms = 0.0, stage_ms[3] = {0.0, 0.0, 0.0};
+    for (size_t k = 0; k < nch; ++k) {
+        const long long a0 = cut[k], a1 = cut[k + 1];
+        if (host) CU(cudaStreamWaitEvent(st, m->s_ev[k], 0));
+        { auto kfn = k_build_pairs;
+          ACE_LAUNCH(kfn, dim3(blocks_for(a1 - a0, kPairAtoms)), dim3(128), (kPairAtoms + 1) * sizeof(long long), st, a0, a1 - a0, na, dfirst, dnbr, dimg, cell, dX, dspc,
+                     m->s_R.as<double>(), species ? m->s_sp.as<int>() : (int*)nullptr, m->s_err.as<int>());
+          CU(cudaGetLastError()); m->launches++; }
+        aceb200_batch sub;
+        sub.nenv = a1 - a0; sub.offsets = reinterpret_cast<const int64_t*>(dfirst + a0); sub.R = m->s_R.as<double>();
+        sub.species = species ? m->s_sp.as<int>() : nullptr; sub.space = ACEB200_DEVICE; sub._pad = 0;
+        Outputs o; o.E = dE + (size_t)a0 * P; o.G = m->s_G.as<double>();
+        run(m, &sub, W_E | W_G, o);
+        kernel_ms += m->last_ms;
+        for (int i = 0; i < 3; ++i) stage_ms[i] += m->stage_ms[i];
+    }
+    if (host) CU(cudaStreamWaitEvent(st, m->s_ev[nch], 0));
+    if (!drev) {       // no reverse table from the caller: find each pair's reverse on the device (all pair tables are resident now)
+        auto kfn = k_find_rev;
+        ACE_LAUNCH(kfn, dim3(blocks_for(na, kPairAtoms)), dim3(128), (kPairAtoms + 1) * sizeof(long long), st, na, dfirst, dnbr, dimg, m->s_rev.as<int>());
+        CU(cudaGetLastError()); m->launches++;
+        drev = m->s_rev.as<int>();
+    }
+    { auto kfn = k_assemble_rev;
+      ACE_LAUNCH(kfn, dim3(blocks_for(na * K, 256)), dim3(256), 0, st, na, K, dfirst, drev, (const double*)m->s_G.as<double>(), dF, m->s_err.as<int>(), np);
+      CU(cudaGetLastError()); m->launches++; }
+    if (W) {
+        const int nblk = (int)std::max<long long>(1, std::min<long long>((long long)m->sm_count * 4, (np + kVirThreads - 1) / kVirThreads));
+        m->s_part.reserve((size_t)T.nprop * nblk * 9 * sizeof(double));
+        auto kfn = k_virial_partial;
+        ACE_LAUNCH(kfn, dim3(nblk, T.nprop), dim3(kVirThreads), kVirThreads * sizeof(double), st, np, T.nprop, (const double*)m->s_G.as<double>(),
+                   (const double*)m->s_R.as<double>(), m->s_part.as<double>());
+        CU(cudaGetLastError()); m->launches++;
+        auto kf2 = k_virial_final;
+        ACE_LAUNCH(kf2, dim3(T.nprop), dim3(32), 0, st, nblk, (const double*)m->s_part.as<double>(), dW);
+        CU(cudaGetLastError()); m->launches++;
+    }
+    int flag = 0;
+    if (host) {
+        if (Esite) CU(cudaMemcpyAsync(Esite, dE, (size_t)na * P * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(F, dF, (size_t)na * K * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (W) CU(cudaMemcpyAsync(W, dW, (size_t)T.nprop * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaMemcpyAsync(&flag, m->s_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    m->last_ms = kernel_ms;
+    for (int i = 0; i < 3; ++i) m->stage_ms[i] = stage_ms[i];
+    if (flag) throw ModelError(ACEB200_EDESC, "structure: neighbour or reverse-pair index out of range");
+}
+
 // FP64 FMA throughput probe: 8 independent dependent-FMA chains per thread.  The roofline
 // denominator of this path is the FP64 pipe, which MEASURED_PEAKS.json does not hold.
 __global__ void k_fp64_peak(int iters, double* sink)
@@ -1206,6 +1350,7 @@ int aceb200_model_create(const aceb200_desc* desc, aceb200_model** out)
             CU(cudaStreamCreateWithFlags(&L.own_stream, cudaStreamNonBlocking));
         }
         m->cur = &m->lanes[0];
+        CU(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
         upload_tables(m);
         upload_weights(m, desc->c);
         *out = m;
@@ -1224,6 +1369,11 @@ int aceb200_model_destroy(aceb200_model* m)
     for (StreamPass& sp : m->passes) { sp.blocks.release(); sp.tinfo.release(); sp.w0.release(); }
     for (int nu = 0; nu <= kMaxOrdDev; ++nu) m->d_lw[nu].release();
     for (Lane& L : m->lanes) L.release();
+    { DevBuf* bufs[] = {&m->s_X, &m->s_first, &m->s_nbr, &m->s_img, &m->s_spc, &m->s_rev, &m->s_R, &m->s_sp, &m->s_G, &m->s_E,
+                        &m->s_F, &m->s_W, &m->s_part, &m->s_err};
+      for (DevBuf* b : bufs) b->release(); }
+    for (cudaEvent_t e : m->s_ev) cudaEventDestroy(e);
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     delete m;
     return ACEB200_OK;
 }
@@ -1336,5 +1486,8 @@ int aceb200_energy(aceb200_model* m, const aceb200_batch* b, double* E)
 
 int aceb200_energy_forces(aceb200_model* m, const aceb200_batch* b, double* E, double* G)
 { API_BEGIN NEED(m, b); if (!G) throw ModelError(ACEB200_EDESC, "null G"); Outputs o; o.E = E; o.G = G; run(m, b, W_E | W_G, o); API_END }
+
+int aceb200_structure_energy_forces(aceb200_model* m, const aceb200_structure* s, double* Esite, double* F, double* W)
+{ API_BEGIN if (!m) throw ModelError(ACEB200_EDESC, "null argument"); run_structure(m, s, Esite, F, W); API_END }
 
 }  // extern "C"

@@ -269,6 +269,35 @@ def main():
     e2e_value = world * nenv * e2e_steps / float(dt.item())
     assert np.array_equal(Eh.numpy(), E.cpu().numpy()), "host-buffer path and device-resident path disagree"
 
+    # ---- end to end through the caller-side entry: a whole periodic structure with its neighbour
+    # list in pinned host memory -> site energies, atomic forces and the virial back in pinned host memory.  The
+    # environments are built and the forces assembled on the device, so the pair gradients never cross PCIe.
+    from ace_jl_b200.structure import B200Structure
+    from ace_jl_b200.utils import fcc_structure
+    ncell = max(2, round((nenv / 4.0) ** (1.0 / 3.0)))
+    sX, scell, sfirst, snbr, simg = fcc_structure(philox(SEED + 99 + rank), ncell)
+    pin = lambda a: torch.from_numpy(a).pin_memory()   # noqa: E731
+    pX, pfirst, pnbr, pimg = pin(sX), pin(sfirst), pin(snbr), pin(simg)
+    st = B200Structure(pX.numpy(), pfirst.numpy(), pnbr.numpy(), pimg.numpy(), scell)
+    sE = torch.empty((st.natoms, 1, 1), dtype=torch.float64).pin_memory()
+    sF = torch.empty((st.natoms, 1, 3, 1), dtype=torch.float64).pin_memory()
+    sW = torch.empty((1, 3, 3), dtype=torch.float64).pin_memory()
+    h.structure_energy_forces(st, True, sE.numpy(), sF.numpy(), sW.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        h.structure_energy_forces(st, True, sE.numpy(), sF.numpy(), sW.numpy())   # returns after the D2H copies
+        _ = float(sE[0, 0, 0])
+    torch.cuda.synchronize()
+    dts = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dts, op=dist.ReduceOp.MAX)
+    struct_value = world * st.natoms * e2e_steps / float(dts.item())
+    struct_h2d = sX.nbytes + sfirst.nbytes + snbr.nbytes + simg.nbytes
+    struct_d2h = sE.numel() * 8 + sF.numel() * 8 + sW.numel() * 8
+    fsum = float(np.abs(sF.numpy().sum(axis=0)).max() / np.abs(sF.numpy()).max())
+    assert fsum < 1e-9, "forces of a periodic structure must sum to zero"
+
     if rank == 0:
         flops = algorithmic_flops(basis, J)
         per_launch_ms = {k: v / args.steps for k, v in stage.items()}
@@ -312,6 +341,12 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(R.nbytes + off.nbytes),
                     "d2h_bytes_per_step": int(Eh.numel() * 8 + Gh.numel() * 8), "steps": e2e_steps,
                     "timer": "host wall clock around the C-ABI calls (they return after the D2H copy)"},
+            "e2e_structure": {"value": struct_value, "unit": UNIT, "h2d_bytes_per_step": int(struct_h2d), "d2h_bytes_per_step": int(struct_d2h),
+                              "steps": e2e_steps, "atoms_per_gpu": st.natoms, "pairs_per_gpu": st.npairs,
+                              "workload": "aceb200_structure_energy_forces: jittered periodic FCC crystal, 42 neighbours per atom inside "
+                                          "rcut, positions + neighbour list (i, j, S) in pinned host memory -> site energies, atomic "
+                                          "forces, virial in pinned host memory (same model; environments built and forces assembled on "
+                                          "the device)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

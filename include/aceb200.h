@@ -179,6 +179,39 @@ int aceb200_energy_forces(aceb200_model *m, const aceb200_batch *b, double *E, d
  * out: [nenv][nB][ncomp] complex. */
 int aceb200_adjoint_eval_d(aceb200_model *m, const aceb200_batch *b, const double *w, double *out);
 
+/* ---- caller side: a whole atomic structure ------------------------------ */
+
+/* An atomic structure with its neighbour list, sorted by centre.  Replaces, around the per-environment
+ * calls above, the loop that JuLIP / ACEatoms.jl run on the host (energy(V, at), forces(V, at), virial(V, at):
+ * for each centre i, Rs = {x_j + S_ij - x_i}, dV = evaluate_d(V, Rs), frc[j] -= dV_j, frc[i] += dV_j,
+ * vir -= dV_j (x) R_j).  Environments are built on the device from X and the pair table, and the pair
+ * gradients never leave it: per pair the interface moves 4 B (+ 3 B with periodic images, + 4 B with a
+ * reverse table) instead of the 48 B of aceb200_energy_forces.  The neighbour list must be a FULL list (every
+ * pair appears under both of its centres), as JuLIP's is. */
+typedef struct aceb200_structure {
+    int64_t natoms;
+    int64_t npairs;           /* < 2^31 */
+    const double  *X;         /* [natoms][3] positions                                                          */
+    const int64_t *first;     /* [natoms+1] pairs first[i]..first[i+1]-1 have centre i; first[0] = 0              */
+    const int32_t *nbr;       /* [npairs] 0-based index j of the neighbour atom                                   */
+    const int8_t  *image;     /* [npairs][3] integer image shift S (JuLIP's neighbour list: i, j, S):
+                                 R = X[j] + S[0] cell[0] + S[1] cell[1] + S[2] cell[2] - X[i]; NULL = no periodic images */
+    const int32_t *species;   /* [natoms] 1-based category of each atom (a pair takes its neighbour's), or NULL   */
+    const int32_t *rev;       /* [npairs] index of the reverse pair (centre j, neighbour i, image -S), -1 if there is
+                                 none (the neighbour is not a centre); NULL = found on the device by searching j's pairs */
+    double cell[9];           /* lattice vectors as rows, HOST memory in either space; unused when image is NULL   */
+    int32_t space;            /* ACEB200_HOST or ACEB200_DEVICE: where every pointer above AND the outputs live   */
+    int32_t _pad;
+} aceb200_structure;
+
+/* Site energies, atomic forces and the virial of a structure for a real (symreal) model:
+ *   Esite [natoms][nprop][ncomp]
+ *   F     [natoms][nprop][3][ncomp]   F_i = -dE/dx_i = sum_{p in env(i)} (g_p - g_rev(p)): a gather, no atomics,
+ *                                      bit-reproducible
+ *   W     [nprop][3][3] or NULL       W_ab = -sum_p g_p[a] R_p[b]   (needs ncomp = 1)
+ * Esite and W may be NULL. */
+int aceb200_structure_energy_forces(aceb200_model *m, const aceb200_structure *s, double *Esite, double *F, double *W);
+
 /* ---- introspection (sizes the host needs to allocate outputs) ------------------------------ */
 typedef struct aceb200_sizes {
     int32_t nA, nAA, nB, ncomp, nprop, maxord, pireal, symreal;

@@ -200,3 +200,27 @@ class Oracle:
         self._call("oracle_naive_energy_forces", C.byref(self.d), C.byref(b), self.d.c,
                    E.ctypes.data_as(C.c_void_p), G.ctypes.data_as(C.c_void_p))
         return E, G
+
+    # ---- caller side: the host loop JuLIP / ACEatoms.jl run around the per-environment calls ----
+    def structure_energy_forces(self, X, first, nbr, image=None, cell=None, species=None):
+        """Site energies, forces and virial of a structure, restating JuLIP's assembly loop literally:
+        for each centre i: Rs = x_j + S . cell - x_i; (E_i, dV) = energy_forces(Rs); frc[j] -= dV_j; frc[i] += dV_j;
+        vir -= dV_j (x) R_j.  Plain Python loop over centres and pairs (small structures only)."""
+        X = np.asarray(X, dtype=np.float64).reshape(-1, 3)
+        first, nbr = np.asarray(first, dtype=np.int64), np.asarray(nbr, dtype=np.int64)
+        n = len(X)
+        centre = np.repeat(np.arange(n), np.diff(first))
+        R = X[nbr] - X[centre]
+        if image is not None:
+            R = R + np.asarray(image, dtype=np.float64).reshape(-1, 3) @ np.asarray(cell, dtype=np.float64).reshape(3, 3)
+        sp = None if species is None else np.asarray(species, dtype=np.int32)[nbr]
+        E, G = self.energy_forces(R, first, sp)              # G [pair][nprop][3][ncomp]
+        F = np.zeros((n,) + G.shape[1:], dtype=G.dtype)
+        W = np.zeros((self.d.nprop, 3, 3))
+        for i in range(n):
+            for p in range(first[i], first[i + 1]):
+                F[nbr[p]] -= G[p]
+                F[i] += G[p]
+                if self.d.ncomp == 1:
+                    W -= np.einsum("qa,b->qab", G[p, :, :, 0].real, R[p])
+        return E, F, W

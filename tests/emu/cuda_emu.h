@@ -93,6 +93,13 @@ inline void sincos(double x, double* s, double* c) { *s = std::sin(x); *c = std:
 inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 inline int atomicMax(int* p, int v) { int o = *p; while (o < v && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
 
+inline double atomicAdd(double* p, double v)
+{
+    double o = *p, n;
+    do { n = o + v; } while (!__atomic_compare_exchange(p, &o, &n, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+    return o;
+}
+
 // ---- runtime API ------------------------------------------------------------------------------
 typedef int cudaError_t;
 typedef void* cudaStream_t;
@@ -125,5 +132,6 @@ inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emuEvent{0}; retur
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return 0; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
 template <class K> inline cudaError_t cudaFuncSetAttribute(K, int, int) { return 0; }

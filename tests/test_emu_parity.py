@@ -63,3 +63,30 @@ def test_emulated_errors(emu):
     assert ei.value.code == -6
     with pytest.raises(_lib.AceB200Error):
         model.evaluate([])
+
+
+def test_emulated_structure_path(emu, monkeypatch):
+    """aceb200_structure_energy_forces (pair gather, chunking, force assembly with the caller's and the device-found reverse table, virial) vs the oracle's
+    JuLIP-style loop, on the emulated kernels."""
+    import numpy as np
+    import ace_jl_b200 as ace
+    from ace_jl_b200.descriptor import basis_descriptor
+    from ace_jl_b200.structure import B200Structure, neighbourlist
+    from ace_jl_b200.utils import philox
+    from conftest import relerr
+    from oracle import Oracle
+    from test_structure import RCUT, periodic_crystal
+    for kind, nprop in (("inv_simple_3_6", 2), ("species_3_5", 1)):
+        basis = make_basis(kind)
+        rng = philox(4)
+        c = rng.random((len(basis), nprop)) - 0.5
+        model = ace.LinearACEModel(basis, c if nprop > 1 else c[:, 0])
+        X, cell = periodic_crystal(rng)
+        first, nbr, image, rev = neighbourlist(X, RCUT, cell, (True, True, True))
+        species = rng.integers(1, 5, len(X)).astype(np.int32) if kind.startswith("species") else None
+        Eo, Fo, Wo = Oracle(basis_descriptor(basis, c)).structure_energy_forces(X, first, nbr, image, cell, species)
+        for mb, r in ((None, rev), ("0.001", rev), ("0.001", None)):
+            if mb:
+                monkeypatch.setenv("ACEB200_STRUCT_MB", mb)
+            E, F, W = model.evaluator.handle.structure_energy_forces(B200Structure(X, first, nbr, image, cell, species, r))
+            assert relerr(E, Eo) < 1e-12 and relerr(F, Fo) < 1e-12 and relerr(W, Wo) < 1e-12
