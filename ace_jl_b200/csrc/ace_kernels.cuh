@@ -1302,16 +1302,28 @@ static __global__ void k_find_rev(long long natoms, const long long* first, cons
         int lo = 0, hi = nc;
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (f[mid] <= p) lo = mid; else hi = mid; }
         const int i = (int)(c0 + lo);
-        const long long j = nbr[p];
+        const long long j = __ldg(nbr + p);
         int found = -1;
         if (j >= 0 && j < natoms) {
             int s0 = 0, s1 = 0, s2 = 0;
-            if (image) { s0 = -image[3 * p]; s1 = -image[3 * p + 1]; s2 = -image[3 * p + 2]; }
-            for (long long q = first[j]; q < first[j + 1]; ++q) {
-                if (nbr[q] != i) continue;
-                if (image && (image[3 * q] != s0 || image[3 * q + 1] != s1 || image[3 * q + 2] != s2)) continue;
+            if (image) { s0 = -__ldg(image + 3 * p); s1 = -__ldg(image + 3 * p + 1); s2 = -__ldg(image + 3 * p + 2); }
+            // neighbour lists are normally sorted by neighbour index within a centre: binary search for the first
+            // entry >= i and walk the (few) images of i; an unsorted list falls back to the linear scan below
+            long long lo2 = __ldg(first + j), hi2 = __ldg(first + j + 1);
+            const long long qb = lo2, qe = hi2;
+            while (lo2 < hi2) { const long long mid = (lo2 + hi2) >> 1; if (__ldg(nbr + mid) < i) lo2 = mid + 1; else hi2 = mid; }
+            for (long long q = lo2; q < qe && __ldg(nbr + q) == i; ++q) {
+                if (image && (__ldg(image + 3 * q) != s0 || __ldg(image + 3 * q + 1) != s1 || __ldg(image + 3 * q + 2) != s2)) continue;
                 found = (int)q;
                 break;
+            }
+            if (found < 0) {
+                for (long long q = qb; q < qe; ++q) {
+                    if (__ldg(nbr + q) != i) continue;
+                    if (image && (__ldg(image + 3 * q) != s0 || __ldg(image + 3 * q + 1) != s1 || __ldg(image + 3 * q + 2) != s2)) continue;
+                    found = (int)q;
+                    break;
+                }
             }
         }
         rev[p] = found;

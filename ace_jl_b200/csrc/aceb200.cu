@@ -110,6 +110,11 @@ struct aceb200_model {
     DevBuf d_ctl;                      // k_adjoint_stream control words (shared by all passes)
     std::vector<StreamPass> passes;    // per-pass leaf blocks and target records (PB channels each)
     int stream_nblk[kStreamWarps] = {0};
+    // energy-only stream (aceb200_energy): every AA function once, under its first factor (see upload_stream)
+    DevBuf e_ctl;
+    std::vector<StreamPass> e_passes;
+    int e_stream_nblk[kStreamWarps] = {0};
+    int e_stream_chunks = 0, e_stream_ntinfo = 0;
     int stream_chunks = 0, stream_nf = 0, stream_ntinfo = 0, stream_pb = 1, stream_epl = 1;   // 0 chunks: use the generic k_adjoint
     // per-call workspace (guarded by mu).  Three lanes: device-resident batches use lane 0 on the caller's
     // stream; host-resident batches are pipelined chunk by chunk over all lanes (H2D copy, kernels and D2H
@@ -170,7 +175,7 @@ static void fill_params(aceb200_model* m, const aceb200_desc& d)
     for (int mm = 0; mm + 1 <= ap.L; ++mm) { ap.A[index_p(mm + 1, mm)] = sqrt(2.0 * mm + 3.0); ap.B[index_p(mm + 1, mm)] = 0.0; }   // :179, :191
 }
 
-static void upload_stream(aceb200_model* m);
+static void upload_stream(aceb200_model* m, bool energy_only = false);
 
 // c~ and the weights that depend on it: order-0/1 weights and the leaf weights of every tree
 static void upload_weights(aceb200_model* m, const double* c)
@@ -215,6 +220,7 @@ static void upload_weights(aceb200_model* m, const double* c)
         m->list[nu].stride = stride;
     }
     upload_stream(m);
+    upload_stream(m, true);
 }
 
 // Host mirror of StreamGeom (ace_kernels.cuh)
@@ -247,12 +253,23 @@ static size_t stream_smem(int nS, const HostGeom& g, int pb, int epl = 1)
 //     Re(c~_i AA_i) + Re(c~_i' AA_i') = Re((c~_i + s conj(c~_i')) AA_i),
 // so only one function of each mirror pair is kept, with the folded weight.  This halves the stream; energy and
 // gradient are unchanged as functions of the positions (only the order of floating-point additions differs).
-static void upload_stream(aceb200_model* m)
+//
+// Energy-only stream (energy_only = true).  evaluate(model, cfg) needs no adjoints, so the Euler pass over every target
+// (each AA function visited once per distinct factor) is nu times more work than necessary.  The same kernel walks a
+// second stream in which an AA function appears exactly once -- under its first factor, with multiplicity 1 and
+// segment scale 1 -- so that  E += Re(A_a * w * prod(other factors)) = w Re(AA)  [src/evaluator.jl:137-143].
+static void upload_stream(aceb200_model* m, bool energy_only)
 {
     HostTables& T = m->T;
-    m->stream_chunks = 0;
-    for (StreamPass& sp : m->passes) { sp.blocks.release(); sp.tinfo.release(); sp.w0.release(); }
-    m->passes.clear();
+    std::vector<StreamPass>& passes = energy_only ? m->e_passes : m->passes;
+    DevBuf& d_ctl = energy_only ? m->e_ctl : m->d_ctl;
+    int* stream_nblk = energy_only ? m->e_stream_nblk : m->stream_nblk;
+    int& stream_chunks = energy_only ? m->e_stream_chunks : m->stream_chunks;
+    int& stream_ntinfo = energy_only ? m->e_stream_ntinfo : m->stream_ntinfo;
+    stream_chunks = 0;
+    for (StreamPass& sp : passes) { sp.blocks.release(); sp.tinfo.release(); sp.w0.release(); }
+    passes.clear();
+    if (energy_only && (m->stream_chunks == 0 || getenv("ACEB200_NO_ENERGY_STREAM"))) return;
     if (T.maxord < 2 || T.maxord > 5 || !T.symreal || getenv("ACEB200_NO_STREAM")) return;
     if (T.nS + 1 >= (1 << 14)) return;                   // 14-bit slot fields
     const int NF = T.maxord <= 3 ? 2 : (T.maxord == 4 ? 3 : 4);
@@ -349,6 +366,8 @@ static void upload_stream(aceb200_model* m)
     };
     // The block structure (codes, ctl, which target a tinfo record belongs to) is the same for every pass;
     // only the weights differ.  Build the structure once per sub-stream, then emit the passes.
+    // energy-only: an AA function belongs to the target that is its first factor
+    auto mine = [&](int a, int aa) { return !energy_only || T.spec[(size_t)aa * T.maxord] == a; };
     struct BlockRef { Leaf L[kBlkLeaves]; int nleaf; unsigned flags; int target; double invnu; };
     std::vector<std::vector<BlockRef>> perslot(T.nS);
     auto add_block = [&](std::vector<BlockRef>& v, const std::vector<Leaf>* leaves, size_t i0, unsigned flags, int target, double invnu) {
@@ -379,13 +398,13 @@ static void upload_stream(aceb200_model* m)
                 const Tree& tr = T.trees[nu];
                 if (!GR) {
                     for (int i = tr.ptr[a]; i < tr.ptr[a + 1]; ++i) {
-                        if (!keep[tr.laa[i]]) continue;
-                        per[nu].push_back(make_leaf(&tr.codes[4 * (size_t)i], nu - 1, tr.laa[i], tr.lmult[i]));
+                        if (!keep[tr.laa[i]] || !mine(a, tr.laa[i])) continue;
+                        per[nu].push_back(make_leaf(&tr.codes[4 * (size_t)i], nu - 1, tr.laa[i], energy_only ? 1 : tr.lmult[i]));
                     }
                 } else {
                     // greedy grouping: repeatedly take the factor shared by the most remaining leaves
                     std::vector<int> rest;
-                    for (int i = tr.ptr[a]; i < tr.ptr[a + 1]; ++i) if (keep[tr.laa[i]]) rest.push_back(i);
+                    for (int i = tr.ptr[a]; i < tr.ptr[a + 1]; ++i) if (keep[tr.laa[i]] && mine(a, tr.laa[i])) rest.push_back(i);
                     const int nf = nu - 1;
                     while (!rest.empty()) {
                         int key = -1;
@@ -422,7 +441,7 @@ static void upload_stream(aceb200_model* m)
                                 if (key >= 0 && !taken && cd[f] == key) { taken = true; continue; }
                                 ord[no++] = cd[f];
                             }
-                            per[nu].push_back(make_leaf_gr(key, ord, no, tr.laa[i], tr.lmult[i], gi + 1 == grp.size()));
+                            per[nu].push_back(make_leaf_gr(key, ord, no, tr.laa[i], energy_only ? 1 : tr.lmult[i], gi + 1 == grp.size()));
                         }
                     }
                 }
@@ -437,7 +456,7 @@ static void upload_stream(aceb200_model* m)
                         flags = (unsigned)nu | kSegEnd | (tflags & (kTgtNeg | kTgtOdd));
                         if (nu == lastnu) flags |= tflags;
                     }
-                    add_block(S, &lv, i, flags, a, 1.0 / nu);
+                    add_block(S, &lv, i, flags, a, energy_only ? 1.0 : 1.0 / nu);
                 }
             }
         }
@@ -460,18 +479,18 @@ static void upload_stream(aceb200_model* m)
         ntinfo = std::max(ntinfo, nt);
     }
     const size_t nchunks = (longest + g.KB - 1) / g.KB;
-    for (int w = 0; w < kStreamWarps; ++w) m->stream_nblk[w] = (int)sub[w].size();
+    for (int w = 0; w < kStreamWarps; ++w) stream_nblk[w] = (int)sub[w].size();
     for (auto& v : sub) while (v.size() < nchunks * g.KB) add_block(v, nullptr, 0, 0u, -1, 0.0);   // inert padding blocks
 
     // ctl (shared by all passes)
     std::vector<uint32_t> ctl;
     for (auto& v : sub) for (auto& b : v) ctl.push_back(b.flags);
-    m->d_ctl.reserve(ctl.size() * 4 + 256);
-    CU(cudaMemcpy(m->d_ctl.p, ctl.data(), ctl.size() * 4, cudaMemcpyHostToDevice));
+    d_ctl.reserve(ctl.size() * 4 + 256);
+    CU(cudaMemcpy(d_ctl.p, ctl.data(), ctl.size() * 4, cudaMemcpyHostToDevice));
 
     // passes
     const int npass = (P + PB - 1) / PB;
-    m->passes.resize(npass);
+    passes.resize(npass);
     for (int ps = 0; ps < npass; ++ps) {
         const int pb0 = ps * PB;
         std::vector<uint32_t> blocks((size_t)kStreamWarps * nchunks * g.CH * 4, 0u);
@@ -518,7 +537,7 @@ static void upload_stream(aceb200_model* m)
         }
         std::vector<double> w0((size_t)PB * g.CS, 0.0);
         if (T.has_const) for (int q = 0; q < PB; ++q) { const cplx z = chan(0, q); w0[q * g.CS] = z.real(); if (CW) w0[q * g.CS + 1] = z.imag(); }
-        StreamPass& sp = m->passes[ps];
+        StreamPass& sp = passes[ps];
         sp.blocks.reserve(blocks.size() * 4 + 4096);
         sp.tinfo.reserve(tinfo.size() * 4 + 256);
         sp.w0.reserve(w0.size() * 8 + 64);
@@ -527,8 +546,9 @@ static void upload_stream(aceb200_model* m)
         CU(cudaMemcpy(sp.w0.p, w0.data(), w0.size() * 8, cudaMemcpyHostToDevice));
         sp.pb0 = pb0;
     }
-    m->stream_chunks = (int)nchunks;
-    m->stream_ntinfo = (int)ntinfo;
+    stream_chunks = (int)nchunks;
+    stream_ntinfo = (int)ntinfo;
+    if (energy_only) return;                     // geometry (NF, PB, EPL) is the full stream's
     m->stream_nf = NF;
     m->stream_pb = PB;
     // two environments per lane for the single-channel real path when two such CTAs still fit on an SM
@@ -812,12 +832,14 @@ static void launch_adjoint(aceb200_model* m, long long nenv, long long ldA, bool
         const long long ntiles = (nenv + 32 * m->stream_epl - 1) / (32 * m->stream_epl);
         const int per_sm = std::max<int>(1, std::min<int>(8, (int)((size_t)m->smem_optin / (smem + 1024))));
         const int grid = (int)std::min<long long>(ntiles, (long long)m->sm_count * per_sm);
-        for (const StreamPass& sp : m->passes) {
+        const bool eo = !want_D && m->e_stream_chunks > 0;       // energy only: the short stream
+        for (const StreamPass& sp : (eo ? m->e_passes : m->passes)) {
             StreamParams p;
-            p.nS = T.nS; p.has_const = T.has_const; p.want_D = want_D ? 1 : 0; p.nchunks = m->stream_chunks; p.ntinfo = m->stream_ntinfo;
-            for (int w = 0; w < kStreamWarps; ++w) p.nblk[w] = m->stream_nblk[w];
+            p.nS = T.nS; p.has_const = T.has_const; p.want_D = want_D ? 1 : 0;
+            p.nchunks = eo ? m->e_stream_chunks : m->stream_chunks; p.ntinfo = eo ? m->e_stream_ntinfo : m->stream_ntinfo;
+            for (int w = 0; w < kStreamWarps; ++w) p.nblk[w] = eo ? m->e_stream_nblk[w] : m->stream_nblk[w];
             p.P = T.P; p.pb0 = sp.pb0;
-            p.stream = sp.blocks.as<uint4>(); p.ctl = m->d_ctl.as<unsigned>(); p.tinfo = sp.tinfo.as<uint4>(); p.w0 = sp.w0.as<double>();
+            p.stream = sp.blocks.as<uint4>(); p.ctl = (eo ? m->e_ctl : m->d_ctl).as<unsigned>(); p.tinfo = sp.tinfo.as<uint4>(); p.w0 = sp.w0.as<double>();
             p.Ac = m->cur->ws_Ac.as<c2>(); p.ldA = ldA; p.Dt = m->cur->ws_Dt.as<c2>(); p.E = m->cur->ws_E.as<double>(); p.nenv = nenv;
             if (m->stream_nf == 2) launch_stream_nf<2>(m, p, grid, smem);
             else if (m->stream_nf == 3) launch_stream_nf<3>(m, p, grid, smem);
@@ -1246,7 +1268,10 @@ static void run_structure(aceb200_model* m, const aceb200_structure* s, double* 
         for (int i = 0; i < 3; ++i) stage_ms[i] += m->stage_ms[i];
     }
     if (host) CU(cudaStreamWaitEvent(st, m->s_ev[nch], 0));
-    if (!drev) {       // no reverse table from the caller: find each pair's reverse on the device (all pair tables are resident now)
+    if (!drev) {
+        // no reverse table from the caller: find each pair's reverse on the device (all pair tables are resident now).
+        // (Running this search on a second, high-priority stream underneath the evaluation kernels was measured and
+        // is slower: the kernels contend for the same SMs, 21 ms vs 17 ms end to end on the benchmark structure.)
         auto kfn = k_find_rev;
         ACE_LAUNCH(kfn, dim3(blocks_for(na, kPairAtoms)), dim3(128), (kPairAtoms + 1) * sizeof(long long), st, na, dfirst, dnbr, dimg, m->s_rev.as<int>());
         CU(cudaGetLastError()); m->launches++;
@@ -1367,6 +1392,8 @@ int aceb200_model_destroy(aceb200_model* m)
     for (DevBuf& b : m->pool) b.release();
     m->d_w0.release(); m->d_w1.release(); m->d_ctl.release(); m->ws_err.release();
     for (StreamPass& sp : m->passes) { sp.blocks.release(); sp.tinfo.release(); sp.w0.release(); }
+    for (StreamPass& sp : m->e_passes) { sp.blocks.release(); sp.tinfo.release(); sp.w0.release(); }
+    m->e_ctl.release();
     for (int nu = 0; nu <= kMaxOrdDev; ++nu) m->d_lw[nu].release();
     for (Lane& L : m->lanes) L.release();
     { DevBuf* bufs[] = {&m->s_X, &m->s_first, &m->s_nbr, &m->s_img, &m->s_spc, &m->s_rev, &m->s_R, &m->s_sp, &m->s_G, &m->s_E,

@@ -127,6 +127,8 @@ inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 enum { cudaStreamNonBlocking = 1 };
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return 0; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+inline cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) { *lo = 0; *hi = 0; return 0; }
+inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = nullptr; return 0; }
 inline cudaError_t cudaDeviceSynchronize() { return 0; }
 inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emuEvent{0}; return 0; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }

@@ -90,3 +90,7 @@ def test_emulated_structure_path(emu, monkeypatch):
                 monkeypatch.setenv("ACEB200_STRUCT_MB", mb)
             E, F, W = model.evaluator.handle.structure_energy_forces(B200Structure(X, first, nbr, image, cell, species, r))
             assert relerr(E, Eo) < 1e-12 and relerr(F, Fo) < 1e-12 and relerr(W, Wo) < 1e-12
+        # a neighbour list that is NOT sorted within a centre: the device-side reverse search falls back to a scan
+        perm = np.concatenate([first[i] + rng.permutation(first[i + 1] - first[i]) for i in range(len(X))])
+        E, F, W = model.evaluator.handle.structure_energy_forces(B200Structure(X, first, nbr[perm], image[perm], cell, species))
+        assert relerr(E, Eo) < 1e-12 and relerr(F, Fo) < 1e-12 and relerr(W, Wo) < 1e-12

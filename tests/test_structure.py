@@ -128,6 +128,11 @@ def test_structure_matches_oracle(kind, nprop, periodic, use_rev, monkeypatch):
         st = B200Structure(X, first, nbr, image, cell, species, rev if use_rev else None)
         E, F, W = model.evaluator.handle.structure_energy_forces(st)
         assert relerr(E, Eo) < TOL and relerr(F, Fo) < TOL and relerr(W, Wo) < TOL
+    # a list that is not sorted within a centre (the device-side reverse search falls back to a scan)
+    perm = np.concatenate([first[i] + rng.permutation(first[i + 1] - first[i]) for i in range(len(X))])
+    Ep, Fp, Wp = model.evaluator.handle.structure_energy_forces(
+        B200Structure(X, first, nbr[perm], None if image is None else image[perm], cell, species))
+    assert relerr(Ep, Eo) < TOL and relerr(Fp, Fo) < TOL and relerr(Wp, Wo) < TOL
     # the model-level wrapper squeezes like evaluate / grad_config
     E1, F1, W1 = model.energy_forces_virial(st)
     assert E1.shape == ((len(X),) if nprop == 1 else (len(X), nprop)) and F1.shape[-1] == 3
