@@ -415,15 +415,19 @@ __global__ void __launch_bounds__(32) k_adjoint(const AdjointParams p)
 constexpr unsigned kSegEnd = 8, kTgtEnd = 16, kTgtNeg = 32, kTgtOdd = 64, kSlotEnd = 128;
 constexpr unsigned kGroupEnd = 0x4000u;     // leaf code bit 14 (grouped form)
 constexpr int kBlkLeaves = 4;               // leaves per block
-constexpr int kStreamWarps = 8;             // warps per CTA; each walks its own sub-stream over the same A tile
+constexpr int kStreamWarps = 12;            // most warps a CTA of k_adjoint_stream can have (StreamGeom::NW); each walks its own
+                                            // sub-stream over the same A tile
 
 template <int NF, int PB, bool CW>
 struct StreamGeom {
     static constexpr int CS = CW ? 2 : 1;
     static constexpr int CWORDS = (NF == 2) ? 1 : 2;                     // code words per leaf
     static constexpr int QB = CWORDS + 2 * PB * CS;                      // uint4 per block (4 leaves)
-    static constexpr int KB = (QB <= 4) ? 32 : 8;                        // blocks per ring chunk
-    static constexpr int QBP = (KB == 32) ? QB : ((QB + 3) / 4) * 4;     // padded so that a chunk is a multiple of 32 uint4
+    // warps per CTA: the single-channel real stream has small rings, so 12 warps share one A tile and two such CTAs still
+    // fit on an SM (24 resident warps instead of 16); the multi-channel streams keep 8 (their rings are 2.5 KB per slot)
+    static constexpr int NW = (PB == 1 && !CW) ? 12 : 8;
+    static constexpr int KB = (QB <= 4) ? 16 : 8;                        // blocks per ring chunk
+    static constexpr int QBP = ((QB + 3) / 4) * 4;                       // padded so that a chunk is a multiple of 32 uint4
     static constexpr int CH = KB * QBP;                                  // uint4 per chunk
     static constexpr int LPC = CH / 32;                                  // uint4 each lane loads per chunk
     static constexpr int TIQ = 1 + (1 + PB * CS + 1) / 2;                // uint4 per tinfo record
@@ -432,7 +436,7 @@ struct StreamGeom {
 struct StreamParams {
     int nS, has_const, want_D, nchunks, ntinfo;
     int P, pb0;                              // channels [pb0, pb0 + PB) of P are computed by this launch
-    int nblk[8];                             // [kStreamWarps] blocks of each sub-stream before its inert padding
+    int nblk[kStreamWarps];                  // [NW] blocks of each sub-stream before its inert padding
     const uint4* stream;                     // [kStreamWarps][nchunks][CH]
     const unsigned* ctl;                     // [kStreamWarps][nchunks * KB]
     const uint4* tinfo;                      // [kStreamWarps][ntinfo][TIQ]
@@ -512,23 +516,23 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity
 // per byte of shared memory is what hides the FP64 and shared-memory latencies of the leaf products; EPL = 2
 // amortises the (warp-uniform) record decode over two environments and doubles the independent work per lane.
 template <int NF, int PB, bool CW, int EPL>
-__global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const StreamParams p)
+__global__ void __launch_bounds__(32 * StreamGeom<NF, PB, CW>::NW, (PB == 1 && !CW) ? 2 : 1) k_adjoint_stream(const StreamParams p)
 {
     typedef StreamGeom<NF, PB, CW> G;
-    constexpr int CS = G::CS, CH = G::CH, QBP = G::QBP, KB = G::KB, LPC = G::LPC, TIQ = G::TIQ;
+    constexpr int CS = G::CS, CH = G::CH, QBP = G::QBP, KB = G::KB, LPC = G::LPC, TIQ = G::TIQ, NW = G::NW;
     constexpr int TW = 32 * EPL;                                // environments per tile
     constexpr int RSH = (EPL == 1) ? 9 : 10;                    // log2 of the tile row pitch in bytes
     ACE_DYN_SMEM(c2, As);                                       // [nS + 1][TW]; slot nS holds 1
-    uint4* rings = reinterpret_cast<uint4*>(As + (size_t)(p.nS + 1) * TW);   // [kStreamWarps][2][CH]
-    double* Epart = reinterpret_cast<double*>(rings + kStreamWarps * 2 * CH); // [kStreamWarps][PB][EPL][32]
+    uint4* rings = reinterpret_cast<uint4*>(As + (size_t)(p.nS + 1) * TW);   // [NW][2][CH]
+    double* Epart = reinterpret_cast<double*>(rings + NW * 2 * CH); // [NW][PB][EPL][32]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4* ring = rings + warp * 2 * CH;
 #if ACEB200_TMA
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(Epart + kStreamWarps * PB * EPL * 32);   // [1 + 2 kStreamWarps]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(Epart + NW * PB * EPL * 32);   // [1 + 2 NW]
     unsigned long long* barA = bars;
     unsigned long long* barR = bars + 1 + 2 * warp;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 1 + 2 * kStreamWarps; ++i) mbar_init(bars + i, 1);
+        for (int i = 0; i < 1 + 2 * NW; ++i) mbar_init(bars + i, 1);
         fence_barrier_init();
     }
     unsigned phA = 0, phR0 = 0, phR1 = 0;
@@ -568,7 +572,7 @@ __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const Stre
         mbar_wait(barA, phA);
         phA ^= 1u;
 #else
-        for (int s = warp; s < p.nS; s += kStreamWarps) {
+        for (int s = warp; s < p.nS; s += NW) {
 #pragma unroll
             for (int j = 0; j < EPL; ++j) As[s * TW + lane + 32 * j] = p.Ac[(size_t)s * p.ldA + e + 32 * j];
         }
@@ -780,7 +784,7 @@ __global__ void __launch_bounds__(32 * kStreamWarps) k_adjoint_stream(const Stre
                     if (p.pb0 + q < p.P && e + 32 * j < p.nenv) {
                         double Et = 0.0;
 #pragma unroll
-                        for (int w = 0; w < kStreamWarps; ++w) Et += Epart[((w * PB + q) * EPL + j) * 32 + lane];
+                        for (int w = 0; w < NW; ++w) Et += Epart[((w * PB + q) * EPL + j) * 32 + lane];
                         p.E[(size_t)(e + 32 * j) * p.P + p.pb0 + q] = Et;
                     }
                 }

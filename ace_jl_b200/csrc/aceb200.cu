@@ -224,15 +224,16 @@ static void upload_weights(aceb200_model* m, const double* c)
 }
 
 // Host mirror of StreamGeom (ace_kernels.cuh)
-struct HostGeom { int CS, CWORDS, QB, KB, QBP, CH, TIQ; };
+struct HostGeom { int CS, CWORDS, QB, KB, QBP, CH, TIQ, NW; };
 static HostGeom stream_geom(int NF, int PB, bool CW)
 {
     HostGeom g;
     g.CS = CW ? 2 : 1;
     g.CWORDS = (NF == 2) ? 1 : 2;
     g.QB = g.CWORDS + 2 * PB * g.CS;
-    g.KB = (g.QB <= 4) ? 32 : 8;
-    g.QBP = (g.KB == 32) ? g.QB : ((g.QB + 3) / 4) * 4;
+    g.NW = (PB == 1 && !CW) ? 12 : 8;
+    g.KB = (g.QB <= 4) ? 16 : 8;
+    g.QBP = ((g.QB + 3) / 4) * 4;
     g.CH = g.KB * g.QBP;
     g.TIQ = 1 + (1 + PB * g.CS + 1) / 2;
     return g;
@@ -241,9 +242,9 @@ static HostGeom stream_geom(int NF, int PB, bool CW)
 static size_t stream_smem(int nS, const HostGeom& g, int pb, int epl = 1)
 {
     return (size_t)(nS + 1) * 32 * epl * sizeof(c2)                // A tile (+ the row of ones)
-         + (size_t)kStreamWarps * 2 * g.CH * sizeof(uint4)          // per-warp stream rings
-         + (size_t)kStreamWarps * pb * epl * 32 * sizeof(double)    // per-warp energy partials
-         + (size_t)(1 + 2 * kStreamWarps) * 8;                      // mbarriers
+         + (size_t)g.NW * 2 * g.CH * sizeof(uint4)                  // per-warp stream rings
+         + (size_t)g.NW * pb * epl * 32 * sizeof(double)            // per-warp energy partials
+         + (size_t)(1 + 2 * g.NW) * 8;                              // mbarriers
 }
 
 // Flatten the adjoint lists into the streams k_adjoint_stream consumes (layout: ace_kernels.cuh).
@@ -461,14 +462,14 @@ static void upload_stream(aceb200_model* m, bool energy_only)
             }
         }
     }
-    // LPT split of the slots over the kStreamWarps sub-streams
+    // LPT split of the slots over the g.NW sub-streams
     std::vector<int> order(T.nS);
     for (int s = 0; s < T.nS; ++s) order[s] = s;
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return perslot[x].size() > perslot[y].size(); });
-    std::vector<std::vector<BlockRef>> sub(kStreamWarps);
+    std::vector<std::vector<BlockRef>> sub(g.NW);
     for (int s : order) {
         int best = 0;
-        for (int w = 1; w < kStreamWarps; ++w) if (sub[w].size() < sub[best].size()) best = w;
+        for (int w = 1; w < g.NW; ++w) if (sub[w].size() < sub[best].size()) best = w;
         sub[best].insert(sub[best].end(), perslot[s].begin(), perslot[s].end());
     }
     size_t longest = 1, ntinfo = 1;
@@ -479,7 +480,7 @@ static void upload_stream(aceb200_model* m, bool energy_only)
         ntinfo = std::max(ntinfo, nt);
     }
     const size_t nchunks = (longest + g.KB - 1) / g.KB;
-    for (int w = 0; w < kStreamWarps; ++w) stream_nblk[w] = (int)sub[w].size();
+    for (int w = 0; w < kStreamWarps; ++w) stream_nblk[w] = w < g.NW ? (int)sub[w].size() : 0;
     for (auto& v : sub) while (v.size() < nchunks * g.KB) add_block(v, nullptr, 0, 0u, -1, 0.0);   // inert padding blocks
 
     // ctl (shared by all passes)
@@ -493,10 +494,10 @@ static void upload_stream(aceb200_model* m, bool energy_only)
     passes.resize(npass);
     for (int ps = 0; ps < npass; ++ps) {
         const int pb0 = ps * PB;
-        std::vector<uint32_t> blocks((size_t)kStreamWarps * nchunks * g.CH * 4, 0u);
-        std::vector<uint32_t> tinfo((size_t)kStreamWarps * ntinfo * g.TIQ * 4, 0u);
+        std::vector<uint32_t> blocks((size_t)g.NW * nchunks * g.CH * 4, 0u);
+        std::vector<uint32_t> tinfo((size_t)g.NW * ntinfo * g.TIQ * 4, 0u);
         auto chan = [&](int aa, int q) { return (aa >= 0 && pb0 + q < P) ? ceff[(size_t)aa * P + pb0 + q] : cplx(0, 0); };
-        for (int w = 0; w < kStreamWarps; ++w) {
+        for (int w = 0; w < g.NW; ++w) {
             size_t ti = 0;
             for (size_t ib = 0; ib < sub[w].size(); ++ib) {
                 const BlockRef& b = sub[w][ib];
@@ -558,7 +559,7 @@ static void upload_stream(aceb200_model* m, bool energy_only)
         size_t kept = 0, total = 0;
         for (int i = 0; i < T.nAA; ++i) { total += T.orders[i] >= 2; kept += (T.orders[i] >= 2 && keep[i]); }
         fprintf(stderr, "[aceb200] stream: NF=%d PB=%d CW=%d passes=%d, %d sub-streams x %zu chunks of %d blocks, AA functions of order >= 2 kept %zu of %zu, smem %zu B\n",
-                NF, PB, (int)CW, npass, kStreamWarps, nchunks, g.KB, kept, total, stream_smem(T.nS, g, PB, m->stream_epl));
+                NF, PB, (int)CW, npass, g.NW, nchunks, g.KB, kept, total, stream_smem(T.nS, g, PB, m->stream_epl));
     }
 }
 
@@ -803,7 +804,7 @@ static void launch_stream_t(aceb200_model* m, const StreamParams& p, int grid, s
 {
     auto kfn = k_adjoint_stream<NF, PB, CW, EPL>;
     CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ACE_LAUNCH(kfn, dim3(grid), dim3(32 * kStreamWarps), smem, m->cur->stream, p);
+    ACE_LAUNCH(kfn, dim3(grid), dim3(32 * StreamGeom<NF, PB, CW>::NW), smem, m->cur->stream, p);
 }
 
 template <int NF>
