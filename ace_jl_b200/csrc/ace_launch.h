@@ -1,5 +1,6 @@
 // ace_launch.h -- the two large kernel families (k_pool, k_forces) are instantiated in one translation unit per
-// radial bound NMAX (inst_NN.cu, generated from inst_template.cuh) so that the library builds in parallel.
+// radial bound NMAX (inst_NN.cu, generated from inst_template.cuh), and k_adjoint_stream in one per number of leaf
+// factors NF (stream_nfN.cu, from stream_template.cuh), so that the library builds in parallel.
 #pragma once
 
 #include <stdexcept>
@@ -24,6 +25,17 @@ namespace aceb200 {
     void pool_inst_##N(bool species, bool staticL, const PoolParams& p, unsigned grid, size_t smem, cudaStream_t st);
 ACE_INST_DECL(4) ACE_INST_DECL(8) ACE_INST_DECL(12) ACE_INST_DECL(16) ACE_INST_DECL(20) ACE_INST_DECL(24) ACE_INST_DECL(32)
 #undef ACE_INST_DECL
+
+void stream_inst_nf2(int pb, bool cw, int epl, const StreamParams& p, int grid, size_t smem, cudaStream_t st);
+void stream_inst_nf3(int pb, bool cw, int epl, const StreamParams& p, int grid, size_t smem, cudaStream_t st);
+void stream_inst_nf4(int pb, bool cw, int epl, const StreamParams& p, int grid, size_t smem, cudaStream_t st);
+
+inline void launch_stream_inst(int nf, int pb, bool cw, int epl, const StreamParams& p, int grid, size_t smem, cudaStream_t st)
+{
+    if (nf == 2) stream_inst_nf2(pb, cw, epl, p, grid, smem, st);
+    else if (nf == 3) stream_inst_nf3(pb, cw, epl, p, grid, smem, st);
+    else stream_inst_nf4(pb, cw, epl, p, grid, smem, st);
+}
 
 inline void launch_forces_inst(int nmax, int pb, bool species, bool staticL, const ForceParams& p, unsigned grid, size_t smem, cudaStream_t st)
 {

@@ -799,31 +799,6 @@ static void launch_adjoint_t(aceb200_model* m, const AdjointParams& p, int grid,
     ACE_LAUNCH(kfn, dim3(grid), dim3(32), smem, m->cur->stream, p);
 }
 
-template <int NF, int PB, bool CW, int EPL = 1>
-static void launch_stream_t(aceb200_model* m, const StreamParams& p, int grid, size_t smem)
-{
-    auto kfn = k_adjoint_stream<NF, PB, CW, EPL>;
-    CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ACE_LAUNCH(kfn, dim3(grid), dim3(32 * StreamGeom<NF, PB, CW>::NW), smem, m->cur->stream, p);
-}
-
-template <int NF>
-static void launch_stream_nf(aceb200_model* m, const StreamParams& p, int grid, size_t smem)
-{
-    const bool cw = m->cw;
-#define ACE_S(PBV) { if (cw) launch_stream_t<NF, PBV, true>(m, p, grid, smem); else launch_stream_t<NF, PBV, false>(m, p, grid, smem); }
-    switch (m->stream_pb) {
-    case 1:
-        if (!cw && m->stream_epl == 2) launch_stream_t<NF, 1, false, 2>(m, p, grid, smem);
-        else ACE_S(1)
-        break;
-    case 2: ACE_S(2) break;
-    case 4: ACE_S(4) break;
-    default: ACE_S(8) break;
-    }
-#undef ACE_S
-}
-
 static void launch_adjoint(aceb200_model* m, long long nenv, long long ldA, bool want_D)
 {
     HostTables& T = m->T;
@@ -842,9 +817,7 @@ static void launch_adjoint(aceb200_model* m, long long nenv, long long ldA, bool
             p.P = T.P; p.pb0 = sp.pb0;
             p.stream = sp.blocks.as<uint4>(); p.ctl = (eo ? m->e_ctl : m->d_ctl).as<unsigned>(); p.tinfo = sp.tinfo.as<uint4>(); p.w0 = sp.w0.as<double>();
             p.Ac = m->cur->ws_Ac.as<c2>(); p.ldA = ldA; p.Dt = m->cur->ws_Dt.as<c2>(); p.E = m->cur->ws_E.as<double>(); p.nenv = nenv;
-            if (m->stream_nf == 2) launch_stream_nf<2>(m, p, grid, smem);
-            else if (m->stream_nf == 3) launch_stream_nf<3>(m, p, grid, smem);
-            else launch_stream_nf<4>(m, p, grid, smem);
+            launch_stream_inst(m->stream_nf, m->stream_pb, m->cw, m->stream_epl, p, grid, smem, m->cur->stream);
             CU(cudaGetLastError());
             m->launches++;
         }
