@@ -94,3 +94,11 @@ def test_emulated_structure_path(emu, monkeypatch):
         perm = np.concatenate([first[i] + rng.permutation(first[i + 1] - first[i]) for i in range(len(X))])
         E, F, W = model.evaluator.handle.structure_energy_forces(B200Structure(X, first, nbr[perm], image[perm], cell, species))
         assert relerr(E, Eo) < 1e-12 and relerr(F, Fo) < 1e-12 and relerr(W, Wo) < 1e-12
+
+
+def test_emulated_many_chunks(emu, monkeypatch):
+    """A host batch of 700 small ragged environments in chunks of 64: every pipeline lane is reused several times."""
+    import numpy as np
+    monkeypatch.setenv("ACEB200_CHUNK_ENVS", "64")
+    rng = np.random.default_rng(5)
+    compare_all(make_basis("inv_simple_3_6"), 1, [int(j) for j in rng.integers(1, 7, 700)], seed=23, jacobians=False)

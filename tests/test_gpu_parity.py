@@ -54,6 +54,10 @@ def test_multichunk_path_matches_oracle(monkeypatch):
     monkeypatch.setenv("ACEB200_CHUNK_ENVS", "32")
     compare_all(make_basis("inv_simple_3_6"), 2, [7] * 70 + [3, 129, 1], seed=21)
     compare_all(make_basis("species_3_5"), 1, [9] * 45, seed=22)
+    # many chunks over all four pipeline lanes, ragged small environments
+    monkeypatch.setenv("ACEB200_CHUNK_ENVS", "64")
+    rng = np.random.default_rng(5)
+    compare_all(make_basis("inv_simple_3_6"), 1, [int(j) for j in rng.integers(1, 7, 700)], seed=23, jacobians=False)
 
 
 def test_device_resident_batch_matches_host_batch():
@@ -260,3 +264,6 @@ def test_config2_sampled_oracle_parity_and_properties():
     model.set_params(c)
     Eh, Gh = h.energy_forces(ace.B200Batch(R[: 40 * 50_000], off[:50_001]))
     assert np.array_equal(Eh, E[:50_000]) and np.array_equal(Gh, G[: 40 * 50_000])
+    # (e) evaluate(model, cfg) alone walks the energy-only stream (every AA function once): same energies
+    Eonly = h.energy(ace.B200Batch(Rd, offd)).cpu().numpy()
+    assert relerr(Eonly, E) < TOL

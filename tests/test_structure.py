@@ -174,3 +174,53 @@ def test_fcc_structure_generator_matches_the_generic_neighbour_list():
     assert key(first, nbr, image) == key(f2, n2, i2)
     rev = reverse_pairs(first, nbr, image)
     assert np.all(rev >= 0) and np.array_equal(rev[rev], np.arange(len(nbr)))
+
+
+@pytest.mark.gpu
+def test_large_periodic_structure_properties():
+    """BASELINE config 2's model on a 10^5-atom periodic crystal (42 neighbours): size-independent properties of the
+    caller-side path, plus a sampled comparison with the oracle and with the per-environment entry point."""
+    import math
+    from ace_jl_b200.utils import RnYlm_1pbasis, fcc_structure
+    Bsel = ace.SparseBasis(maxorder=3, p=1, default_maxdeg=12, weight={"n": 1.0, "l": 1.5})
+    basis = ace.SymmetricBasis(ace.Invariant(), RnYlm_1pbasis(maxdeg=12, maxL=math.ceil(12 / 1.5), Bsel=Bsel), Bsel)
+    rng = philox(31)
+    c = rng.random(len(basis)) - 0.5
+    model = ace.LinearACEModel(basis, c)
+    h = model.evaluator.handle
+    X, cell, first, nbr, image = fcc_structure(rng, 29)            # 97 556 atoms, 4.1 * 10^6 pairs
+    st = B200Structure(X, first, nbr, image, cell)
+    E, F, W = h.structure_energy_forces(st)
+    F3, W3 = F[:, 0, :, 0], W[0]
+    assert np.all(np.isfinite(E)) and np.all(np.isfinite(F))
+    # Newton's third law over the periodic cell, and a symmetric virial (rotation invariance of the energy)
+    assert np.abs(F3.sum(axis=0)).max() < 1e-10 * np.abs(F3).max() * math.sqrt(len(X))
+    assert np.abs(W3 - W3.T).max() < 1e-10 * np.abs(W3).max()
+    # a rigid translation changes nothing; the result does not depend on the chunking of the centres
+    E2, F2, W2 = h.structure_energy_forces(B200Structure(X + np.array([0.3, -1.1, 2.7]), first, nbr, image, cell))
+    assert relerr(E2, E) < 1e-11 and relerr(F2, F) < 1e-9
+    import os
+    os.environ["ACEB200_STRUCT_MB"] = "1"
+    try:
+        E4, F4, W4 = h.structure_energy_forces(st)
+    finally:
+        del os.environ["ACEB200_STRUCT_MB"]
+    assert np.array_equal(E4, E) and np.array_equal(F4, F)
+    # the per-environment entry point on the same environments gives the same site energies, and its pair gradients
+    # assemble to the same forces
+    R, off, _, centre = st.environments()
+    Eb, G = h.energy_forces(ace.B200Batch(R, off))
+    assert np.array_equal(Eb, E)
+    Fa = np.zeros_like(F3)
+    np.add.at(Fa, centre, G[:, 0, :, 0])
+    np.add.at(Fa, nbr, -G[:, 0, :, 0])
+    assert relerr(Fa, F3) < 1e-11
+    assert relerr(-np.einsum("pa,pb->ab", G[:, 0, :, 0], R), W3) < 1e-11
+    # a sample of centres against the oracle
+    o = Oracle(basis_descriptor(basis, c.reshape(-1, 1)))
+    sel = rng.choice(len(X), size=300, replace=False)
+    Rs = np.concatenate([R[off[i]:off[i + 1]] for i in sel])
+    offs = np.concatenate(([0], np.cumsum([off[i + 1] - off[i] for i in sel])))
+    Eo, Go = o.energy_forces(Rs, offs)
+    assert relerr(E[sel], Eo) < TOL
+    assert relerr(np.concatenate([G[off[i]:off[i + 1]] for i in sel]), Go) < TOL
