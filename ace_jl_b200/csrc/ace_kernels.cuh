@@ -884,8 +884,8 @@ __global__ void __launch_bounds__(kForceThreads, ACE_FORCE_MINB) k_forces(const 
         }
         __syncthreads();
         const int nj = joff[ne];
+        int el = 0;                          // j only grows from pass to pass: the environment search resumes where it stopped
         for (int j = tid; j < nj; j += kForceThreads) {
-            int el = 0;
             while (el + 1 < ne && joff[el + 1] <= j) ++el;
             const double x = Rb[3 * j], y = Rb[3 * j + 1], z = Rb[3 * j + 2];
             int q = 0;
