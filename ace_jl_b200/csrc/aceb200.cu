@@ -953,7 +953,15 @@ static void harvest(aceb200_model* m, Lane& L, double& kernel_ms, double (&stage
     L.busy = false;
 }
 
-static void run(aceb200_model* m, const aceb200_batch* b, int want, const Outputs& o)
+// What an internal caller (the structure driver) already knows about a DEVICE batch, so that run() need not
+// synchronise with the GPU to learn it: the host copy of the offsets, and that the error flag is checked later.
+struct RunHints {
+    const long long* host_offsets = nullptr;   // [nenv + 1], the same numbers as the device-resident batch.offsets
+    bool defer_errflag = false;                // do not reset / read back ws_err in this call, and do not wait for the
+                                               // kernels either (no per-call timing): the caller synchronises once
+};
+
+static void run(aceb200_model* m, const aceb200_batch* b, int want, const Outputs& o, const RunHints* hints = nullptr)
 {
     validate_batch(b);
     HostTables& T = m->T;
@@ -977,7 +985,16 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
     m->cur = &m->lanes[0];
 
     // workspace bytes per environment (J-dependent parts use the batch average, bounded below)
-    std::vector<long long> ends = boundary_offsets(m, b, b->nenv);   // total neighbour count
+    auto bounds = [&](long long stp) {
+        if (hints && hints->host_offsets) {
+            const long long nb = (b->nenv + stp - 1) / stp;
+            std::vector<long long> out(nb + 1);
+            for (long long i = 0; i <= nb; ++i) out[i] = hints->host_offsets[std::min(i * stp, (long long)b->nenv)];
+            return out;
+        }
+        return boundary_offsets(m, b, stp);
+    };
+    std::vector<long long> ends = bounds(b->nenv);   // total neighbour count
     const long long nJ_tot = ends[1] - ends[0];
     const double Jav = std::max(1.0, (double)nJ_tot / (double)b->nenv);
     size_t per_env = (size_t)T.nS * 16 + 64;
@@ -1006,21 +1023,24 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
     }
     // chunk boundaries in environments (uniform; ramping the first and last chunks of a host batch down to step/8 was
     // measured and changes nothing: 23.6 ms vs 23.5 ms per 10^6 environments, the link itself is the bound)
-    std::vector<long long> bo = boundary_offsets(m, b, step);
+    std::vector<long long> bo = bounds(step);
     std::vector<long long> eb;
     for (long long e = 0; e < b->nenv; e += step) eb.push_back(e);
     eb.push_back(b->nenv);
 
     m->ws_err.reserve(sizeof(int));
-    CU(cudaMemsetAsync(m->ws_err.p, 0, sizeof(int), m->lanes[0].stream));
-    CU(cudaStreamSynchronize(m->lanes[0].stream));
+    if (!(hints && hints->defer_errflag)) {
+        CU(cudaMemsetAsync(m->ws_err.p, 0, sizeof(int), m->lanes[0].stream));
+        CU(cudaStreamSynchronize(m->lanes[0].stream));
+    }
     double kernel_ms = 0.0;
     double stage_ms[3] = {0.0, 0.0, 0.0};
     const long long nchunks = (long long)eb.size() - 1;
     for (long long ic = 0; ic < nchunks; ++ic) {
         Lane& L = m->lanes[ic % nlanes];
         m->cur = &L;
-        harvest(m, L, kernel_ms, stage_ms);      // the lane's previous chunk must be done before its buffers are reused
+        if (!(hints && hints->defer_errflag && !host)) harvest(m, L, kernel_ms, stage_ms);      // the lane's previous chunk must be done before its buffers are
+                                                      // reused (a deferred device batch runs on one stream: stream order suffices)
         Chunk c;
         c.e0 = eb[ic]; c.e1 = eb[ic + 1]; c.j0 = bo[ic]; c.j1 = bo[ic + 1];
         const long long ne = c.e1 - c.e0, nj = c.j1 - c.j0;
@@ -1135,11 +1155,12 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
         }
         L.busy = true;
     }
-    for (int l = 0; l < nlanes; ++l) harvest(m, m->lanes[l], kernel_ms, stage_ms);
+    if (hints && hints->defer_errflag) { for (int l = 0; l < nlanes; ++l) m->lanes[l].busy = false; }
+    else for (int l = 0; l < nlanes; ++l) harvest(m, m->lanes[l], kernel_ms, stage_ms);
     m->cur = &m->lanes[0];
     m->last_ms = kernel_ms;
     for (int i = 0; i < 3; ++i) m->stage_ms[i] = stage_ms[i];
-    check_errflag(m);
+    if (!(hints && hints->defer_errflag)) check_errflag(m);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1186,7 +1207,7 @@ static void run_structure(aceb200_model* m, const aceb200_structure* s, double* 
         }
     } else cut.push_back(na);
     const size_t nch = cut.size() - 1;
-    while (m->s_ev.size() < nch + 2) { cudaEvent_t e; CU(cudaEventCreate(&e)); m->s_ev.push_back(e); }
+    while (m->s_ev.size() < nch + 3) { cudaEvent_t e; CU(cudaEventCreate(&e)); m->s_ev.push_back(e); }
 
     m->s_err.reserve(sizeof(int));
     CU(cudaMemsetAsync(m->s_err.p, 0, sizeof(int), st));
@@ -1232,6 +1253,9 @@ static void run_structure(aceb200_model* m, const aceb200_structure* s, double* 
         dE = Esite ? Esite : m->s_E.as<double>(); dF = F; dW = W;
     }
 
+    m->ws_err.reserve(sizeof(int));
+    CU(cudaMemsetAsync(m->ws_err.p, 0, sizeof(int), st));
+    CU(cudaEventRecord(m->s_ev[nch + 1], st));         // the whole device-side sequence is timed as one interval
     double kernel_ms = 0.0, stage_ms[3] = {0.0, 0.0, 0.0};
     for (size_t k = 0; k < nch; ++k) {
         const long long a0 = cut[k], a1 = cut[k + 1];
@@ -1244,9 +1268,10 @@ static void run_structure(aceb200_model* m, const aceb200_structure* s, double* 
         sub.nenv = a1 - a0; sub.offsets = reinterpret_cast<const int64_t*>(dfirst + a0); sub.R = m->s_R.as<double>();
         sub.species = species ? m->s_sp.as<int>() : nullptr; sub.space = ACEB200_DEVICE; sub._pad = 0;
         Outputs o; o.E = dE + (size_t)a0 * P; o.G = m->s_G.as<double>();
-        run(m, &sub, W_E | W_G, o);
-        kernel_ms += m->last_ms;
-        for (int i = 0; i < 3; ++i) stage_ms[i] += m->stage_ms[i];
+        RunHints hints;
+        hints.host_offsets = host ? reinterpret_cast<const long long*>(s->first) + a0 : nullptr;
+        hints.defer_errflag = true;              // one read-back for the whole structure, below
+        run(m, &sub, W_E | W_G, o, &hints);
     }
     if (host) CU(cudaStreamWaitEvent(st, m->s_ev[nch], 0));
     if (!drev) {
@@ -1272,17 +1297,23 @@ static void run_structure(aceb200_model* m, const aceb200_structure* s, double* 
         ACE_LAUNCH(kf2, dim3(T.nprop), dim3(32), 0, st, nblk, (const double*)m->s_part.as<double>(), dW);
         CU(cudaGetLastError()); m->launches++;
     }
+    CU(cudaEventRecord(m->s_ev[nch + 2], st));
     int flag = 0;
     if (host) {
         if (Esite) CU(cudaMemcpyAsync(Esite, dE, (size_t)na * P * sizeof(double), cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(F, dF, (size_t)na * K * sizeof(double), cudaMemcpyDeviceToHost, st));
         if (W) CU(cudaMemcpyAsync(W, dW, (size_t)T.nprop * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
+    int eflag = 0;
     CU(cudaMemcpyAsync(&flag, m->s_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&eflag, m->ws_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    { float ms = 0.f; CU(cudaEventElapsedTime(&ms, m->s_ev[nch + 1], m->s_ev[nch + 2])); kernel_ms = ms; }
     m->last_ms = kernel_ms;
     for (int i = 0; i < 3; ++i) m->stage_ms[i] = stage_ms[i];
     if (flag) throw ModelError(ACEB200_EDESC, "structure: neighbour or reverse-pair index out of range");
+    if (eflag == 5) throw ModelError(ACEB200_EEMPTY, "Product1pBasis can only be evaluated with non-empty configurations");
+    if (eflag == 6) throw ModelError(ACEB200_ECATEGORY, "species code not found in the category list");
 }
 
 // FP64 FMA throughput probe: 8 independent dependent-FMA chains per thread.  The roofline
