@@ -827,6 +827,13 @@ constexpr int kForceTEmax = 32;      // environments per CTA (ForceParams::TE), 
 // u += D[n] R[n], v += D[n] dR[n] for n < cnt, with n a compile-time register index: a fall-through
 // switch on the (warp-uniform) column length replaces a per-n predicate.  R_n lives in registers; dR_n/dr is
 // parked in shared memory ([n][thread]) so that the register budget allows ACE_FORCE_MINB resident CTAs.
+// dR_n/dr is re-read from shared memory at every use: through a plain pointer ptxas hoists all NMAX loads above the column
+// loop and keeps them in 2 NMAX registers for the whole harmonics walk, which is what pushed k_forces into spilling.
+#ifdef ACEB200_EMU
+#define ACE_DR_LOAD(p) (*(p))
+#else
+#define ACE_DR_LOAD(p) (*reinterpret_cast<const volatile double*>(p))
+#endif
 template <int NMAX, int STRIDE>
 __device__ __forceinline__ void column_dot(const c2* D, int cnt, const double (&Rn)[NMAX], const double* dRs,
                                            double& ur, double& ui, double& vr, double& vi)
@@ -835,7 +842,7 @@ __device__ __forceinline__ void column_dot(const c2* D, int cnt, const double (&
     case (n) + 1:                                                                        \
         if ((n) < NMAX) {                                                                \
             const c2 d = D[(size_t)(n) * STRIDE];                                        \
-            const double dr = dRs[(n) * kForceThreads];                                  \
+            const double dr = ACE_DR_LOAD(dRs + (n) * kForceThreads);                    \
             ur += d.x * Rn[(n) < NMAX ? (n) : 0]; ui += d.y * Rn[(n) < NMAX ? (n) : 0];      \
             vr += d.x * dr; vi += d.y * dr;                                              \
         }

@@ -863,9 +863,11 @@ static void launch_forces(aceb200_model* m, const BatchDev& B, long long nJ, lon
     const double Jbar = (double)nJ / (double)B.nenv;
     int best = 1;
     double besteff = 0.0;
+    int minb = ACE_FORCE_MINB;                       // resident CTAs per SM the shared-memory budget is sized for
+    if (const char* ov = getenv("ACEB200_FORCE_MINB")) minb = std::max(1, atoi(ov));
     for (int te = 1; te <= kForceTEmax; ++te) {
         const size_t sm = (size_t)te * p.dpitch * sizeof(c2) + misc;
-        if (te > 1 && (sm > (size_t)m->smem_optin / ACE_FORCE_MINB - 1024 || (B.nenv + te - 1) / te < 2LL * 5 * m->sm_count)) break;
+        if (te > 1 && (sm > (size_t)m->smem_optin / minb - 1024 || (B.nenv + te - 1) / te < 2LL * 5 * m->sm_count)) break;
         const double rows = te * Jbar, eff = rows / (kForceThreads * ceil(rows / kForceThreads));
         if (eff >= besteff - 1e-9) { besteff = eff; best = te; }
     }
