@@ -1310,7 +1310,9 @@ static __global__ void k_build_pairs(long long a0, long long na, long long natom
     }
 }
 
-// rev[p] for the pairs of 32 centres per CTA: scan the pair list of j = nbr[p] for (neighbour i, image -S)
+// rev[p] for the pairs of 32 centres per CTA: scan the pair list of j = nbr[p] for (neighbour i, image -S).  The table is
+// symmetric, so only one pair of each (p, rev p) couple searches -- the one whose (centre, image) is smaller than its
+// reverse's -- and writes both entries; rev is pre-set to -1 (no reverse pair) by the caller.
 static __global__ void k_find_rev(long long natoms, const long long* first, const int* nbr, const signed char* image, int* rev)
 {
     ACE_DYN_SMEM(long long, f);                 // [kPairAtoms + 1]
@@ -1324,30 +1326,37 @@ static __global__ void k_find_rev(long long natoms, const long long* first, cons
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (f[mid] <= p) lo = mid; else hi = mid; }
         const int i = (int)(c0 + lo);
         const long long j = __ldg(nbr + p);
+        if (j < 0 || j >= natoms) continue;
+        int s0 = 0, s1 = 0, s2 = 0;             // the reverse pair's image
+        if (image) { s0 = -__ldg(image + 3 * p); s1 = -__ldg(image + 3 * p + 1); s2 = -__ldg(image + 3 * p + 2); }
+        // who searches: the pair with the smaller centre; for a self-image pair (i == j) the one whose image is
+        // lexicographically smaller than its reverse's (a pair that is its own reverse cannot occur: S = 0 means r = 0)
+        if (j < i) continue;
+        if (j == i) {
+            const int t0 = -s0, t1 = -s1, t2 = -s2;     // this pair's own image
+            const bool smaller = t0 != s0 ? t0 < s0 : (t1 != s1 ? t1 < s1 : t2 < s2);
+            if (!smaller) continue;
+        }
         int found = -1;
-        if (j >= 0 && j < natoms) {
-            int s0 = 0, s1 = 0, s2 = 0;
-            if (image) { s0 = -__ldg(image + 3 * p); s1 = -__ldg(image + 3 * p + 1); s2 = -__ldg(image + 3 * p + 2); }
-            // neighbour lists are normally sorted by neighbour index within a centre: binary search for the first
-            // entry >= i and walk the (few) images of i; an unsorted list falls back to the linear scan below
-            long long lo2 = __ldg(first + j), hi2 = __ldg(first + j + 1);
-            const long long qb = lo2, qe = hi2;
-            while (lo2 < hi2) { const long long mid = (lo2 + hi2) >> 1; if (__ldg(nbr + mid) < i) lo2 = mid + 1; else hi2 = mid; }
-            for (long long q = lo2; q < qe && __ldg(nbr + q) == i; ++q) {
+        // neighbour lists are normally sorted by neighbour index within a centre: binary search for the first
+        // entry >= i and walk the (few) images of i; an unsorted list falls back to the linear scan below
+        long long lo2 = __ldg(first + j), hi2 = __ldg(first + j + 1);
+        const long long qb = lo2, qe = hi2;
+        while (lo2 < hi2) { const long long mid = (lo2 + hi2) >> 1; if (__ldg(nbr + mid) < i) lo2 = mid + 1; else hi2 = mid; }
+        for (long long q = lo2; q < qe && __ldg(nbr + q) == i; ++q) {
+            if (image && (__ldg(image + 3 * q) != s0 || __ldg(image + 3 * q + 1) != s1 || __ldg(image + 3 * q + 2) != s2)) continue;
+            found = (int)q;
+            break;
+        }
+        if (found < 0) {
+            for (long long q = qb; q < qe; ++q) {
+                if (__ldg(nbr + q) != i) continue;
                 if (image && (__ldg(image + 3 * q) != s0 || __ldg(image + 3 * q + 1) != s1 || __ldg(image + 3 * q + 2) != s2)) continue;
                 found = (int)q;
                 break;
             }
-            if (found < 0) {
-                for (long long q = qb; q < qe; ++q) {
-                    if (__ldg(nbr + q) != i) continue;
-                    if (image && (__ldg(image + 3 * q) != s0 || __ldg(image + 3 * q + 1) != s1 || __ldg(image + 3 * q + 2) != s2)) continue;
-                    found = (int)q;
-                    break;
-                }
-            }
         }
-        rev[p] = found;
+        if (found >= 0) { rev[p] = found; rev[found] = (int)p; }
     }
 }
 

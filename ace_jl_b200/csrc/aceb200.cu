@@ -1280,6 +1280,7 @@ static void run_structure(aceb200_model* m, const aceb200_structure* s, double* 
         // no reverse table from the caller: find each pair's reverse on the device (all pair tables are resident now).
         // (Running this search on a second, high-priority stream underneath the evaluation kernels was measured and
         // is slower: the kernels contend for the same SMs, 21 ms vs 17 ms end to end on the benchmark structure.)
+        CU(cudaMemsetAsync(m->s_rev.p, 0xff, std::max<long long>(np, 1) * sizeof(int), st));      // -1: no reverse pair
         auto kfn = k_find_rev;
         ACE_LAUNCH(kfn, dim3(blocks_for(na, kPairAtoms)), dim3(128), (kPairAtoms + 1) * sizeof(long long), st, na, dfirst, dnbr, dimg, m->s_rev.as<int>());
         CU(cudaGetLastError()); m->launches++;

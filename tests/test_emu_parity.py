@@ -96,6 +96,28 @@ def test_emulated_structure_path(emu, monkeypatch):
         assert relerr(E, Eo) < 1e-12 and relerr(F, Fo) < 1e-12 and relerr(W, Wo) < 1e-12
 
 
+def test_emulated_structure_self_images(emu):
+    """A cell smaller than the cutoff: pairs with i == j (an atom and its own periodic image) in the reverse search."""
+    import numpy as np
+    import ace_jl_b200 as ace
+    from ace_jl_b200.descriptor import basis_descriptor
+    from ace_jl_b200.structure import B200Structure, neighbourlist
+    from ace_jl_b200.utils import philox
+    from conftest import relerr
+    from oracle import Oracle
+    from test_structure import RCUT, tiny_cell
+    basis = make_basis("inv_simple_3_6")
+    rng = philox(23)
+    c = rng.random((len(basis), 1)) - 0.5
+    model = ace.LinearACEModel(basis, c[:, 0])
+    X, cell = tiny_cell(rng)
+    first, nbr, image, rev = neighbourlist(X, RCUT, cell, (True, True, True))
+    Eo, Fo, Wo = Oracle(basis_descriptor(basis, c)).structure_energy_forces(X, first, nbr, image, cell)
+    for r in (rev, None):
+        E, F, W = model.evaluator.handle.structure_energy_forces(B200Structure(X, first, nbr, image, cell, None, r))
+        assert relerr(E, Eo) < 1e-12 and relerr(F, Fo) < 1e-10 and relerr(W, Wo) < 1e-12
+
+
 def test_emulated_many_chunks(emu, monkeypatch):
     """A host batch of 700 small ragged environments in chunks of 64: every pipeline lane is reused several times."""
     import numpy as np

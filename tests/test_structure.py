@@ -99,6 +99,13 @@ def test_oracle_assembly_is_minus_the_gradient_of_the_total_energy():
     assert np.abs(F.sum(axis=0)).max() < 1e-12 * np.abs(F).max() * len(X)
 
 
+def tiny_cell(rng):
+    """Two atoms in a cell smaller than the cutoff: every atom sees several images of itself (pairs with i == j)."""
+    cell = np.array([[1.9, 0.0, 0.0], [0.3, 2.1, 0.0], [0.0, 0.2, 2.0]])
+    X = np.array([[0.1, 0.2, 0.1], [1.0, 1.1, 0.9]]) + 0.05 * rng.random((2, 3))
+    return X, cell
+
+
 GPU_CASES = [("inv_simple_3_6", 1, True, False), ("inv_sparse_3_12", 1, True, True), ("inv_simple_3_6", 3, False, True),
              ("species_3_5", 4, True, True), ("inv_sparse_4_8", 1, False, False)]
 
@@ -143,6 +150,22 @@ def test_structure_matches_oracle(kind, nprop, periodic, use_rev, monkeypatch):
     sd = B200Structure(t(X), t(first), t(nbr), t(image), cell, t(species), t(rev) if use_rev else None)
     Ed, Fd, Wd = model.evaluator.handle.structure_energy_forces(sd)
     assert np.array_equal(Fd.cpu().numpy(), F) and np.array_equal(Ed.cpu().numpy(), E)
+
+
+@pytest.mark.gpu
+def test_structure_with_self_images():
+    basis = make_basis("inv_simple_3_6")
+    rng = philox(23)
+    c = rng.random((len(basis), 1)) - 0.5
+    model = ace.LinearACEModel(basis, c[:, 0])
+    X, cell = tiny_cell(rng)
+    first, nbr, image, rev = neighbourlist(X, RCUT, cell, (True, True, True))
+    centre = np.repeat(np.arange(2), np.diff(first))
+    assert np.any(nbr == centre) and np.all(rev >= 0)
+    Eo, Fo, Wo = Oracle(basis_descriptor(basis, c)).structure_energy_forces(X, first, nbr, image, cell)
+    for r in (rev, None):
+        E, F, W = model.evaluator.handle.structure_energy_forces(B200Structure(X, first, nbr, image, cell, None, r))
+        assert relerr(E, Eo) < TOL and relerr(F, Fo) < 1e-10 and relerr(W, Wo) < TOL   # forces nearly cancel: looser
 
 
 @pytest.mark.gpu
