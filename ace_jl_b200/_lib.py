@@ -97,6 +97,7 @@ SYMBOLS = [
     ("aceb200_last_kernel_ms", C.c_int, [C.c_void_p, c_double_p]),
     ("aceb200_last_stage_ms", C.c_int, [C.c_void_p, c_double_p]),
     ("aceb200_measure_fp64", C.c_int, [c_double_p]),
+    ("aceb200_measure_dmma", C.c_int, [c_double_p]),
 ]
 
 

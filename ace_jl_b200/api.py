@@ -233,6 +233,8 @@ class Handle:
         E = st.empty((st.natoms, self.s.nprop, self.s.ncomp)) if E is None else E
         F = st.empty((st.natoms, self.s.nprop, 3, self.s.ncomp)) if F is None else F
         W = (st.empty((self.s.nprop, 3, 3)) if virial else None) if W is None else W
+        if st.device:
+            self.use_current_torch_stream()      # inputs produced on a non-default torch stream stay stream-ordered
         cs = st.c_struct()
         L.check(self.lib.aceb200_structure_energy_forces(self.ptr, C.byref(cs), _out_ptr(E), _out_ptr(F), _out_ptr(W)))
         return E, F, W
@@ -241,6 +243,13 @@ class Handle:
 def measure_fp64_tflops() -> float:
     v = C.c_double()
     L.check(L.load().aceb200_measure_fp64(C.byref(v)))
+    return v.value
+
+
+def measure_dmma_tflops() -> float:
+    """FP64 tensor-core (mma.sync.m8n8k4.f64) throughput of the current device, TFLOP/s."""
+    v = C.c_double()
+    L.check(L.load().aceb200_measure_dmma(C.byref(v)))
     return v.value
 
 
@@ -261,13 +270,25 @@ def _trivial_symm(basis) -> SymmetricBasis:
     return SymmetricBasis.from_parts(Invariant(), pib, A2B, NoSym(), False)
 
 
+def _table_stamp(obj) -> tuple:
+    """Version counters of every table a handle of `obj` is built from.  sparsify / clean_* / set_spec mutate the
+    tables in place (as the reference's `sparsify!`, `clean_pibasis!`, `set_spec!` do) and bump these counters."""
+    chain = [obj]
+    if isinstance(obj, SymmetricBasis):
+        chain += [obj.pibasis, obj.pibasis.basis1p, id(obj.A2Bmap)]
+    elif isinstance(obj, PIBasis):
+        chain += [obj.basis1p, id(obj.spec)]
+    return tuple(getattr(o, "_version", 0) if not isinstance(o, int) else o for o in chain)
+
+
 def _handle_of(obj) -> Handle:
-    h = getattr(obj, "_b200_handle", None)
-    if h is None:
+    cached = getattr(obj, "_b200_handle", None)
+    stamp = _table_stamp(obj)
+    if cached is None or cached[1] != stamp:        # never evaluate with device tables of a basis that has changed since
         symm = obj if isinstance(obj, SymmetricBasis) else _trivial_symm(obj)
-        h = Handle(basis_descriptor(symm, None))
-        obj._b200_handle = h
-    return h
+        cached = (Handle(basis_descriptor(symm, None)), stamp)
+        obj._b200_handle = cached
+    return cached[0]
 
 
 def _species_map(basis1p: Product1pBasis):

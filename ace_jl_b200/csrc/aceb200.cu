@@ -1333,6 +1333,28 @@ __global__ void k_fp64_peak(int iters, double* sink)
     if (s == 123.456) sink[threadIdx.x] = s;
 }
 
+
+// FP64 tensor-core (DMMA, mma.sync.m8n8k4.f64) throughput probe: 8 independent accumulator pairs per thread.
+// One warp-level m8n8k4 is 8 * 8 * 4 FMAs = 512 flops.  north_star asks for the tensor-core roofline of the
+// multi-property readout to be reported against a measured figure.
+__global__ void k_dmma_peak(int iters, double* sink)
+{
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    double c[8][2];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { c[k][0] = k * 1e-3; c[k][1] = -k * 1e-3; }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                         : "+d"(c[k][0]), "+d"(c[k][1]) : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += c[k][0] + c[k][1];
+    if (s == 123.456) sink[threadIdx.x] = s;
+}
+
 // ----------------------------------------------------------------------------------------------
 // extern "C"
 // ----------------------------------------------------------------------------------------------
@@ -1493,6 +1515,37 @@ int aceb200_measure_fp64(double* tflops)
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, e0, e1));
         double fl = (double)blocks * threads * (double)iters * 8.0 * 2.0;
+        if (ms > 0.f) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    *tflops = best;
+    API_END
+}
+
+
+int aceb200_measure_dmma(double* tflops)
+{
+    API_BEGIN
+    if (!tflops) throw ModelError(ACEB200_EDESC, "null argument");
+    if (aceb200_device_count() <= 0) throw ModelError(ACEB200_ECUDA, "no CUDA device");
+    CU(cudaSetDevice(g_device));
+    int sms = 148;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g_device));
+    double* sink = nullptr;
+    CU(cudaMalloc((void**)&sink, 1024 * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    const int iters = 1 << 13, threads = 256, blocks = sms * 8;
+    auto kfn = k_dmma_peak;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(cudaEventRecord(e0, nullptr));
+        ACE_LAUNCH(kfn, dim3(blocks), dim3(threads), 0, (cudaStream_t) nullptr, iters, sink);
+        CU(cudaEventRecord(e1, nullptr));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        double fl = (double)blocks * (threads / 32) * (double)iters * 8.0 * 512.0;
         if (ms > 0.f) best = std::max(best, fl / (ms * 1e-3) / 1e12);
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);

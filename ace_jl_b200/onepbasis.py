@@ -193,6 +193,7 @@ class Product1pBasis:
 
     def set_spec(self, spec: Sequence[tuple]):
         """product_1pbasis.jl:308-315."""
+        self._version = getattr(self, "_version", 0) + 1      # invalidates device handles built from the old tables (api._handle_of)
         self.spec = [tuple(b) for b in spec]
         self.indices = np.array(
             [[B.get_index(self._sub(b, i)) for i, B in enumerate(self.bases)] for b in self.spec],

@@ -132,6 +132,7 @@ class PIBasis:
         return [self.basis1p.get_spec(v) for v in self.spec.get_spec(i)]
 
     def sparsify(self, Ikeep):
+        self._version = getattr(self, "_version", 0) + 1
         self.spec = self.spec.sparsify(Ikeep)
         return self
 
@@ -145,5 +146,6 @@ class PIBasis:
         newtab = tab.copy()
         newtab[nz] = new_inds[tab[nz] - 1]
         assert np.all(newtab[nz] > 0)
+        self._version = getattr(self, "_version", 0) + 1
         self.spec = PIBasisSpec(self.spec.orders, newtab)
         return self

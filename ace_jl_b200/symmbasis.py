@@ -201,6 +201,7 @@ class SymmetricBasis:
 
     def clean_pibasis(self, atol: float = 0.0):
         """symmbasis.jl:225-236."""
+        self._version = getattr(self, "_version", 0) + 1
         nrm = self.A2Bmap.col_norms()
         Inz = np.nonzero(nrm > atol)[0]
         if len(Inz) < self.A2Bmap.n:
@@ -217,5 +218,6 @@ class SymmetricBasis:
             dele = set(int(d) for d in delete)
             keep = [i for i in range(1, len(self) + 1) if i not in dele]
         keep0 = np.asarray(sorted(int(k) - 1 for k in keep))
+        self._version = getattr(self, "_version", 0) + 1
         self.A2Bmap = self.A2Bmap.select_rows(keep0)
         return self.clean_pibasis(atol=0.0)

@@ -36,11 +36,15 @@ class O3:
         """symmetrygroups.jl:119-128.  Returns U (nrows, nM, ncomp) and the list of mm tuples."""
         canon = {}
         pattern = tuple(canon.setdefault(n, len(canon)) for n in nn)
-        key = (id(rotc), ll, pattern)
+        # keyed on the PROPERTY (type + component count), never on id(rotc): a Rot3DCoeffs is a short-lived local of
+        # SymmetricBasis._build_A2B and CPython reuses ids, so an O3() shared by two bases of different properties
+        # (the reference's O3 is a stateless singleton) would otherwise be served stale coefficients
+        pkey = (type(rotc.phi).__name__, getattr(rotc.phi, "ncomp", None), repr(getattr(rotc.phi, "__dict__", None)))
+        key = (pkey, ll, pattern)
         hit = self._rpe_cache.get(key)
         if hit is not None:
             return hit
-        rkey = (id(rotc), ll)
+        rkey = (pkey, ll)
         if rkey not in self._re_cache:
             self._re_cache[rkey] = re_basis(rotc, ll)
         Ure, Mre = self._re_cache[rkey]

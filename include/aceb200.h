@@ -230,6 +230,11 @@ int aceb200_last_stage_ms(const aceb200_model *m, double *ms3);
  * MEASURED_PEAKS.json does not record it. */
 int aceb200_measure_fp64(double *tflops);
 
+/* Measured FP64 tensor-core (DMMA, mma.sync.m8n8k4.f64) throughput of the current device in TFLOP/s: the
+ * roofline the north_star names for the dense multi-property readout (src/evaluator.jl:137-143 with SVector
+ * coefficients); reported next to the FMA figure so that the choice between the two pipes is made on data. */
+int aceb200_measure_dmma(double *tflops);
+
 #ifdef __cplusplus
 }
 #endif

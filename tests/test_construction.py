@@ -147,3 +147,40 @@ def test_discrete_jacobi_recursion_is_consistent():
         P.append((J.A[n] * t + J.B[n]) * P[n - 1] + J.C[n] * P[n - 2])
     G = np.array([[np.dot(a, J.ww * b) for b in P] for a in P])
     assert np.abs(G - np.eye(8)).max() < 1e-10
+
+
+def test_shared_O3_does_not_serve_stale_coupling_coefficients():
+    """One O3() reused for bases of different properties (the reference's O3 is a stateless singleton,
+    src/symmetrygroups.jl:66-94): the rpe cache must be keyed on the property, not on a recyclable object id."""
+    import gc
+    from ace_jl_b200.symmetrygroups import O3
+    from ace_jl_b200.rotations3d import Rot3DCoeffs
+    grp = O3()
+    U1, _ = grp.rpe_basis(Rot3DCoeffs(ace.EuclideanMatrix()), (1, 1), (1, 1))
+    gc.collect()
+    U2, M2 = grp.rpe_basis(Rot3DCoeffs(ace.Invariant()), (1, 1), (1, 1))
+    assert U1.shape[2] == 9 and U2.shape == (1, len(M2), 1)
+    # and whole bases built through one shared group object equal the ones built with private groups
+    B1p = RnYlm_1pbasis(maxdeg=4)
+    Bsel = ace.SimpleSparseBasis(2, 4)
+    shared = O3()
+    a = ace.SymmetricBasis(ace.EuclideanVector(), RnYlm_1pbasis(maxdeg=4), shared, Bsel)
+    b = ace.SymmetricBasis(ace.Invariant(), RnYlm_1pbasis(maxdeg=4), shared, Bsel)
+    b0 = ace.SymmetricBasis(ace.Invariant(), B1p, Bsel)
+    assert a.A2Bmap.ncomp == 3 and b.A2Bmap.ncomp == 1
+    assert np.array_equal(b.A2Bmap.nzval, b0.A2Bmap.nzval) and np.array_equal(b.A2Bmap.rowval, b0.A2Bmap.rowval)
+
+
+def test_mutating_a_basis_invalidates_its_device_handle_stamp():
+    """sparsify! / clean_pibasis! change the tables in place (src/symmbasis.jl:204-236): a cached device handle is
+    only reused while the table stamp is unchanged (api._handle_of)."""
+    from ace_jl_b200.api import _table_stamp
+    basis = ace.SymmetricBasis(ace.Invariant(), RnYlm_1pbasis(maxdeg=4), ace.SimpleSparseBasis(2, 4))
+    s0 = _table_stamp(basis)
+    assert _table_stamp(basis) == s0
+    n0 = len(basis)
+    basis.sparsify(keep=list(range(1, n0 // 2)))
+    assert len(basis) < n0 and _table_stamp(basis) != s0
+    s1 = _table_stamp(basis.pibasis)
+    basis.pibasis.basis1p.set_spec(basis.pibasis.basis1p.spec)
+    assert _table_stamp(basis.pibasis) != s1
