@@ -178,8 +178,9 @@ class Handle:
         self._call("aceb200_eval_AA", b, out)
         return out
 
-    def eval_B(self, b: B200Batch):
-        out = b.empty((b.nenv, self.s.nB, self.s.ncomp), not self.s.symreal)
+    def eval_B(self, b: B200Batch, out=None):
+        if out is None:
+            out = b.empty((b.nenv, self.s.nB, self.s.ncomp), not self.s.symreal)
         self._call("aceb200_eval_B", b, out)
         return out
 
@@ -213,8 +214,9 @@ class Handle:
         self._call("aceb200_adjoint_eval_d", b, w, out)
         return out
 
-    def energy(self, b: B200Batch):
-        E = b.empty((b.nenv, self.s.nprop, self.s.ncomp), not self.s.symreal)
+    def energy(self, b: B200Batch, E=None):
+        if E is None:
+            E = b.empty((b.nenv, self.s.nprop, self.s.ncomp), not self.s.symreal)
         self._call("aceb200_energy", b, E)
         return E
 

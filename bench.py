@@ -1,26 +1,31 @@
 #!/usr/bin/env python
-"""bench.py -- atom-environments/sec for ACE energy + forces (FP64), BASELINE.json's metric.
+"""bench.py -- atom-environments/sec of the ACE evaluation hot path (FP64), BASELINE.json's metric.
 
-Workload (config.workload): BASELINE config 2 -- LinearACEModel, Invariant, ord = 3, maxdeg = 12, wL = 1.5
-(SparseBasis), 40 random neighbours per environment (rho ~ U[rin, rcut], direction uniform), 10^6
-environments per GPU, synthetic (Philox-seeded) positions and random coefficients.
+  python bench.py [--config 2] [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl reference]
 
-One "step" = one evaluate + grad_config pass over the whole batch (every environment's energy and all
-40 x 3 force components).  `value` times K steps with the batch resident in HBM; `e2e` times the same
-call through the C ABI with PINNED HOST buffers (host->device copy of positions and offsets and
-device->host copy of energies and forces inside the timed region).
+--config selects one of BASELINE.json's configurations (ace_jl_b200/workloads.py); the default, 2, is the one the
+metric is quoted on: LinearACEModel energy+forces, Invariant, ord = 3, maxdeg = 12, wL = 1.5 SparseBasis, 40 random
+neighbours per environment, 10^6 environments per GPU, synthetic (Philox-seeded) positions, random coefficients.
+  1   evaluate(basis::SymmetricBasis, cfg) (B values), ord 3 / deg 10, 30 neighbours
+  3   energy+forces, ord 4 / deg 14, 60 neighbours (north_star's 8-GPU configuration: --config 3 --gpus 8)
+  4a / 4   B values of the EuclideanVector / EuclideanMatrix bases, ord 3 / deg 10
+  5 / 5f   16-property, 4-species model: energies / energies + 16 force fields
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl reference]
+One "step" = one pass of the call over the whole batch.  `value` times K steps with the batch resident in HBM;
+`e2e` times the call a user makes with PINNED HOST buffers (host->device copy of the inputs and device->host copy
+of the results inside the timed region).  For the energy+forces configurations the primary `e2e` is the
+caller-shaped entry point aceb200_structure_energy_forces (positions + neighbour list in, site energies + atomic
+forces + virial out); the per-environment call (48 B per pair over PCIe, the reference's own call shape) is reported
+beside it as `e2e_per_environment`.
 
-N > 1 is launched by torchrun (one rank per GPU); environments are independent, so each rank evaluates its
-own shard (weak scaling: E environments per GPU) and the only collective is the all-reduce of the total
-energy (NCCL), issued inside the timed region.
+N > 1 is launched by torchrun (one rank per GPU); environments are independent, so each rank evaluates its own
+shard (weak scaling: E environments per GPU) and the only collective is the all-reduce of the total energy (NCCL),
+issued inside the timed region.
 """
 from __future__ import annotations
 
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
@@ -32,35 +37,10 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-METRIC = "atom-environments/sec (energy+forces, FP64)"
 UNIT = "env/s"
-J = 40
-ORD, MAXDEG, WL = 3, 12, 1.5
-SEED = 20242
-
-
-def build_model(nprop: int = 1):
-    import ace_jl_b200 as ace
-    from ace_jl_b200.utils import RnYlm_1pbasis, philox
-    Bsel = ace.SparseBasis(maxorder=ORD, p=1, default_maxdeg=MAXDEG, weight={"n": 1.0, "l": WL})
-    B1p = RnYlm_1pbasis(maxdeg=MAXDEG, maxL=math.ceil(MAXDEG / WL), Bsel=Bsel)
-    basis = ace.SymmetricBasis(ace.Invariant(), B1p, Bsel)
-    c = philox(SEED + 1000).random(len(basis)) - 0.5
-    return basis, c
-
-
-def algorithmic_flops(basis, nJ: int, P: int = 1):
-    """SURVEY.md section 8(d), split by kernel."""
-    b1p = basis.pibasis.basis1p
-    Nn = len(b1p.component(0).R)
-    L = max(b[b1p.sym_index("l")] for b in b1p.spec)
-    sizeP, sizeY, nA = (L + 1) * (L + 2) // 2, (L + 1) ** 2, len(b1p)
-    orders = basis.pibasis.spec.orders
-    f = lambda nu: 6 * (nu - 1) + 18 * max(nu - 2, 0) + (4 * nu + 2) * P  # noqa: E731
-    pool = nJ * (28 + 5 * Nn + 15 * sizeP + 4 * nA)
-    adj = float(sum(int((orders == nu).sum()) * f(nu) for nu in range(1, int(orders.max()) + 1)))
-    forces = nJ * (6 * Nn + 22 * sizeP + (8 * nA + 16 * sizeY) * P)
-    return {"pool": float(pool), "adjoint": adj, "forces": float(forces)}
+METRICS = {"EF": "atom-environments/sec (energy+forces, FP64)",
+           "E": "atom-environments/sec (energies, FP64)",
+           "B": "atom-environments/sec (basis values, FP64)"}
 
 
 class ClockSampler:
@@ -112,79 +92,91 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "scope": scope}
 
 
-def cpu_reference_rate(basis, c, nenv_sample: int, repeats: int = 1):
-    """The restated reference (oracle, C + OpenMP over environments) on this box's host cores."""
+def make_inputs(w, basis, nenv, seed):
+    from ace_jl_b200.utils import philox, rand_envs
+    return rand_envs(philox(seed), basis.pibasis.basis1p.component(0), nenv, w.J, w.nspecies)
+
+
+def cpu_reference_rate(w, basis, c, nenv_sample: int):
+    """The restated reference (oracle, C + OpenMP over environments) on this box's host cores, same call."""
     import oracle as orc
     from ace_jl_b200.descriptor import basis_descriptor
-    from ace_jl_b200.utils import philox, rand_envs
-    o = orc.Oracle(basis_descriptor(basis, c.reshape(-1, 1)))
+    o = orc.Oracle(basis_descriptor(basis, c))
     o.set_threads(len(os.sched_getaffinity(0)))   # all host cores (torchrun exports OMP_NUM_THREADS=1)
-    R, off, _ = rand_envs(philox(SEED + 7), basis.pibasis.basis1p.component(0), nenv_sample, J)
-    o.energy_forces(R[: J * 64], off[:65])  # warm-up (thread pool, page faults)
-    best = float("inf")
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        o.energy_forces(R, off)
-        best = min(best, time.perf_counter() - t0)
-    return nenv_sample / best, o.num_threads(), best
+    R, off, sp = make_inputs(w, basis, nenv_sample, w.seed + 7)
+    fn = {"EF": o.energy_forces, "E": o.energy, "B": o.eval_B}[w.call]
+    nw = min(64, nenv_sample)
+    fn(R[: w.J * nw], off[: nw + 1], None if sp is None else sp[: w.J * nw])  # warm-up (thread pool, page faults)
+    t0 = time.perf_counter()
+    fn(R, off, sp)
+    dt = time.perf_counter() - t0
+    return nenv_sample / dt, o.num_threads(), dt
 
 
-def run_reference_arm(args):
+def default_cpu_sample(w, basis) -> int:
+    """About 10 s of CPU work on 16 cores for the call (measured rates: config 2 ~ 1e5 env/s)."""
+    from ace_jl_b200.workloads import algorithmic_work
+    fl = algorithmic_work(basis, w.J, w.call, w.nprop)["flops_total"] * (10.0 if w.call == "EF" else 3.0)   # the oracle materialises dA
+    return int(max(500, min(100_000, 2.0e11 / fl)))
+
+
+def workload_config(w, nenv, ngpu):
+    return {"workload": f"{w.title}, {nenv} environments per GPU", "baseline_config": w.key,
+            "envs_per_gpu": nenv, "neighbours": w.J, "nprop": w.nprop, "parallelism": f"env-shard x{ngpu}",
+            "l2_policy": "inputs (24*J B/env) and outputs exceed the 126 MB L2: no flush needed"}
+
+
+def run_reference_arm(args, w):
     """--impl reference: the reference's own CPU path.  ACE.jl is Julia and cannot be installed here
     (no Julia, no registry), so this arm times the line-by-line C restatement in oracle/ -- same
     algorithm incl. the materialised dA matrix and the full (maxL+1)^2 harmonics -- with OpenMP over
     environments standing in for `Threads.@threads` over configurations, on all host cores."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    basis, c = build_model()
-    sample = args.cpu_envs
-    times = []
-    cores = 1
+    from ace_jl_b200.workloads import build_basis, coefficients
+    basis = build_basis(w)
+    c = coefficients(w, basis)
+    sample = args.cpu_envs or default_cpu_sample(w, basis)
+    times, cores = [], 1
     for s in range(args.warmup + args.steps):
-        rate, cores, dt = cpu_reference_rate(basis, c, sample)
+        _, cores, dt = cpu_reference_rate(w, basis, c, sample)
         if s >= args.warmup:
             times.append(dt)
     value = sample * len(times) / sum(times)
-    line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    print(json.dumps({
+        "impl": "reference", "metric": METRICS[w.call], "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.envs, 1),
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(w, args.envs or w.nenv, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} environments x {J} neighbours per step (bounded sample of the 1e6-environment workload)"},
+                         "sample": f"{sample} environments x {w.J} neighbours per step (bounded sample of the workload)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(line), flush=True)
-
-
-def workload_config(nenv, ngpu):
-    return {"workload": f"LinearACEModel energy+forces, Invariant, ord={ORD}, maxdeg={MAXDEG}, wL={WL} SparseBasis, "
-                        f"{J} neighbours, {nenv} environments per GPU (BASELINE config 2)",
-            "envs_per_gpu": nenv, "neighbours": J, "parallelism": f"env-shard x{ngpu}",
-            "l2_policy": "inputs (24*J B/env) and outputs exceed the 126 MB L2: no flush needed"}
+        "gpu_launches": 0}), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="2", help="BASELINE configuration: 1, 2, 3, 4a, 4, 5, 5f")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--envs", type=int, default=1_000_000, help="environments per GPU")
-    ap.add_argument("--cpu-envs", type=int, default=100_000, help="environments in the CPU baseline sample")
+    ap.add_argument("--envs", type=int, default=0, help="environments per GPU (default: the configuration's)")
+    ap.add_argument("--cpu-envs", type=int, default=0, help="environments in the CPU baseline sample (default: ~10 s of work)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer legs")
     args = ap.parse_args()
+    from ace_jl_b200.workloads import WORKLOADS, algorithmic_work, build_basis, coefficients
+    if args.config not in WORKLOADS:
+        raise SystemExit(f"--config must be one of {sorted(WORKLOADS)}")
+    w = WORKLOADS[args.config]
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
-        return run_reference_arm(args)
+        return run_reference_arm(args, w)
 
     import torch
     import torch.distributed as dist
     import ace_jl_b200 as ace
-    from ace_jl_b200.api import measure_fp64_tflops
-    from ace_jl_b200.utils import philox, rand_envs
+    from ace_jl_b200.api import measure_dmma_tflops, measure_fp64_tflops
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -198,23 +190,34 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    basis, c = build_model()
-    model = ace.LinearACEModel(basis, c)
+    basis = build_basis(w)
+    c = coefficients(w, basis)
+    model = ace.LinearACEModel(basis, c if w.nprop > 1 else c[:, 0])
     h = model.evaluator.handle
-    nenv = args.envs
-    rng = philox(SEED + 17 * rank)
-    R, off, _ = rand_envs(rng, basis.pibasis.basis1p.component(0), nenv, J)
-    Rd, offd = torch.from_numpy(R).to(dev), torch.from_numpy(off).to(dev)
-    batch = ace.B200Batch(Rd, offd)
-    E = torch.empty((nenv, 1, 1), dtype=torch.float64, device=dev)
-    G = torch.empty((nenv * J, 1, 3, 1), dtype=torch.float64, device=dev)
-    etot = torch.zeros(1, dtype=torch.float64, device=dev)
+    nenv = args.envs or w.nenv
+    J, P = w.J, w.nprop * basis.A2Bmap.ncomp
+    R, off, sp = make_inputs(w, basis, nenv, w.seed + 17 * rank)
+    t = lambda a: None if a is None else torch.from_numpy(a).to(dev)   # noqa: E731
+    batch = ace.B200Batch(t(R), t(off), t(sp))
+    nB, ncomp = len(basis), basis.A2Bmap.ncomp
+    if w.call == "B":
+        out = [torch.empty((nenv, nB, ncomp), dtype=torch.float64 if basis.real else torch.complex128, device=dev)]
+        call = lambda b, o: h.eval_B(b, o[0])   # noqa: E731
+    elif w.call == "E":
+        out = [torch.empty((nenv, w.nprop, ncomp), dtype=torch.float64, device=dev)]
+        call = lambda b, o: h.energy(b, o[0])   # noqa: E731
+    else:
+        out = [torch.empty((nenv, w.nprop, ncomp), dtype=torch.float64, device=dev),
+               torch.empty((nenv * J, w.nprop, 3, ncomp), dtype=torch.float64, device=dev)]
+        call = lambda b, o: h.energy_forces(b, o[0], o[1])   # noqa: E731
+    tot = torch.zeros(1, dtype=torch.float64, device=dev)
 
     def step():
-        h.energy_forces(batch, E, G)
-        etot.copy_(E.sum().reshape(1))
-        if world > 1:
-            dist.all_reduce(etot)          # the one collective of the path: total energy over all shards
+        call(batch, out)
+        if w.call != "B":
+            tot.copy_(out[0].sum().reshape(1))
+            if world > 1:
+                dist.all_reduce(tot)          # the one collective of the path: total energy over all shards
 
     def barrier():
         if world > 1:
@@ -222,13 +225,14 @@ def main():
         torch.cuda.synchronize()
 
     fp64_peak = measure_fp64_tflops()
+    dmma_peak = measure_dmma_tflops()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
-    stage = {"pool": 0.0, "adjoint": 0.0, "forces": 0.0}
+    stage = {}
     l0 = h.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -237,7 +241,8 @@ def main():
     for _ in range(args.steps):
         step()
         for k, v in h.last_stage_ms().items():
-            stage[k] += v
+            k = "basis" if (w.call == "B" and k == "adjoint") else k      # the second launch of a B call is the fused value kernel
+            stage[k] = stage.get(k, 0.0) + v
     e1.record()
     barrier()
     sampler.mark_end()
@@ -249,111 +254,158 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     value = world * nenv * args.steps / (total_ms * 1e-3)
 
-    # ---- end to end through the C ABI with pinned host buffers
-    Rh = torch.from_numpy(R).pin_memory()
-    offh = torch.from_numpy(off).pin_memory()
-    Eh = torch.empty((nenv, 1, 1), dtype=torch.float64).pin_memory()
-    Gh = torch.empty((nenv * J, 1, 3, 1), dtype=torch.float64).pin_memory()
-    hb = ace.B200Batch(Rh.numpy(), offh.numpy())
+    # ---- sampled parity against the CPU oracle (outside every timed region): the numbers above are only worth
+    # reporting if the kernels computed the right thing at this size
+    parity = None
+    if rank == 0:
+        from ace_jl_b200.descriptor import basis_descriptor
+        from oracle import Oracle
+        ns = min(nenv, 100 if len(basis.pibasis) > 20000 else 400)
+        sel = np.sort(np.random.default_rng(5).choice(nenv, size=ns, replace=False))
+        Rs = np.concatenate([R[off[e]:off[e + 1]] for e in sel])
+        sps = None if sp is None else np.concatenate([sp[off[e]:off[e + 1]] for e in sel])
+        offs = np.arange(ns + 1, dtype=np.int64) * J
+        o = Oracle(basis_descriptor(basis, c))
+        o.set_threads(len(os.sched_getaffinity(0)))
+        rel = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))   # noqa: E731
+        if w.call == "B":
+            errs = {"B": rel(out[0].cpu().numpy()[sel], o.eval_B(Rs, offs, sps))}
+        elif w.call == "E":
+            errs = {"E": rel(out[0].cpu().numpy()[sel], o.energy(Rs, offs, sps))}
+        else:
+            Eo, Go = o.energy_forces(Rs, offs, sps)
+            G = out[1].cpu().numpy().reshape(nenv, J, *out[1].shape[1:])[sel].reshape(ns * J, *out[1].shape[1:])
+            errs = {"E": rel(out[0].cpu().numpy()[sel], Eo), "G": rel(G, Go)}
+        parity = {"ok": all(v < 1e-12 for v in errs.values()), "rel_err_vs_oracle": errs, "sampled_envs": int(ns), "tol": 1e-12}
+
+    # ---- end to end through the C ABI with pinned host buffers (the per-environment call, the reference's call shape)
+    e2e_env = e2e_struct = None
     e2e_steps = max(1, min(args.steps, 10))
-    h.energy_forces(hb, Eh.numpy(), Gh.numpy())
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        h.energy_forces(hb, Eh.numpy(), Gh.numpy())   # returns after the D2H copies have completed
-        _ = float(Eh[0, 0, 0])
-    torch.cuda.synchronize()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_value = world * nenv * e2e_steps / float(dt.item())
-    assert np.array_equal(Eh.numpy(), E.cpu().numpy()), "host-buffer path and device-resident path disagree"
+    if not args.no_e2e:
+        pin = lambda a: None if a is None else torch.from_numpy(a).pin_memory()   # noqa: E731
+        Rh, offh, sph = pin(R), pin(off), pin(sp)
+        outh = [torch.empty(o_.shape, dtype=o_.dtype).pin_memory() for o_ in out]
+        hb = ace.B200Batch(Rh.numpy(), offh.numpy(), None if sph is None else sph.numpy())
+        outn = [o_.numpy() for o_ in outh]
+        call(hb, outn)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            call(hb, outn)                       # returns after the D2H copies have completed
+            _ = outh[0].view(-1)[0].item()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        assert np.array_equal(outn[0], out[0].cpu().numpy()), "host-buffer path and device-resident path disagree"
+        e2e_env = {"value": world * nenv * e2e_steps / float(dt.item()), "unit": UNIT,
+                   "h2d_bytes_per_step": int(R.nbytes + off.nbytes + (0 if sp is None else sp.nbytes)),
+                   "d2h_bytes_per_step": int(sum(o_.numel() * o_.element_size() for o_ in outh)), "steps": e2e_steps,
+                   "call": {"EF": "aceb200_energy_forces", "E": "aceb200_energy", "B": "aceb200_eval_B"}[w.call],
+                   "timer": "host wall clock around the C-ABI calls (they return after the D2H copy)"}
 
     # ---- end to end through the caller-side entry: a whole periodic structure with its neighbour
     # list in pinned host memory -> site energies, atomic forces and the virial back in pinned host memory.  The
     # environments are built and the forces assembled on the device, so the pair gradients never cross PCIe.
-    from ace_jl_b200.structure import B200Structure
-    from ace_jl_b200.utils import fcc_structure
-    ncell = max(2, round((nenv / 4.0) ** (1.0 / 3.0)))
-    sX, scell, sfirst, snbr, simg = fcc_structure(philox(SEED + 99 + rank), ncell)
-    pin = lambda a: torch.from_numpy(a).pin_memory()   # noqa: E731
-    pX, pfirst, pnbr, pimg = pin(sX), pin(sfirst), pin(snbr), pin(simg)
-    st = B200Structure(pX.numpy(), pfirst.numpy(), pnbr.numpy(), pimg.numpy(), scell)
-    sE = torch.empty((st.natoms, 1, 1), dtype=torch.float64).pin_memory()
-    sF = torch.empty((st.natoms, 1, 3, 1), dtype=torch.float64).pin_memory()
-    sW = torch.empty((1, 3, 3), dtype=torch.float64).pin_memory()
-    h.structure_energy_forces(st, True, sE.numpy(), sF.numpy(), sW.numpy())
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        h.structure_energy_forces(st, True, sE.numpy(), sF.numpy(), sW.numpy())   # returns after the D2H copies
-        _ = float(sE[0, 0, 0])
-    torch.cuda.synchronize()
-    dts = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(dts, op=dist.ReduceOp.MAX)
-    struct_value = world * st.natoms * e2e_steps / float(dts.item())
-    struct_h2d = sX.nbytes + sfirst.nbytes + snbr.nbytes + simg.nbytes
-    struct_d2h = sE.numel() * 8 + sF.numel() * 8 + sW.numel() * 8
-    fsum = float(np.abs(sF.numpy().sum(axis=0)).max() / np.abs(sF.numpy()).max())
-    assert fsum < 1e-9, "forces of a periodic structure must sum to zero"
+    if w.call == "EF" and w.nspecies == 0 and ncomp == 1 and not args.no_e2e:
+        from ace_jl_b200.structure import B200Structure
+        from ace_jl_b200.utils import fcc_structure, philox
+        ncell = max(2, round((nenv / 4.0) ** (1.0 / 3.0)))
+        sX, scell, sfirst, snbr, simg = fcc_structure(philox(w.seed + 99 + rank), ncell)
+        pX, pfirst, pnbr, pimg = (torch.from_numpy(a).pin_memory() for a in (sX, sfirst, snbr, simg))
+        st = B200Structure(pX.numpy(), pfirst.numpy(), pnbr.numpy(), pimg.numpy(), scell)
+        sE = torch.empty((st.natoms, w.nprop, 1), dtype=torch.float64).pin_memory()
+        sF = torch.empty((st.natoms, w.nprop, 3, 1), dtype=torch.float64).pin_memory()
+        sW = torch.empty((w.nprop, 3, 3), dtype=torch.float64).pin_memory()
+        h.structure_energy_forces(st, True, sE.numpy(), sF.numpy(), sW.numpy())
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            h.structure_energy_forces(st, True, sE.numpy(), sF.numpy(), sW.numpy())   # returns after the D2H copies
+            _ = float(sE[0, 0, 0])
+        torch.cuda.synchronize()
+        dts = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dts, op=dist.ReduceOp.MAX)
+        fsum = float(np.abs(sF.numpy().sum(axis=0)).max() / np.abs(sF.numpy()).max())
+        assert fsum < 1e-9, "forces of a periodic structure must sum to zero"
+        e2e_struct = {"value": world * st.natoms * e2e_steps / float(dts.item()), "unit": UNIT,
+                      "h2d_bytes_per_step": int(sX.nbytes + sfirst.nbytes + snbr.nbytes + simg.nbytes),
+                      "d2h_bytes_per_step": int(sE.numel() * 8 + sF.numel() * 8 + sW.numel() * 8),
+                      "steps": e2e_steps, "atoms_per_gpu": st.natoms, "pairs_per_gpu": st.npairs,
+                      "call": "aceb200_structure_energy_forces",
+                      "workload": "jittered periodic FCC crystal, 42 neighbours per atom inside rcut, positions + neighbour list "
+                                  "(i, j, S) in pinned host memory -> site energies, atomic forces, virial in pinned host memory "
+                                  "(same model; environments built and forces assembled on the device)",
+                      "timer": "host wall clock around the C-ABI calls (they return after the D2H copy)"}
 
     if rank == 0:
-        flops = algorithmic_flops(basis, J)
-        per_launch_ms = {k: v / args.steps for k, v in stage.items()}
-        dom = max(per_launch_ms, key=per_launch_ms.get)
-        ach = flops[dom] * nenv / (per_launch_ms[dom] * 1e-3) / 1e12
-        tot_flops = sum(flops.values())
-        hbm_bytes = 24 * J + 24 * J + 8 + 8
+        work = algorithmic_work(basis, J, w.call, w.nprop)
+        flops = work["flops"]
+        per_launch_ms = {k: v / args.steps for k, v in stage.items() if v > 0.0}
+        kernel_names = {"pool": "k_pool", "adjoint": "k_adjoint_stream", "forces": "k_forces", "product": "k_basis_stream", "coupling": "k_basis_stream"}
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/), per launch
+        step_ms = total_ms / args.steps
+        hbm_ach = value / world * work["bytes"] / 1e9
+        whole_tflops = work["flops_total"] * nenv / (step_ms * 1e-3) / 1e12
+        stage_flops = dict(flops)
+        if "product" in stage_flops:                # the fused value kernel does products + coupling in one launch
+            stage_flops["basis"] = stage_flops.pop("product") + stage_flops.pop("coupling")
+            kernel_names["basis"] = "k_basis_stream"
+        common = {k: v for k, v in per_launch_ms.items() if k in stage_flops}
+        dom = max(common, key=common.get) if common else None
+        fp64_roof = None
+        if dom:
+            ach = stage_flops[dom] * nenv / (common[dom] * 1e-3) / 1e12
+            fp64_roof = {"bound": "fp64", "kernel": kernel_names.get(dom, dom), "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": ach / fp64_peak if fp64_peak else None}
         traffic = None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            kname = {"pool": "k_pool", "adjoint": "k_adjoint_stream", "forces": "k_forces"}[dom]
-            t = tr[kname]
-            traffic = (t["dram_read_bytes"] + t["dram_write_bytes"]) * nenv / t["envs_per_launch"]
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            tk = tr.get(f"config{w.key}", {}).get(kernel_names.get(dom, ""), None)
+            if tk:
+                traffic = (tk["dram_read_bytes"] + tk["dram_write_bytes"]) * nenv / tk["envs_per_launch"]
         except Exception:
             pass
+        hbm_roof = {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                    "algorithmic_bytes_per_env": work["bytes"], "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"}
+        # which roofline bounds the call: whichever fraction is larger (FP64 for the model calls, output
+        # bandwidth for the vector- / matrix-valued basis)
+        whole_frac = whole_tflops / fp64_peak if fp64_peak else 0.0
+        if hbm_roof["frac"] > whole_frac:
+            roofline = dict(hbm_roof)
+            roofline["fp64"] = fp64_roof
+        else:
+            roofline = dict(fp64_roof or {"bound": "fp64", "achieved": whole_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": whole_frac})
+            roofline["hbm"] = hbm_roof
+        roofline.update({
+            "traffic": traffic,
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/r2_traffic.json",
+            "peak_source": "FP64 FMA probe run in this process (MEASURED_PEAKS.json holds no FP64 figure)",
+            "fp64_dmma_peak_tflops": dmma_peak,
+            "algorithmic_flops_per_env": flops, "ms_per_launch": per_launch_ms,
+            "whole_step_tflops": whole_tflops, "whole_step_frac": whole_frac})
+        primary = e2e_struct or e2e_env
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": workload_config(nenv, world),
-            "roofline": {
-                "bound": "fp64", "kernel": {"pool": "k_pool", "adjoint": "k_adjoint", "forces": "k_forces"}[dom],
-                "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak if fp64_peak else None,
-                "traffic": traffic,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/r1_traffic.json (includes the "
-                                  "[slot][env] workspace the three kernels exchange: 1.2 KB/env each way)",
-                "peak_source": "FP64 FMA probe run in this process (MEASURED_PEAKS.json holds no FP64 figure)",
-                "algorithmic_flops_per_env": flops, "ms_per_launch": per_launch_ms,
-                "whole_step_tflops": tot_flops * nenv / (total_ms / args.steps * 1e-3) / 1e12,
-                "hbm": {"achieved": value / world * hbm_bytes / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": value / world * hbm_bytes / 1e9 / hbm_peak, "algorithmic_bytes_per_env": hbm_bytes,
-                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
-            },
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(R.nbytes + off.nbytes),
-                    "d2h_bytes_per_step": int(Eh.numel() * 8 + Gh.numel() * 8), "steps": e2e_steps,
-                    "timer": "host wall clock around the C-ABI calls (they return after the D2H copy)"},
-            "e2e_structure": {"value": struct_value, "unit": UNIT, "h2d_bytes_per_step": int(struct_h2d), "d2h_bytes_per_step": int(struct_d2h),
-                              "steps": e2e_steps, "atoms_per_gpu": st.natoms, "pairs_per_gpu": st.npairs,
-                              "workload": "aceb200_structure_energy_forces: jittered periodic FCC crystal, 42 neighbours per atom inside "
-                                          "rcut, positions + neighbour list (i, j, S) in pinned host memory -> site energies, atomic "
-                                          "forces, virial in pinned host memory (same model; environments built and forces assembled on "
-                                          "the device)"},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
+            "metric": METRICS[w.call], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(w, nenv, world),
+            "roofline": roofline, "parity": parity, "gpu_launches": int(launches), "clocks": clocks,
         }
+        if primary:
+            line["e2e"] = primary
+        if e2e_struct and e2e_env:
+            line["e2e_per_environment"] = e2e_env
         if not args.no_cpu:
-            rate, cores, dtc = cpu_reference_rate(basis, c, args.cpu_envs)
+            sample = args.cpu_envs or default_cpu_sample(w, basis)
+            rate, cores, dtc = cpu_reference_rate(w, basis, c, sample)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{args.cpu_envs} environments x {J} neighbours, {dtc:.1f} s, restated reference "
+                                    "sample": f"{sample} environments x {J} neighbours, {dtc:.1f} s, restated reference "
                                               "(C + OpenMP over environments, materialised dA like src/evaluator.jl:169)"}
         print(json.dumps(line), flush=True)
     if world > 1:
