@@ -251,6 +251,210 @@ __global__ void __launch_bounds__(kPoolThreads) k_pool(const PoolParams p)
 }
 
 // ------------------------------------------------------------------------------------------------
+// FP64 tensor-core building block: D(8x8) += A(8x4, row-major) * B(4x8, column-major), mma.sync.m8n8k4.f64 (SASS DMMA).
+// Fragments: lane i holds A[i / 4][i % 4], B[i % 4][i / 4] and C[i / 4][2 (i % 4) + {0, 1}].
+// One operand pair (two 8-byte shared-memory loads per lane) feeds 256 FMAs of the warp, against 8 FMAs for the four
+// loads of the register-blocked FMA formulation: the pooling / force contractions stop being shared-memory bound.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
+{
+#ifdef ACEB200_EMU
+    emu::mma_m8n8k4(c0, c1, a, b);
+#else
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_pool_mma: the pooling  A_{n, lm} = sum_j R_n(r_j) Y_lm(r_j)  of one environment as a small dense product
+//     [n] x [j] . [j] x [(lm, re / im)]
+// on the FP64 tensor cores.  Phase a is k_pool's (one thread per neighbour: R_n and Y_l^m, m >= 0, into shared-memory
+// planes); phase b hands (environment, column tile) units to the four warps.  A column tile is four (l, m) columns
+// = eight real columns of the B operand; the radial index runs over up to NT row tiles of eight, of which only those
+// below the tile's longest column are computed (columns are sorted by length, so the staircase (n, l) pattern of a
+// level-truncated one-particle basis wastes as little as an 8 x 8 tiling allows).  Each lane ends up with the complex
+// A value of (n = 8 nt + lane / 4, column = lane % 4) -- exactly one canonical slot -- and stores it.
+// The plane pitch is 4 mod 16 doubles: the A and B fragment loads (lane -> row lane / 4 | lane % 4 apart by one
+// pitch) then touch every bank exactly twice, the minimum for 32 eight-byte loads.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPoolMmaThreads = 256;     // k_pool_mma: 128 staged neighbours per sub-tile, two threads each in phase a, eight warps in phase b
+constexpr int kMmaPitch = 132;           // doubles per staged plane: >= 128 + 3 (tail reads), = 4 mod 16
+struct PoolTile { int ip[4], base[4], cnt[4], nnt, pad[3]; };   // four columns: harmonic index, first slot, length; row tiles
+
+struct PoolMmaParams {
+    RadialParams rp;
+    AlpParams ap;
+    BatchDev B;
+    c2* Ac; long long ldA;
+    int* errflag;
+    int TE, nP;
+    const PoolTile* tiles; int ntiles;
+};
+
+// acc[nt] += R-tile(nt)[8 x nr] . Y-tile[nr x 8] over the nr staged rows of one environment, NNT row tiles
+template <int NNT, int NT>
+__device__ __forceinline__ void pool_unit(const double* pa, const double* pb, const int (&rowA)[NT], int nr, int k4, double (&acc)[NT][2])
+{
+    const double* qa[NNT];
+#pragma unroll
+    for (int nt = 0; nt < NNT; ++nt) qa[nt] = pa + rowA[nt];
+    double alt[NNT][2];                                 // second accumulator set: two independent DMMA chains per row tile
+#pragma unroll
+    for (int nt = 0; nt < NNT; ++nt) { alt[nt][0] = 0.0; alt[nt][1] = 0.0; }
+    int k = 0;
+#pragma unroll 1
+    for (; k + 8 <= nr; k += 8) {
+        const double b0 = pb[0], b1 = pb[4];
+        double a0[NNT], a1[NNT];
+#pragma unroll
+        for (int nt = 0; nt < NNT; ++nt) { a0[nt] = qa[nt][0]; a1[nt] = qa[nt][4]; }
+#pragma unroll
+        for (int nt = 0; nt < NNT; ++nt) dmma(acc[nt][0], acc[nt][1], a0[nt], b0);
+#pragma unroll
+        for (int nt = 0; nt < NNT; ++nt) dmma(alt[nt][0], alt[nt][1], a1[nt], b1);
+        pb += 8;
+#pragma unroll
+        for (int nt = 0; nt < NNT; ++nt) qa[nt] += 8;
+    }
+#pragma unroll
+    for (int nt = 0; nt < NNT; ++nt) { acc[nt][0] += alt[nt][0]; acc[nt][1] += alt[nt][1]; }
+    if (k + 4 <= nr) {
+        const double b0 = pb[0];
+#pragma unroll
+        for (int nt = 0; nt < NNT; ++nt) dmma(acc[nt][0], acc[nt][1], qa[nt][0], b0);
+        pb += 4; k += 4;
+#pragma unroll
+        for (int nt = 0; nt < NNT; ++nt) qa[nt] += 4;
+    }
+    if (k < nr) {                                       // last, partial k-step: rows beyond the environment count as zero
+        const bool ok = k + k4 < nr;
+        const double b0 = ok ? pb[0] : 0.0;
+#pragma unroll
+        for (int nt = 0; nt < NNT; ++nt) dmma(acc[nt][0], acc[nt][1], ok ? qa[nt][0] : 0.0, b0);
+    }
+}
+
+template <int NMAX, int WALK>
+__global__ void __launch_bounds__(kPoolMmaThreads) k_pool_mma(const PoolMmaParams p)
+{
+    constexpr int NT = (NMAX + 7) / 8;
+    constexpr int P = kMmaPitch;
+    ACE_DYN_SMEM(double, smem);
+    const int N = p.rp.N, nP = p.nP, ntiles = p.ntiles;
+    double* SYr = smem;                                        // [nP][P]
+    double* SYi = SYr + (size_t)nP * P;                        // [nP][P]
+    double* SR = SYi + (size_t)nP * P;                         // [N][P]
+    PoolTile* tl = reinterpret_cast<PoolTile*>(SR + (size_t)N * P);   // [ntiles]
+    int* joff = reinterpret_cast<int*>(tl + ntiles);           // [TE + 1]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long e0 = (long long)blockIdx.x * p.TE;
+    if (e0 >= p.B.nenv) return;
+    const int ne = (int)((p.B.nenv - e0) < p.TE ? (p.B.nenv - e0) : p.TE);
+    const long long jbeg = p.B.off[e0];
+    if (tid <= ne) joff[tid] = (int)(p.B.off[e0 + tid] - jbeg);
+    for (int i = tid; i < ntiles * (int)(sizeof(PoolTile) / sizeof(int)); i += kPoolMmaThreads)
+        reinterpret_cast<int*>(tl)[i] = __ldg(reinterpret_cast<const int*>(p.tiles) + i);
+    const double* Rb = p.B.R + 3 * (jbeg - p.B.jbase);
+    const int k4 = lane & 3, g = lane >> 2;
+    int rowA[NT];                                         // plane offset of this lane's A-fragment row in each row tile
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) { const int n = nt * 8 + g; rowA[nt] = (n < N ? n : N - 1) * P; }   // rows >= N: finite, never stored
+    __syncthreads();
+
+    int e = 0, j0 = 0;
+    while (e < ne) {
+        // ---- the sub-tile [j0, j1): whole environments e..e2-1, or a 128-neighbour piece of environment e
+        const int jend_e = joff[e + 1];
+        int e2 = e + 1, j1;
+        bool done_e, first_piece = true;
+        if (j0 == joff[e] && jend_e - j0 <= kPoolThreads) {
+            while (e2 < ne && joff[e2 + 1] - j0 <= kPoolThreads) ++e2;
+            j1 = joff[e2];
+            done_e = true;
+        } else {
+            first_piece = (j0 == joff[e]);
+            j1 = (j0 + kPoolThreads < jend_e) ? j0 + kPoolThreads : jend_e;
+            done_e = (j1 == jend_e);
+        }
+        const int nrows = j1 - j0;
+
+        // ---- phase a: two threads per neighbour (threads 0..127: R_n, threads 128..255: Y_l^m of neighbour tid % 128)
+        {
+            const int rowa = tid & (kPoolThreads - 1);
+            if (rowa < nrows) {
+                const int j = j0 + rowa;
+                const double x = Rb[3 * j], y = Rb[3 * j + 1], z = Rb[3 * j + 2];
+                if (tid < kPoolThreads) {
+                    const double r2 = x * x + y * y + z * z;
+#ifdef __CUDA_ARCH__
+                    const double r = r2 * rsqrt(r2);
+#else
+                    const double r = r2 * (1.0 / sqrt(r2));
+#endif
+                    double Rn[NMAX];
+                    radial_e<NMAX>(p.rp, r, Rn);
+#pragma unroll
+                    for (int n = 0; n < NMAX; ++n) if (n < N) SR[n * P + rowa] = Rn[n];
+                } else {
+                    const Spher sp = cart2spher(x, y, z);
+                    for_each_lm<WALK>(p.ap, sp, [&](int l, int m, double Pv, double epr, double epi) {
+                        SYr[index_p(l, m) * P + rowa] = epr * Pv;
+                        SYi[index_p(l, m) * P + rowa] = epi * Pv;
+                    });
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase b: (environment, column tile) units, heaviest tiles first, dealt round-robin to the warps.
+        // The k-loop is the hot spot and is issue-bound: operands come through per-operand running pointers with
+        // immediate offsets (two k-steps per trip) and the number of row tiles is a compile-time constant per branch,
+        // so that a trip is 2 (1 + NNT) LDS.64 + 2 NNT DMMA + a handful of integer instructions.
+        const int nes = e2 - e;
+        {
+            int t = 0, el = warp;                          // unit u = t * nes + el, u = warp, warp + 4, ...
+            while (el >= nes) { el -= nes; ++t; }
+            while (t < ntiles) {
+                const PoolTile& T = tl[t];
+                int ra = joff[e + el] - j0, rb = joff[e + el + 1] - j0;
+                if (ra == rb && t == 0 && lane == 0) atomicMax(p.errflag, 5);      // EEMPTY (src/product_1pbasis.jl:124)
+                if (ra < 0) ra = 0;
+                if (rb > nrows) rb = nrows;
+                const int nr = rb - ra, nnt = T.nnt;
+                const double* pb = ((g & 1) ? SYi : SYr) + T.ip[g >> 1] * P + ra + k4;
+                const double* pa = SR + ra + k4;
+                double acc[NT][2];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = 0.0; acc[nt][1] = 0.0; }
+                switch (nnt) {
+                case 1: pool_unit<1, NT>(pa, pb, rowA, nr, k4, acc); break;
+                case 2: if (NT >= 2) pool_unit<(NT >= 2 ? 2 : 1), NT>(pa, pb, rowA, nr, k4, acc); break;
+                case 3: if (NT >= 3) pool_unit<(NT >= 3 ? 3 : 1), NT>(pa, pb, rowA, nr, k4, acc); break;
+                case 4: if (NT >= 4) pool_unit<(NT >= 4 ? 4 : 1), NT>(pa, pb, rowA, nr, k4, acc); break;
+                default: break;
+                }
+                const int cnt = T.cnt[k4];
+                c2* out = p.Ac + (size_t)(T.base[k4] + g) * p.ldA + (e0 + e + el);
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    if (nt < nnt && nt * 8 + g < cnt) {
+                        c2* o = out + (size_t)(nt * 8) * p.ldA;
+                        c2 v = c2{acc[nt][0], acc[nt][1]};
+                        if (!first_piece) { const c2 w = *o; v.x += w.x; v.y += w.y; }   // a later piece of a > 128-neighbour environment
+                        *o = v;
+                    }
+                }
+                el += kPoolMmaThreads / 32;
+                while (el >= nes) { el -= nes; ++t; }
+            }
+        }
+        __syncthreads();
+        j0 = j1;
+        if (done_e) e = e2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_adjoint: per environment  E = sum_AA c~ prod A   and   D~_slot = dE/dA folded onto m >= 0
 // ------------------------------------------------------------------------------------------------
 struct AdjointParams {
@@ -937,6 +1141,267 @@ __global__ void __launch_bounds__(kForceThreads, ACE_FORCE_MINB) k_forces(const 
                 g[0] = gx; g[p.ncomp] = gy; g[2 * p.ncomp] = gz;
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_forces_mma: the force contraction on the FP64 tensor cores (single output channel, single species)
+// ------------------------------------------------------------------------------------------------
+//   u_{lm}(j) = sum_n D~_{n,lm} R_n(r_j),   v_{lm}(j) = sum_n D~_{n,lm} R_n'(r_j)
+// is, per environment, the product  [j] x [n] . [n] x [(lm, re / im)]  (twice: R and R').  With eight neighbours as the
+// rows of an m8n8k4 tile, four radial indices per k-step and four (l, m) columns as its eight real columns, every lane
+// ends up holding the complex u and v of ONE (neighbour, column) pair.  The harmonics that u and v are contracted with
+//     S0 += f0 Re(v ep),  S1 += m Pt Im(u ep),  S2 += dP Re(u ep)          (f0 = |Y| factor, ep = e^{i m phi} / sqrt 2)
+// are staged by phase a in shared-memory planes [function][row] and read back in the fragment layout (lane -> row
+// lane / 4, column lane % 4: conflict-free at a pitch of 4 mod 16); the three scalars are then summed over the four
+// lanes of a quad and over the column tiles, and lanes 0..2 of each quad write one Cartesian component
+//     g = rhat S0 + (1 / r) [ sphi S1 + cphi cth S2,  -cphi S1 + sphi cth S2,  -sth S2 ].
+// Phase a is one thread per neighbour as in k_forces (R_n, R_n' by the recurrence, the harmonics walk with the
+// pole-stable derivative), but it only produces operands -- no dot products, no column switch.
+constexpr int kFmmaEnvs = 8;             // environments staged per sub-tile (their D~)
+constexpr int kFmmaRows = 128;           // neighbours per sub-tile
+constexpr int kFmmaThreads = 256;        // phase a: threads 0..127 radial part, 128..255 angular part of neighbour tid % 128;
+                                         // phase b: eight warps
+struct ForceTile { int offF[4], offE[4], base[4], cnt[4], ks, pad[3]; };   // four columns: double offsets of the column's harmonic
+                                                                           // planes (F: [ip][3][P], E: [m][2][P]), first slot, length;
+                                                                           // ks = k-steps (of four radial indices)
+
+struct ForceMmaParams {
+    RadialParams rp;
+    AlpParams ap;
+    BatchDev B;
+    const c2* Dt; long long ldA;
+    int nS, dpitch, TE, nP;
+    const ForceTile* tiles; int ntiles;
+    double* G;               // [neighbour][3], chunk-relative
+};
+
+// R_n and dR_n/dr straight into shared-memory planes (two rolling registers each)
+template <int NMAX>
+__device__ __forceinline__ void radial_ed_planes(const RadialParams& rp, double r, double* sR, double* sD, int stride)
+{
+    double t, dt, f, df;
+    transform_ed(rp, r, t, dt);
+    envelope_ed(rp, t, f, df);
+    double r2 = rp.A[0] * f, d2 = rp.A[0] * df, r1 = 0.0, d1 = 0.0;
+    sR[0] = r2; sD[0] = d2 * dt;
+    if (NMAX > 1 && rp.N > 1) {
+        const double al = rp.A[1] * t + rp.B[1];
+        r1 = al * r2;
+        d1 = al * d2 + rp.A[1] * r2;
+        sR[stride] = r1; sD[stride] = d1 * dt;
+    }
+#pragma unroll
+    for (int n = 2; n < NMAX; ++n) {
+        if (n < rp.N) {
+            const double al = rp.A[n] * t + rp.B[n];
+            const double rn = al * r1 + rp.C[n] * r2;
+            const double dn = al * d1 + rp.C[n] * d2 + rp.A[n] * r1;
+            r2 = r1; r1 = rn; d2 = d1; d1 = dn;
+            sR[n * stride] = rn; sD[n * stride] = dn * dt;
+        }
+    }
+}
+
+// u, v of one column tile for JT row tiles: KS k-steps of four radial indices (compile-time, so the chain is straight-line)
+template <int KS, int JT, int NT4>
+__device__ __forceinline__ void force_tile_mma(const double* dB, int cntB, int k4, const double (&aR)[JT][NT4], const double (&aD)[JT][NT4],
+                                               double (&ur)[JT], double (&ui)[JT], double (&vr)[JT], double (&vi)[JT])
+{
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk) {
+        const int n = kk * 4 + k4;
+        const double b = n < cntB ? dB[2 * n] : 0.0;
+#pragma unroll
+        for (int s = 0; s < JT; ++s) {
+            dmma(ur[s], ui[s], aR[s][kk], b);
+            dmma(vr[s], vi[s], aD[s][kk], b);
+        }
+    }
+}
+
+// One unit: JT row tiles (eight neighbours each) of one environment against every column tile.
+template <int JT, int NT4>
+__device__ __forceinline__ void force_unit(const ForceTile* tl, int ntiles, const c2* De, const double* SR, const double* SD, const double* SF,
+                                           const double* SE, const double* SGm, int N, int r0, int rb, int nrows, int k4, int g, double* Gout)
+{
+    constexpr int P = kMmaPitch;
+    int row[JT];
+#pragma unroll
+    for (int s = 0; s < JT; ++s) { const int r = r0 + s * 8 + g; row[s] = r < nrows ? r : nrows - 1; }
+    // A fragments (rows = neighbours, k = radial index): R and R'
+    double aR[JT][NT4], aD[JT][NT4];
+#pragma unroll
+    for (int kk = 0; kk < NT4; ++kk) {
+        const int n = kk * 4 + k4, nc = n < N ? n : N - 1;     // n >= N meets a zero of D~: any finite value will do
+#pragma unroll
+        for (int s = 0; s < JT; ++s) { aR[s][kk] = SR[nc * P + row[s]]; aD[s][kk] = SD[nc * P + row[s]]; }
+    }
+    double S0[JT], S1[JT], S2[JT];
+#pragma unroll
+    for (int s = 0; s < JT; ++s) { S0[s] = 0.0; S1[s] = 0.0; S2[s] = 0.0; }
+    const int colB = g >> 1, part = g & 1;
+#pragma unroll 1
+    for (int t = 0; t < ntiles; ++t) {
+        const ForceTile& T = tl[t];
+        const int cntB = T.cnt[colB];
+        const double* dB = reinterpret_cast<const double*>(De + T.base[colB]) + part;
+        double ur[JT], ui[JT], vr[JT], vi[JT];
+#pragma unroll
+        for (int s = 0; s < JT; ++s) { ur[s] = 0.0; ui[s] = 0.0; vr[s] = 0.0; vi[s] = 0.0; }
+        switch (T.ks) {
+        case 1: force_tile_mma<1, JT, NT4>(dB, cntB, k4, aR, aD, ur, ui, vr, vi); break;
+        case 2: force_tile_mma<(NT4 >= 2 ? 2 : 1), JT, NT4>(dB, cntB, k4, aR, aD, ur, ui, vr, vi); break;
+        case 3: force_tile_mma<(NT4 >= 3 ? 3 : 1), JT, NT4>(dB, cntB, k4, aR, aD, ur, ui, vr, vi); break;
+        case 4: force_tile_mma<(NT4 >= 4 ? 4 : 1), JT, NT4>(dB, cntB, k4, aR, aD, ur, ui, vr, vi); break;
+        case 5: force_tile_mma<(NT4 >= 5 ? 5 : 1), JT, NT4>(dB, cntB, k4, aR, aD, ur, ui, vr, vi); break;
+        case 6: force_tile_mma<(NT4 >= 6 ? 6 : 1), JT, NT4>(dB, cntB, k4, aR, aD, ur, ui, vr, vi); break;
+        case 7: force_tile_mma<(NT4 >= 7 ? 7 : 1), JT, NT4>(dB, cntB, k4, aR, aD, ur, ui, vr, vi); break;
+        default: force_tile_mma<NT4, JT, NT4>(dB, cntB, k4, aR, aD, ur, ui, vr, vi); break;
+        }
+        // this lane now holds u, v of (neighbour row[s], column k4 of the tile)
+        const double* pF = SF + T.offF[k4];
+        const double* pE = SE + T.offE[k4];
+#pragma unroll
+        for (int s = 0; s < JT; ++s) {
+            const double er = pE[row[s]], ei = pE[P + row[s]];
+            const double f0 = pF[row[s]], f1 = pF[P + row[s]], f2 = pF[2 * P + row[s]];
+            const double ve = vr[s] * er - vi[s] * ei;
+            const double zr = ur[s] * er - ui[s] * ei;
+            const double zi = ur[s] * ei + ui[s] * er;
+            S0[s] += f0 * ve; S1[s] += f1 * zi; S2[s] += f2 * zr;
+        }
+    }
+    // sum over the four columns of the quad, then lanes 0..2 of the quad write x, y, z
+#pragma unroll
+    for (int s = 0; s < JT; ++s) {
+#ifdef ACEB200_EMU
+        S0[s] += emu::shfl_xor(S0[s], 1); S1[s] += emu::shfl_xor(S1[s], 1); S2[s] += emu::shfl_xor(S2[s], 1);
+        S0[s] += emu::shfl_xor(S0[s], 2); S1[s] += emu::shfl_xor(S1[s], 2); S2[s] += emu::shfl_xor(S2[s], 2);
+#else
+        S0[s] += __shfl_xor_sync(0xffffffffu, S0[s], 1); S1[s] += __shfl_xor_sync(0xffffffffu, S1[s], 1); S2[s] += __shfl_xor_sync(0xffffffffu, S2[s], 1);
+        S0[s] += __shfl_xor_sync(0xffffffffu, S0[s], 2); S1[s] += __shfl_xor_sync(0xffffffffu, S1[s], 2); S2[s] += __shfl_xor_sync(0xffffffffu, S2[s], 2);
+#endif
+        const int r = r0 + s * 8 + g;
+        if (k4 < 3 && r < rb) {
+            const double* gm = SGm + (3 * k4) * P + r;
+            Gout[(size_t)r * 3 + k4] = gm[0] * S0[s] + gm[P] * S1[s] + gm[2 * P] * S2[s];
+        }
+    }
+}
+
+template <int NMAX, int WALK>
+__global__ void __launch_bounds__(kFmmaThreads) k_forces_mma(const ForceMmaParams p)
+{
+    constexpr int P = kMmaPitch;
+    constexpr int NT4 = (NMAX + 3) / 4;             // k-steps covering every radial index
+    constexpr int NW = kFmmaThreads / 32;
+    ACE_DYN_SMEM(double, smem);
+    const int N = p.rp.N, nP = p.nP, ntiles = p.ntiles, L = p.ap.L;
+    double* SR = smem;                                  // [N][P]        R_n
+    double* SD = SR + (size_t)N * P;                    // [N][P]        dR_n/dr
+    double* SF = SD + (size_t)N * P;                    // [nP][3][P]    Pt sin(th) (m > 0) | P_l^0;  m Pt;  dP/dtheta
+    double* SE = SF + (size_t)3 * nP * P;               // [L + 1][2][P] Re, Im of e^{i m phi} / sqrt 2
+    double* SGm = SE + (size_t)2 * (L + 1) * P;         // [9][P]        Cartesian assembly coefficients
+    c2* Ds = reinterpret_cast<c2*>(SGm + 9 * P);        // [kFmmaEnvs][dpitch]
+    ForceTile* tl = reinterpret_cast<ForceTile*>(Ds + (size_t)kFmmaEnvs * p.dpitch);   // [ntiles]
+    int* joff = reinterpret_cast<int*>(tl + ntiles);    // [TE + 1]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long e0 = (long long)blockIdx.x * p.TE;
+    if (e0 >= p.B.nenv) return;
+    const int ne = (int)((p.B.nenv - e0) < p.TE ? (p.B.nenv - e0) : p.TE);
+    const long long jbeg = p.B.off[e0];
+    if (tid <= ne) joff[tid] = (int)(p.B.off[e0 + tid] - jbeg);
+    for (int i = tid; i < ntiles * (int)(sizeof(ForceTile) / sizeof(int)); i += kFmmaThreads)
+        reinterpret_cast<int*>(tl)[i] = __ldg(reinterpret_cast<const int*>(p.tiles) + i);
+    const double* Rb = p.B.R + 3 * (jbeg - p.B.jbase);
+    double* Gb = p.G + (size_t)(jbeg - p.B.off[0]) * 3;
+    const int k4 = lane & 3, g = lane >> 2;
+    __syncthreads();
+
+    int e = 0, j0 = 0;
+    while (e < ne) {
+        const int jend_e = joff[e + 1];
+        int e2 = e + 1, j1;
+        bool done_e;
+        if (j0 == joff[e] && jend_e - j0 <= kFmmaRows) {
+            while (e2 < ne && e2 - e < kFmmaEnvs && joff[e2 + 1] - j0 <= kFmmaRows) ++e2;
+            j1 = joff[e2];
+            done_e = true;
+        } else {
+            j1 = (j0 + kFmmaRows < jend_e) ? j0 + kFmmaRows : jend_e;
+            done_e = (j1 == jend_e);
+        }
+        const int nrows = j1 - j0, nes = e2 - e;
+
+        // ---- stage D~ of the sub-tile's environments: Ds[el][slot]
+        for (int idx = tid; idx < p.nS * nes; idx += kFmmaThreads) {
+            const int el = idx % nes, s = idx / nes;
+            Ds[el * p.dpitch + s] = p.Dt[(size_t)s * p.ldA + e0 + e + el];
+        }
+        // ---- phase a: two threads per neighbour -> operand planes
+        {
+            const int rowa = tid & (kFmmaRows - 1);
+            if (rowa < nrows) {
+                const int j = j0 + rowa;
+                const double x = Rb[3 * j], y = Rb[3 * j + 1], z = Rb[3 * j + 2];
+                if (tid < kFmmaRows) {            // radial part
+                    const double r2 = x * x + y * y + z * z;
+#ifdef __CUDA_ARCH__
+                    const double r = r2 * rsqrt(r2);
+#else
+                    const double r = r2 * (1.0 / sqrt(r2));
+#endif
+                    radial_ed_planes<NMAX>(p.rp, r, SR + rowa, SD + rowa, P);
+                } else {                          // angular part + Cartesian assembly coefficients
+                    const Spher sp = cart2spher(x, y, z);
+                    double* gm = SGm + rowa;
+                    gm[0 * P] = sp.sth * sp.cphi; gm[1 * P] = sp.rinv * sp.sphi;  gm[2 * P] = sp.rinv * sp.cphi * sp.cth;
+                    gm[3 * P] = sp.sth * sp.sphi; gm[4 * P] = -sp.rinv * sp.cphi; gm[5 * P] = sp.rinv * sp.sphi * sp.cth;
+                    gm[6 * P] = sp.cth;           gm[7 * P] = 0.0;                gm[8 * P] = -sp.rinv * sp.sth;
+                    double* sf = SF + rowa;
+                    double* se = SE + rowa;
+                    for_each_lm_ed<WALK>(p.ap, sp, [&](int l, int m, double Pt, double dP, double epr, double epi) {
+                        const int ip = index_p(l, m);
+                        sf[(3 * ip) * P] = (m == 0) ? Pt : Pt * sp.sth;
+                        sf[(3 * ip + 1) * P] = (double)m * Pt;
+                        sf[(3 * ip + 2) * P] = dP;
+                        if (l == m) { se[(2 * m) * P] = epr; se[(2 * m + 1) * P] = epi; }
+                    });
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase b: units of up to two row tiles (8 neighbours each) of one environment, dealt in contiguous runs to the warps
+        int nunits = 0;
+        for (int el = 0; el < nes; ++el) {
+            int ra = joff[e + el] - j0, rb = joff[e + el + 1] - j0;
+            if (ra < 0) ra = 0;
+            if (rb > nrows) rb = nrows;
+            nunits += (rb - ra + 15) >> 4;
+        }
+        const int per = (nunits + NW - 1) / NW;
+        const int u0 = warp * per, u1 = (u0 + per < nunits) ? u0 + per : nunits;
+        int el = 0, ubase = 0;                 // environment of the current unit and the index of its first unit
+        for (int u = u0; u < u1; ++u) {
+            int ra, rb;
+            for (;;) {
+                ra = joff[e + el] - j0; rb = joff[e + el + 1] - j0;
+                if (ra < 0) ra = 0;
+                if (rb > nrows) rb = nrows;
+                const int nu_e = (rb - ra + 15) >> 4;
+                if (u < ubase + nu_e) break;
+                ubase += nu_e; ++el;
+            }
+            const int r0 = ra + (u - ubase) * 16;          // first staged row of this unit
+            const c2* De = Ds + el * p.dpitch;
+            if (r0 + 8 < rb) force_unit<2, NT4>(tl, ntiles, De, SR, SD, SF, SE, SGm, N, r0, rb, nrows, k4, g, Gb + (size_t)j0 * 3);
+            else force_unit<1, NT4>(tl, ntiles, De, SR, SD, SF, SE, SGm, N, r0, rb, nrows, k4, g, Gb + (size_t)j0 * 3);
+        }
+        __syncthreads();
+        j0 = j1;
+        if (done_e) e = e2;
     }
 }
 

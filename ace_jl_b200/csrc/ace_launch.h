@@ -22,7 +22,9 @@ namespace aceb200 {
 
 #define ACE_INST_DECL(N)                                                                                                    \
     void forces_inst_##N(int pb, bool species, bool staticL, const ForceParams& p, unsigned grid, size_t smem, cudaStream_t st); \
-    void pool_inst_##N(bool species, bool staticL, const PoolParams& p, unsigned grid, size_t smem, cudaStream_t st);
+    void pool_inst_##N(bool species, bool staticL, const PoolParams& p, unsigned grid, size_t smem, cudaStream_t st);               \
+    void pool_mma_inst_##N(bool staticL, const PoolMmaParams& p, unsigned grid, size_t smem, cudaStream_t st);                     \
+    void forces_mma_inst_##N(bool staticL, const ForceMmaParams& p, unsigned grid, size_t smem, cudaStream_t st);
 ACE_INST_DECL(4) ACE_INST_DECL(8) ACE_INST_DECL(12) ACE_INST_DECL(16) ACE_INST_DECL(20) ACE_INST_DECL(24) ACE_INST_DECL(32)
 #undef ACE_INST_DECL
 
@@ -60,6 +62,32 @@ inline void launch_pool_inst(int nmax, bool species, bool staticL, const PoolPar
     case 20: pool_inst_20(species, staticL, p, grid, smem, st); break;
     case 24: pool_inst_24(species, staticL, p, grid, smem, st); break;
     default: pool_inst_32(species, staticL, p, grid, smem, st); break;
+    }
+}
+
+inline void launch_forces_mma_inst(int nmax, bool staticL, const ForceMmaParams& p, unsigned grid, size_t smem, cudaStream_t st)
+{
+    switch (nmax) {
+    case 4: forces_mma_inst_4(staticL, p, grid, smem, st); break;
+    case 8: forces_mma_inst_8(staticL, p, grid, smem, st); break;
+    case 12: forces_mma_inst_12(staticL, p, grid, smem, st); break;
+    case 16: forces_mma_inst_16(staticL, p, grid, smem, st); break;
+    case 20: forces_mma_inst_20(staticL, p, grid, smem, st); break;
+    case 24: forces_mma_inst_24(staticL, p, grid, smem, st); break;
+    default: forces_mma_inst_32(staticL, p, grid, smem, st); break;
+    }
+}
+
+inline void launch_pool_mma_inst(int nmax, bool staticL, const PoolMmaParams& p, unsigned grid, size_t smem, cudaStream_t st)
+{
+    switch (nmax) {
+    case 4: pool_mma_inst_4(staticL, p, grid, smem, st); break;
+    case 8: pool_mma_inst_8(staticL, p, grid, smem, st); break;
+    case 12: pool_mma_inst_12(staticL, p, grid, smem, st); break;
+    case 16: pool_mma_inst_16(staticL, p, grid, smem, st); break;
+    case 20: pool_mma_inst_20(staticL, p, grid, smem, st); break;
+    case 24: pool_mma_inst_24(staticL, p, grid, smem, st); break;
+    default: pool_mma_inst_32(staticL, p, grid, smem, st); break;
     }
 }
 

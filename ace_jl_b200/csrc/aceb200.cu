@@ -101,6 +101,9 @@ struct aceb200_model {
     const int *d_slot_pos = nullptr, *d_slot_neg = nullptr, *d_code = nullptr;
     const int4* d_pool_blk = nullptr;
     int n_pool_blk = 0;
+    const PoolTile* d_pool_tiles = nullptr;    // k_pool_mma column tiles (single-species models)
+    int n_pool_tiles = 0;
+    const ForceTile* d_force_tiles = nullptr;  // k_forces_mma column tiles (same column order)
     const int *d_orders = nullptr, *d_spec = nullptr;
     const int *d_csr_ptr = nullptr, *d_csr_col = nullptr;
     const c2* d_csr_val = nullptr;
@@ -605,6 +608,42 @@ static void upload_tables(aceb200_model* m)
         m->n_pool_blk = (int)blk.size();
         m->d_pool_blk = upload(m->pool, blk);
     }
+    if (T.nQ == 1) {
+        // column tiles for k_pool_mma: columns sorted by length (longest first), four to a tile
+        std::vector<const Column*> cs;
+        for (const Column& c : T.cols) cs.push_back(&c);
+        std::stable_sort(cs.begin(), cs.end(), [](const Column* a, const Column* b) { return a->cnt > b->cnt; });
+        std::vector<PoolTile> tiles;
+        for (size_t i = 0; i < cs.size(); i += 4) {
+            PoolTile t;
+            memset(&t, 0, sizeof(t));
+            int longest = 0;
+            for (int k = 0; k < 4; ++k) {
+                const Column* c = i + k < cs.size() ? cs[i + k] : nullptr;
+                t.ip[k] = c ? c->ip : 0; t.base[k] = c ? c->base : 0; t.cnt[k] = c ? c->cnt : 0;   // a missing column stores nothing
+                longest = std::max(longest, t.cnt[k]);
+            }
+            t.nnt = (longest + 7) / 8;
+            tiles.push_back(t);
+        }
+        m->n_pool_tiles = (int)tiles.size();
+        m->d_pool_tiles = upload(m->pool, tiles);
+        std::vector<ForceTile> ftiles;
+        for (size_t i = 0; i < cs.size(); i += 4) {
+            ForceTile t;
+            memset(&t, 0, sizeof(t));
+            int longest = 0;
+            for (int k = 0; k < 4; ++k) {
+                const Column* c = i + k < cs.size() ? cs[i + k] : nullptr;
+                t.offF[k] = (c ? c->ip : 0) * 3 * kMmaPitch; t.offE[k] = (c ? c->m : 0) * 2 * kMmaPitch;
+                t.base[k] = c ? c->base : 0; t.cnt[k] = c ? c->cnt : 0;
+                longest = std::max(longest, t.cnt[k]);
+            }
+            t.ks = (longest + 3) / 4;
+            ftiles.push_back(t);
+        }
+        m->d_force_tiles = upload(m->pool, ftiles);
+    }
     m->d_slot_pos = upload(m->pool, T.slot_pos);
     m->d_slot_neg = upload(m->pool, T.slot_neg);
     m->d_code = upload(m->pool, T.iA_code);
@@ -721,9 +760,36 @@ static BatchDev batch_dev(const Staged& s, const Chunk& c)
 // ----------------------------------------------------------------------------------------------
 // kernel launch helpers
 // ----------------------------------------------------------------------------------------------
+// pooling on the FP64 tensor cores (single-species models; ACEB200_POOL_MMA=0 selects the FMA kernel for comparisons)
+static bool launch_pool_mma(aceb200_model* m, const BatchDev& B, long long nJ, long long ldA)
+{
+    HostTables& T = m->T;
+    static const bool off = getenv("ACEB200_POOL_MMA") && atoi(getenv("ACEB200_POOL_MMA")) == 0;
+    if (off || T.nQ != 1 || B.species || m->n_pool_tiles == 0) return false;
+    PoolMmaParams p;
+    p.rp = m->rp; p.ap = m->ap; p.B = B;
+    p.Ac = m->cur->ws_Ac.as<c2>(); p.ldA = ldA; p.errflag = m->ws_err.as<int>();
+    p.tiles = m->d_pool_tiles; p.ntiles = m->n_pool_tiles;
+    p.nP = (T.Lused + 1) * (T.Lused + 2) / 2;
+    // environments per CTA: a multiple of the whole environments one 128-row sub-tile holds, so that the last
+    // sub-tile of a CTA is as full as the others
+    const double Jbar = std::max(1.0, (double)nJ / (double)std::max<long long>(1, B.nenv));
+    int k = std::max(1, (int)(kPoolThreads / Jbar));
+    p.TE = k >= 8 ? std::min(k, kPoolTEmax) : k * ((8 + k - 1) / k);
+    if (p.TE > kPoolTEmax) p.TE = (kPoolTEmax / k) * k;
+    const size_t smem = (size_t)kMmaPitch * (2 * p.nP + m->rp.N) * sizeof(double) + (size_t)p.ntiles * sizeof(PoolTile)
+                      + (kPoolTEmax + 1) * sizeof(int);
+    if (smem > (size_t)m->smem_optin) return false;
+    launch_pool_mma_inst(m->NMAX, p.ap.L <= kStaticL, p, (unsigned)((B.nenv + p.TE - 1) / p.TE), smem, m->cur->stream);
+    CU(cudaGetLastError());
+    m->launches++;
+    return true;
+}
+
 static void launch_pool(aceb200_model* m, const BatchDev& B, long long nJ, long long ldA)
 {
     HostTables& T = m->T;
+    if (launch_pool_mma(m, B, nJ, ldA)) return;
     PoolParams p;
     p.rp = m->rp; p.ap = m->ap; p.C = m->C; p.B = B;
     p.Ac = m->cur->ws_Ac.as<c2>(); p.ldA = ldA; p.errflag = m->ws_err.as<int>();
@@ -849,9 +915,37 @@ static void launch_adjoint(aceb200_model* m, long long nenv, long long ldA, bool
     m->launches++;
 }
 
+// The force contraction on the FP64 tensor cores (one channel, one species).  OPT-IN (ACEB200_FORCES_MMA=1): measured on
+// B200 at config 2 it loses to k_forces, 7.5 ms against 3.45 ms per 10^6 environments (profiles/r2_dmma_study.md): staging
+// 87 operand planes per neighbour and the per-(neighbour, column) epilogue cost more instructions than the 296 FMAs per
+// neighbour they replace, and 103 KB of planes per CTA leaves 2 CTAs per SM.  Kept for the record and for wider bases.
+static bool launch_forces_mma(aceb200_model* m, const BatchDev& B, long long nJ, long long ldA, double* G)
+{
+    HostTables& T = m->T;
+    static const bool on = getenv("ACEB200_FORCES_MMA") && atoi(getenv("ACEB200_FORCES_MMA")) == 1;
+    if (!on || T.P != 1 || T.nQ != 1 || B.species || m->n_pool_tiles == 0) return false;
+    ForceMmaParams p;
+    p.rp = m->rp; p.ap = m->ap; p.B = B;
+    p.Dt = m->cur->ws_Dt.as<c2>(); p.ldA = ldA; p.nS = T.nS; p.dpitch = T.nS | 1; p.G = G;
+    p.tiles = m->d_force_tiles; p.ntiles = m->n_pool_tiles;
+    p.nP = (T.Lused + 1) * (T.Lused + 2) / 2;
+    const double Jbar = std::max(1.0, (double)nJ / (double)std::max<long long>(1, B.nenv));
+    int k = std::max(1, std::min(kFmmaEnvs, (int)(kFmmaRows / Jbar)));       // whole environments per 128-row sub-tile
+    p.TE = k >= 8 ? k : k * ((8 + k - 1) / k);
+    if (p.TE > kForceTEmax) p.TE = (kForceTEmax / k) * k;
+    const size_t smem = (size_t)kMmaPitch * (2 * m->rp.N + 3 * p.nP + 2 * (T.Lused + 1) + 9) * sizeof(double)
+                      + (size_t)kFmmaEnvs * p.dpitch * sizeof(c2) + (size_t)p.ntiles * sizeof(ForceTile) + (kForceTEmax + 1) * sizeof(int);
+    if (smem > (size_t)m->smem_optin) return false;
+    launch_forces_mma_inst(m->NMAX, p.ap.L <= kStaticL, p, (unsigned)((B.nenv + p.TE - 1) / p.TE), smem, m->cur->stream);
+    CU(cudaGetLastError());
+    m->launches++;
+    return true;
+}
+
 static void launch_forces(aceb200_model* m, const BatchDev& B, long long nJ, long long ldA, double* G)
 {
     if (nJ == 0) return;
+    if (launch_forces_mma(m, B, nJ, ldA, G)) return;
     ForceParams p;
     p.rp = m->rp; p.ap = m->ap; p.C = m->C; p.B = B;
     p.Dt = m->cur->ws_Dt.as<c2>(); p.ldA = ldA; p.P = m->T.P; p.nprop = m->T.nprop; p.ncomp = m->T.ncomp; p.G = G;
@@ -1345,9 +1439,7 @@ __global__ void k_dmma_peak(int iters, double* sink)
     for (int k = 0; k < 8; ++k) { c[k][0] = k * 1e-3; c[k][1] = -k * 1e-3; }
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-                         : "+d"(c[k][0]), "+d"(c[k][1]) : "d"(a), "d"(b));
+        for (int k = 0; k < 8; ++k) dmma(c[k][0], c[k][1], a, b);
     }
     double s = 0.0;
 #pragma unroll

@@ -43,4 +43,30 @@ void ACE_CAT(pool_inst_, ACE_INST_NMAX)(bool species, bool staticL, const PoolPa
     else { if (staticL) pool_go<false, kWalkStatic>(p, grid, smem, st); else pool_go<false, kWalkRolled>(p, grid, smem, st); }
 }
 
+template <int WALK>
+static void pool_mma_go(const PoolMmaParams& p, unsigned grid, size_t smem, cudaStream_t st)
+{
+    auto kfn = k_pool_mma<ACE_INST_NMAX, WALK>;
+    CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ACE_LAUNCH(kfn, dim3(grid), dim3(kPoolMmaThreads), smem, st, p);
+}
+
+void ACE_CAT(pool_mma_inst_, ACE_INST_NMAX)(bool staticL, const PoolMmaParams& p, unsigned grid, size_t smem, cudaStream_t st)
+{
+    if (staticL) pool_mma_go<kWalkStatic>(p, grid, smem, st); else pool_mma_go<kWalkRolled>(p, grid, smem, st);
+}
+
+template <int WALK>
+static void forces_mma_go(const ForceMmaParams& p, unsigned grid, size_t smem, cudaStream_t st)
+{
+    auto kfn = k_forces_mma<ACE_INST_NMAX, WALK>;
+    CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ACE_LAUNCH(kfn, dim3(grid), dim3(kFmmaThreads), smem, st, p);
+}
+
+void ACE_CAT(forces_mma_inst_, ACE_INST_NMAX)(bool staticL, const ForceMmaParams& p, unsigned grid, size_t smem, cudaStream_t st)
+{
+    if (staticL) forces_mma_go<kWalkStatic>(p, grid, smem, st); else forces_mma_go<kWalkRolled>(p, grid, smem, st);
+}
+
 }  // namespace aceb200

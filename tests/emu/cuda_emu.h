@@ -42,7 +42,7 @@ inline double __hiloint2double(int hi, int lo) { union { double d; unsigned long
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
 
 namespace emu {
-struct BlockCtx { pthread_barrier_t bar; pthread_barrier_t wbar[32]; unsigned char* smem; };
+struct BlockCtx { pthread_barrier_t bar; pthread_barrier_t wbar[32]; unsigned char* smem; double frag_a[32][32]; double frag_b[32][32]; };
 inline thread_local uint3 t_threadIdx, t_blockIdx;
 inline thread_local dim3 t_blockDim, t_gridDim;
 inline thread_local BlockCtx* t_ctx;
@@ -89,6 +89,34 @@ inline void __syncwarp()
     pthread_barrier_wait(&emu::t_ctx->wbar[t / 32]);
 }
 template <class T> inline T __ldg(const T* p) { return *p; }
+namespace emu {
+// mma.sync.aligned.m8n8k4.row.col.f64: D = A(8x4, row) * B(4x8, col) + C.  Fragments (PTX ISA): lane i holds
+// A[i / 4][i % 4], B[i % 4][i / 4], C[i / 4][2 (i % 4) + {0, 1}].
+inline void mma_m8n8k4(double& c0, double& c1, double a, double b)
+{
+    unsigned t = t_threadIdx.x + t_blockDim.x * (t_threadIdx.y + t_blockDim.y * t_threadIdx.z);
+    unsigned w = t / 32, lane = t % 32;
+    t_ctx->frag_a[w][lane] = a; t_ctx->frag_b[w][lane] = b;
+    pthread_barrier_wait(&t_ctx->wbar[w]);
+    unsigned row = lane / 4, col = 2 * (lane % 4);
+    for (unsigned k = 0; k < 4; ++k) {
+        double av = t_ctx->frag_a[w][row * 4 + k];
+        c0 = std::fma(av, t_ctx->frag_b[w][col * 4 + k], c0);
+        c1 = std::fma(av, t_ctx->frag_b[w][(col + 1) * 4 + k], c1);
+    }
+    pthread_barrier_wait(&t_ctx->wbar[w]);
+}
+inline double shfl_xor(double v, int mask)
+{
+    unsigned t = t_threadIdx.x + t_blockDim.x * (t_threadIdx.y + t_blockDim.y * t_threadIdx.z);
+    unsigned w = t / 32, lane = t % 32;
+    t_ctx->frag_a[w][lane] = v;
+    pthread_barrier_wait(&t_ctx->wbar[w]);
+    double r = t_ctx->frag_a[w][lane ^ (unsigned)mask];
+    pthread_barrier_wait(&t_ctx->wbar[w]);
+    return r;
+}
+}  // namespace emu
 inline void sincos(double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }
 inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 inline int atomicMax(int* p, int v) { int o = *p; while (o < v && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
