@@ -298,9 +298,9 @@ __device__ __forceinline__ void pool_unit(const double* pa, const double* pb, co
     const double* qa[NNT];
 #pragma unroll
     for (int nt = 0; nt < NNT; ++nt) qa[nt] = pa + rowA[nt];
-    double alt[NNT][2];                                 // second accumulator set: two independent DMMA chains per row tile
-#pragma unroll
-    for (int nt = 0; nt < NNT; ++nt) { alt[nt][0] = 0.0; alt[nt][1] = 0.0; }
+    // One accumulator chain per row tile, k-steps strictly in order: appending neighbours that contribute exact zeros
+    // (beyond the cutoff, src/polynomials/orthpolys.jl:41-46) then leaves every bit of A unchanged, as in the reference's
+    // sequential sum.  (The 26-cycle DMMA latency is hidden by the ten resident warps per SMSP, not by a second chain.)
     int k = 0;
 #pragma unroll 1
     for (; k + 8 <= nr; k += 8) {
@@ -311,13 +311,11 @@ __device__ __forceinline__ void pool_unit(const double* pa, const double* pb, co
 #pragma unroll
         for (int nt = 0; nt < NNT; ++nt) dmma(acc[nt][0], acc[nt][1], a0[nt], b0);
 #pragma unroll
-        for (int nt = 0; nt < NNT; ++nt) dmma(alt[nt][0], alt[nt][1], a1[nt], b1);
+        for (int nt = 0; nt < NNT; ++nt) dmma(acc[nt][0], acc[nt][1], a1[nt], b1);
         pb += 8;
 #pragma unroll
         for (int nt = 0; nt < NNT; ++nt) qa[nt] += 8;
     }
-#pragma unroll
-    for (int nt = 0; nt < NNT; ++nt) { acc[nt][0] += alt[nt][0]; acc[nt][1] += alt[nt][1]; }
     if (k + 4 <= nr) {
         const double b0 = pb[0];
 #pragma unroll
@@ -1004,6 +1002,212 @@ __global__ void __launch_bounds__(32 * StreamGeom<NF, PB, CW>::NW, (PB == 1 && !
                 }
         }
         __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_basis_stream: evaluate(basis::SymmetricBasis, cfg) fused -- B = real?(A2Bmap . AA), AA = prod A, without AA in HBM
+// ------------------------------------------------------------------------------------------------
+// [replaces evaluate!(AA, pibasis, A) (src/pibasis.jl:265-275) + genmul! (src/symmbasis.jl:248-264, 312-316)]
+// Same mapping as k_adjoint_stream: the pooled A of 32 environments sits in shared memory as [slot][lane] (brought in by
+// TMA bulk copies), one lane = one environment, and every warp walks its own pre-flattened stream of leaves with
+// warp-uniform control flow.  A leaf is one non-zero of A2Bmap: up to NFAC slot codes (the AA function's factors) and, per
+// real output channel, a weight pair (p, q):  out += p Re(X) - q Im(X),  X = prod of the factors.  The host folds into
+// (p, q): the A2Bmap value (complex in general), all (-1)^m signs and the conjugation of the first factor, the real /
+// imaginary part selection of a complex B, and -- for a real B -- the mirror partner of the AA function (the function
+// with every m negated equals +-conj(AA), so one product serves both non-zeros).  Rows of B are dealt to the warps in
+// contiguous ranges balanced by leaf count; a leaf carries a row-end bit.  Finished rows go to a per-warp shared-memory
+// staging area [environment][W] and leave the SM as contiguous >= 128-byte segments per environment: B is
+// environment-major ([env][row][component]) while the lanes are environments, so direct stores would be 8-byte pieces
+// 2-55 KB apart.  Only B crosses HBM (config 4b: 55 KB per environment out, 0.7 KB in).
+constexpr unsigned kRowEnd = 0x4000u;      // leaf code bit 14
+constexpr int kBasisMaxWarps = 16;
+
+template <int NFAC, int NCH, bool CW>
+struct BasisGeom {
+    static constexpr int CS = CW ? 2 : 1;
+    static constexpr int CWORDS = (NFAC <= 2) ? 1 : 2;                   // code words per leaf
+    static constexpr int QB = CWORDS + 2 * NCH * CS;                     // uint4 per block (4 leaves)
+    static constexpr int KB = (QB * 16 >= 512) ? 2 : ((QB * 16 >= 256) ? 4 : ((QB * 16 >= 128) ? 8 : 16));   // blocks per ring chunk
+    static constexpr int CH = KB * QB;                                   // uint4 per chunk
+    static constexpr int ROWS = (NCH >= 9) ? 1 : (16 + NCH - 1) / NCH;   // rows staged per flush (>= 72 contiguous bytes per environment)
+    static constexpr int W = ROWS * NCH;                                 // doubles staged per environment
+    static constexpr int WP = W | 1;                                     // odd pitch: conflict-free staging
+};
+
+struct BasisParams {
+    int nS, nw, nchunks;
+    int nblk[kBasisMaxWarps];                // blocks of each warp's sub-stream
+    int row0[kBasisMaxWarps];                // first B row of each warp
+    const uint4* stream;                     // [nw][nchunks][CH]
+    const c2* Ac; long long ldA;
+    double* out;                             // [nenv][rowlen]
+    long long rowlen;                        // nB * NCH
+    long long nenv;
+};
+
+// EPL environments per lane (1 or 2): the (warp-uniform) leaf decode and the broadcast weight loads are shared by the
+// lane's environments, which also doubles the independent work per lane.
+template <int NFAC, int NCH, bool CW, int EPL>
+__global__ void __launch_bounds__((EPL == 2 && NCH >= 9) ? 384 : 32 * kBasisMaxWarps, 1) k_basis_stream(const BasisParams p)
+{
+    typedef BasisGeom<NFAC, NCH, CW> G;
+    constexpr int CS = G::CS, CH = G::CH, QB = G::QB, KB = G::KB, W = G::W, WP = G::WP;
+    constexpr int TW = 32 * EPL;                                        // environments per tile
+    constexpr int RSH = (EPL == 1) ? 9 : 10;                            // log2 of the tile row pitch in bytes
+    const int NW = p.nw;
+    ACE_DYN_SMEM(c2, As);                                               // [nS + 1][TW]; slot nS holds 1
+    uint4* rings = reinterpret_cast<uint4*>(As + (size_t)(p.nS + 1) * TW);   // [NW][2][CH]
+    double* stg_all = reinterpret_cast<double*>(rings + (size_t)NW * 2 * CH);  // [NW][TW][WP]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4* ring = rings + (size_t)warp * 2 * CH;
+    double* stg = stg_all + (size_t)warp * TW * WP;
+#if ACEB200_TMA
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(stg_all + (size_t)NW * TW * WP);   // [1 + 2 NW]
+    unsigned long long* barA = bars;
+    unsigned long long* barR = bars + 1 + 2 * warp;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 1 + 2 * NW; ++i) mbar_init(bars + i, 1);
+        fence_barrier_init();
+    }
+    unsigned phA = 0, phR0 = 0, phR1 = 0;
+#endif
+    if (warp == 0) {
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) As[p.nS * TW + lane + 32 * j] = c2{1.0, 0.0};
+    }
+    __syncthreads();
+    const int nblkw = p.nblk[warp];
+    const int nchw = (nblkw + KB - 1) / KB;
+    const uint4* stream = p.stream + (size_t)warp * p.nchunks * CH;
+    const unsigned char* Ab = reinterpret_cast<const unsigned char*>(As) + lane * 16;
+    const long long ntiles = (p.nenv + TW - 1) / TW;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+#if ACEB200_TMA
+        if (threadIdx.x == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(barA, (unsigned)(p.nS * TW * sizeof(c2)));
+            for (int s = 0; s < p.nS; ++s) bulk_g2s(As + s * TW, p.Ac + (size_t)s * p.ldA + tile * TW, TW * sizeof(c2), barA);
+        }
+        if (lane == 0 && nchw > 0) {
+            fence_proxy_async();
+            mbar_expect_tx(barR, CH * sizeof(uint4));
+            bulk_g2s(ring, stream, CH * sizeof(uint4), barR);
+            if (nchw > 1) {
+                mbar_expect_tx(barR + 1, CH * sizeof(uint4));
+                bulk_g2s(ring + CH, stream + CH, CH * sizeof(uint4), barR + 1);
+            }
+        }
+        mbar_wait(barA, phA);
+        phA ^= 1u;
+#else
+        for (int s = warp; s < p.nS; s += NW) {
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) As[s * TW + lane + 32 * j] = p.Ac[(size_t)s * p.ldA + tile * TW + lane + 32 * j];
+        }
+        for (int c = 0; c < 2 && c < nchw; ++c)
+            for (int k = lane; k < CH; k += 32) ring[c * CH + k] = __ldg(stream + (size_t)c * CH + k);
+        __syncthreads();
+#endif
+        double S[NCH][EPL];
+#pragma unroll
+        for (int q = 0; q < NCH; ++q)
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) S[q][j] = 0.0;
+        int pos = 0;                                   // doubles staged per environment
+        long long o0 = (long long)p.row0[warp] * NCH;  // output offset (within an environment's row) of stg[.][0]
+        // write the staged [environment][pos] block: consecutive lanes -> consecutive doubles of one environment.
+        // (env, k) of element idx = lane + 32 i advance incrementally (no division in the loop).
+        auto flush = [&]() {
+            __syncwarp();
+            const int n = pos;                                           // == W except for the last flush of a warp
+            const int dE = 32 / n, dK = 32 - dE * n;
+            int env = lane / n, k = lane - env * n;
+            const int envmax = (int)((p.nenv - tile * TW) < TW ? (p.nenv - tile * TW) : TW);
+            double* outp = p.out + (size_t)(tile * TW) * p.rowlen + o0;
+            const int iters = (TW * n + 31) / 32;
+            for (int i = 0; i < iters; ++i) {
+                if (env < envmax) outp[(size_t)env * p.rowlen + k] = stg[env * WP + k];
+                env += dE; k += dK;
+                if (k >= n) { k -= n; ++env; }
+            }
+            __syncwarp();
+            o0 += n;
+            pos = 0;
+        };
+        for (int ch = 0; ch < nchw; ++ch) {
+            const bool havepre = ch + 2 < nchw;
+#if ACEB200_TMA
+            if (ch & 1) { mbar_wait(barR + 1, phR1); phR1 ^= 1u; }
+            else { mbar_wait(barR, phR0); phR0 ^= 1u; }
+#endif
+            const uint4* rb = ring + (ch & 1) * CH;
+            const int nb = (nblkw - ch * KB < KB) ? nblkw - ch * KB : KB;
+            // One leaf per trip and NOT unrolled: the body (product + NCH channel updates for EPL environments + the
+            // row-end path with its flush) is ~100-250 instructions; unrolled four times it overflowed the instruction
+            // cache with a dozen warps at different places in it (ncu: "no instruction" became the top stall).
+#pragma unroll 1
+            for (int lf = 0; lf < 4 * nb; ++lf) {
+                {
+                    const int b = lf >> 2, k = lf & 3;
+                    const unsigned* blk = reinterpret_cast<const unsigned*>(rb + b * QB);
+                    const unsigned c = blk[k];
+                    const unsigned cc2 = (NFAC > 2) ? blk[4 + k] : 0u;
+                    const double* wl = reinterpret_cast<const double*>(blk + 4 * G::CWORDS) + k * NCH * CS;     // [NCH][CS]
+                    c2 X[EPL];
+#pragma unroll
+                    for (int j = 0; j < EPL; ++j) X[j] = lds_c2(Ab + 512 * j, (c & 0x3fffu) << RSH);
+                    if (NFAC >= 2) {
+                        const unsigned o2 = ((c >> 16) & 0x3fffu) << RSH, m2 = c & 0x80000000u;
+#pragma unroll
+                        for (int j = 0; j < EPL; ++j) { c2 a2 = lds_c2(Ab + 512 * j, o2); a2.y = xor_hi(a2.y, m2); X[j] = cmul(X[j], a2); }
+                    }
+                    if (NFAC >= 3) {
+                        const unsigned o3 = (cc2 & 0x3fffu) << RSH, m3 = (cc2 & 0x8000u) << 16;
+#pragma unroll
+                        for (int j = 0; j < EPL; ++j) { c2 a3 = lds_c2(Ab + 512 * j, o3); a3.y = xor_hi(a3.y, m3); X[j] = cmul(X[j], a3); }
+                    }
+                    if (NFAC >= 4) {
+                        const unsigned o4 = ((cc2 >> 16) & 0x3fffu) << RSH, m4 = cc2 & 0x80000000u;
+#pragma unroll
+                        for (int j = 0; j < EPL; ++j) { c2 a4 = lds_c2(Ab + 512 * j, o4); a4.y = xor_hi(a4.y, m4); X[j] = cmul(X[j], a4); }
+                    }
+#pragma unroll
+                    for (int q = 0; q < NCH; ++q) {
+                        if (CW) {        // two FMAs (the host stores -q): written out so that no separate multiply / add is formed
+                            const double w0 = wl[q * 2], w1 = wl[q * 2 + 1];
+#pragma unroll
+                            for (int j = 0; j < EPL; ++j) { S[q][j] = fma(w0, X[j].x, S[q][j]); S[q][j] = fma(w1, X[j].y, S[q][j]); }
+                        } else {
+                            const double w0 = wl[q];
+#pragma unroll
+                            for (int j = 0; j < EPL; ++j) S[q][j] = fma(w0, X[j].x, S[q][j]);
+                        }
+                    }
+                    if (c & kRowEnd) {                 // warp-uniform: every lane walks the same stream
+#pragma unroll
+                        for (int j = 0; j < EPL; ++j)
+#pragma unroll
+                            for (int q = 0; q < NCH; ++q) { stg[(lane + 32 * j) * WP + pos + q] = S[q][j]; S[q][j] = 0.0; }
+                        pos += NCH;
+                        if (pos + NCH > W) flush();
+                    }
+                }
+            }
+            __syncwarp();            // every lane is done reading this ring slot
+#if ACEB200_TMA
+            if (havepre && lane == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(barR + (ch & 1), CH * sizeof(uint4));
+                bulk_g2s(ring + (ch & 1) * CH, stream + (size_t)(ch + 2) * CH, CH * sizeof(uint4), barR + (ch & 1));
+            }
+#else
+            if (havepre) for (int k = lane; k < CH; k += 32) ring[(ch & 1) * CH + k] = __ldg(stream + (size_t)(ch + 2) * CH + k);
+            __syncwarp();
+#endif
+        }
+        if (pos > 0) flush();
+        __syncthreads();             // the A tile is free for the next tile's copies
     }
 }
 

@@ -67,7 +67,7 @@ constexpr int kLanes = 4;
 
 struct Lane {
     DevBuf ws_Ac, ws_Dt, ws_E, ws_G, ws_A, ws_AA, ws_dA, ws_dAA, ws_out;
-    DevBuf in_off, in_R, in_sp, in_w, ws_Aw, ws_A2;
+    DevBuf in_off, in_R, in_sp, in_w, ws_Aw, ws_A2, ws_part;
     cudaStream_t stream = nullptr;       // the stream this lane currently launches on
     cudaStream_t own_stream = nullptr;   // private non-blocking stream (host-batch pipeline)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
@@ -75,7 +75,7 @@ struct Lane {
     bool timed_ef = false;
     void release()
     {
-        DevBuf* bufs[] = {&ws_Ac, &ws_Dt, &ws_E, &ws_G, &ws_A, &ws_AA, &ws_dA, &ws_dAA, &ws_out, &in_off, &in_R, &in_sp, &in_w, &ws_Aw, &ws_A2};
+        DevBuf* bufs[] = {&ws_Ac, &ws_Dt, &ws_E, &ws_G, &ws_A, &ws_AA, &ws_dA, &ws_dAA, &ws_out, &in_off, &in_R, &in_sp, &in_w, &ws_Aw, &ws_A2, &ws_part};
         for (DevBuf* b : bufs) b->release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -86,6 +86,16 @@ struct Lane {
 };
 
 struct StreamPass { DevBuf blocks, tinfo, w0; int pb0 = 0; };
+
+// A packed leaf stream for k_basis_stream and its geometry
+struct BStream {
+    DevBuf buf;
+    int nw = 0, nchunks = 0, nfac = 0, nch = 0, QB = 0, KB = 0, W = 0, epl = 1, nrows = 0;
+    bool cw = false;
+    int nblk[kBasisMaxWarps] = {0}, row0[kBasisMaxWarps] = {0};
+    size_t smem = 0;
+};
+struct BLeaf { unsigned c0, c1; std::vector<double> w; };     // slot codes; w: [nch][cs] = (p, -q) pairs
 
 struct aceb200_model {
     int device = 0;
@@ -104,6 +114,11 @@ struct aceb200_model {
     const PoolTile* d_pool_tiles = nullptr;    // k_pool_mma column tiles (single-species models)
     int n_pool_tiles = 0;
     const ForceTile* d_force_tiles = nullptr;  // k_forces_mma column tiles (same column order)
+    // k_basis_stream (fused B = A2Bmap . prod A): leaf stream per warp; depends on the tables only, not on c
+    BStream bs;                                // B = A2Bmap . AA
+    // the same kernel as the energy readout of evaluate(model, cfg) (src/evaluator.jl:137-143): one pseudo-row per warp
+    // holding a share of the AA functions, weights c~ (rebuilt by set_params), channels = properties x components
+    BStream es;
     const int *d_orders = nullptr, *d_spec = nullptr;
     const int *d_csr_ptr = nullptr, *d_csr_col = nullptr;
     const c2* d_csr_val = nullptr;
@@ -179,6 +194,7 @@ static void fill_params(aceb200_model* m, const aceb200_desc& d)
 }
 
 static void upload_stream(aceb200_model* m, bool energy_only = false);
+static void upload_energy_stream(aceb200_model* m);
 
 // c~ and the weights that depend on it: order-0/1 weights and the leaf weights of every tree
 static void upload_weights(aceb200_model* m, const double* c)
@@ -224,6 +240,7 @@ static void upload_weights(aceb200_model* m, const double* c)
     }
     upload_stream(m);
     upload_stream(m, true);
+    upload_energy_stream(m);
 }
 
 // Host mirror of StreamGeom (ace_kernels.cuh)
@@ -566,6 +583,291 @@ static void upload_stream(aceb200_model* m, bool energy_only)
     }
 }
 
+// Mirror partner of every AA function (all m negated), or -1: AA' = s conj(AA), s = (-1)^{sum m}
+static void mirror_partners(const HostTables& T, std::vector<int>& partner, std::vector<int>& sign)
+{
+    partner.assign(T.nAA, -1); sign.assign(T.nAA, 1);
+    std::map<std::tuple<int, int, int, int>, int> inv1p;
+    for (int a = 0; a < T.nA; ++a) inv1p[std::make_tuple(T.iA_q[a], T.iA_n[a], T.iA_l[a], T.iA_m[a])] = a;
+    std::vector<int> mirA(T.nA, -1);
+    for (int a = 0; a < T.nA; ++a) {
+        auto it = inv1p.find(std::make_tuple(T.iA_q[a], T.iA_n[a], T.iA_l[a], -T.iA_m[a]));
+        if (it != inv1p.end()) mirA[a] = it->second;
+    }
+    std::map<std::vector<int>, int> invAA;
+    auto keyof = [&](int i, bool mirror, bool& ok) {
+        std::vector<int> k;
+        ok = true;
+        for (int t = 0; t < T.orders[i]; ++t) {
+            int a = T.spec[(size_t)i * T.maxord + t];
+            if (mirror) { a = mirA[a]; if (a < 0) { ok = false; a = 0; } }
+            k.push_back(a);
+        }
+        std::sort(k.begin(), k.end(), std::greater<int>());
+        return k;
+    };
+    bool ok;
+    for (int i = 0; i < T.nAA; ++i) invAA[keyof(i, false, ok)] = i;
+    for (int i = 0; i < T.nAA; ++i) {
+        std::vector<int> k = keyof(i, true, ok);
+        if (!ok) continue;
+        auto it = invAA.find(k);
+        if (it == invAA.end()) continue;
+        partner[i] = it->second;
+        int summ = 0;
+        for (int t = 0; t < T.orders[i]; ++t) summ += T.iA_m[T.spec[(size_t)i * T.maxord + t]];
+        sign[i] = (summ & 1) ? -1 : 1;
+    }
+}
+
+// slot codes and sign bookkeeping of one AA function:  AA = sg * flip^{k1}(Y),  Y = A~_1 * prod_{f > 1} cj^{k_f xor k_1}(A~_f),
+// so that  p Re(AA) - q Im(AA) = (sg p) Re(Y) - (sg fy q) Im(Y)
+static void aa_codes(const HostTables& T, int aa, unsigned& c0, unsigned& c1, double& sg, double& fy)
+{
+    const unsigned ONE = (unsigned)T.nS;
+    unsigned slot[4] = {ONE, ONE, ONE, ONE}, cj[4] = {0u, 0u, 0u, 0u};
+    sg = 1.0;
+    unsigned k1 = 0;
+    for (int f = 0; f < T.orders[aa]; ++f) {
+        const unsigned c = (unsigned)T.iA_code[T.spec[(size_t)aa * T.maxord + f]];
+        const unsigned neg = c & 1u, odd = (c >> 1) & 1u;
+        if (neg && odd) sg = -sg;
+        if (f == 0) k1 = neg;
+        slot[f] = c >> 2;
+        cj[f] = (f > 0 && (neg ^ k1)) ? 1u : 0u;
+    }
+    fy = k1 ? -1.0 : 1.0;
+    c0 = slot[0] | (slot[1] << 16) | (cj[1] << 31);
+    c1 = slot[2] | (cj[2] << 15) | (slot[3] << 16) | (cj[3] << 31);
+}
+
+// Pack rows of leaves into the per-warp streams of k_basis_stream and choose the launch geometry.
+static bool pack_bstream(aceb200_model* m, std::vector<std::vector<BLeaf>>& rows, int nfac, int nch, bool cw, BStream& out, const char* what)
+{
+    HostTables& T = m->T;
+    out.nw = 0;
+    int QB, KB, W;
+    if (!basis_geom(nfac, nch, cw, QB, KB, W)) return false;
+    const int cs = cw ? 2 : 1, nrows = (int)rows.size();
+    const unsigned ONE = (unsigned)T.nS;
+    size_t nleaves = 0;
+    for (auto& r : rows) {
+        if (r.empty()) {      // a structurally empty row still produces its zeros
+            BLeaf L; L.c0 = ONE | (ONE << 16); L.c1 = ONE | (ONE << 16); L.w.assign((size_t)nch * cs, 0.0);
+            r.push_back(L);
+        }
+        r.back().c0 |= kRowEnd;
+        nleaves += r.size();
+    }
+    auto smem_of = [&](int nw, int epl) {
+        return (size_t)(T.nS + 1) * 32 * epl * sizeof(c2) + (size_t)nw * 2 * KB * QB * 16 + (size_t)nw * 32 * epl * (W | 1) * sizeof(double)
+             + (size_t)(1 + 2 * nw) * 8;
+    };
+    // The kernel is latency-bound (dependent FP64 chains): what counts is warps per SM, so take as many as fit in shared
+    // memory (and in the register file: 12 for the 9-channel, two-environment variant, which needs 168 registers).
+    const bool epl2ok = basis_epl2(nch, cw);
+    int epl = epl2ok ? 2 : 1;
+    if (const char* ov = getenv("ACEB200_BASIS_EPL")) epl = (atoi(ov) == 2 && epl2ok) ? 2 : 1;
+    if (epl == 2 && smem_of(8, 2) > (size_t)m->smem_optin) epl = 1;
+    int nw = (epl == 2 && nch >= 9) ? 12 : kBasisMaxWarps;
+    while (nw > 1 && smem_of(nw, epl) > (size_t)m->smem_optin) --nw;
+    if (const char* ov = getenv("ACEB200_BASIS_WARPS")) nw = std::max(1, std::min(nw, atoi(ov)));
+    if (smem_of(nw, epl) > (size_t)m->smem_optin) return false;
+    nw = std::min(nw, std::max(1, nrows));
+    // contiguous row ranges balanced by cost: a leaf costs its product + nch channel updates, a row its share of a flush
+    std::vector<int> cut(nw + 1, nrows);
+    cut[0] = 0;
+    { const double cleaf = 14.0 + 6.0 * (nfac - 1) + (cw ? 3.0 : 2.0) * nch, crow = 8.0 + 14.0 * nch;
+      double tot = 0.0, acc = 0.0;
+      for (int r = 0; r < nrows; ++r) tot += cleaf * rows[r].size() + crow;
+      int w = 1;
+      for (int r = 0; r < nrows && w < nw; ++r) {
+          acc += cleaf * rows[r].size() + crow;
+          while (w < nw && acc * nw >= tot * w) cut[w++] = r + 1;
+      } }
+    size_t longest = 1;
+    for (int w = 0; w < nw; ++w) { size_t nl = 0; for (int r = cut[w]; r < cut[w + 1]; ++r) nl += rows[r].size(); longest = std::max(longest, (nl + 3) / 4); }
+    const size_t nchunks = (longest + KB - 1) / KB;
+    std::vector<uint32_t> blocks((size_t)nw * nchunks * KB * QB * 4, 0u);
+    const int cwords = nfac <= 2 ? 1 : 2;
+    for (int w = 0; w < nw; ++w) {
+        size_t il = 0;
+        auto emit = [&](const BLeaf* L) {
+            uint32_t* blk = &blocks[(((size_t)w * nchunks * KB) + il / 4) * QB * 4];
+            const int k = (int)(il % 4);
+            blk[k] = L ? L->c0 : (ONE | (ONE << 16));
+            if (cwords == 2) blk[4 + k] = L ? L->c1 : (ONE | (ONE << 16));
+            double* wd = reinterpret_cast<double*>(blk + 4 * cwords) + (size_t)k * nch * cs;
+            for (int i = 0; i < nch * cs; ++i) wd[i] = L ? L->w[i] : 0.0;
+            ++il;
+        };
+        for (int r = cut[w]; r < cut[w + 1]; ++r) for (const BLeaf& L : rows[r]) emit(&L);
+        out.nblk[w] = (int)((il + 3) / 4);
+        while (il % 4) emit(nullptr);                  // inert leaves: zero weights, no row end
+        out.row0[w] = cut[w];
+    }
+    out.buf.reserve(blocks.size() * 4 + 4096);
+    CU(cudaMemcpy(out.buf.p, blocks.data(), blocks.size() * 4, cudaMemcpyHostToDevice));
+    out.nw = nw; out.nchunks = (int)nchunks; out.nfac = nfac; out.nch = nch; out.cw = cw; out.QB = QB; out.KB = KB; out.W = W; out.epl = epl;
+    out.nrows = nrows; out.smem = smem_of(nw, epl);
+    if (getenv("ACEB200_VERBOSE"))
+        fprintf(stderr, "[aceb200] %s stream: NFAC=%d NCH=%d CW=%d EPL=%d, %d warps x %zu chunks of %d blocks, %zu leaves in %d rows, smem %zu B\n",
+                what, nfac, nch, (int)cw, epl, nw, nchunks, KB, nleaves, nrows, out.smem);
+    return true;
+}
+
+// Flatten A2Bmap (CSR) into the leaf streams k_basis_stream walks (layout: ace_kernels.cuh).
+static void upload_basis_stream(aceb200_model* m)
+{
+    HostTables& T = m->T;
+    m->bs.nw = 0;
+    if (getenv("ACEB200_NO_BASIS_STREAM")) return;
+    if (T.nB == 0 || T.maxord > 4 || T.nS + 1 >= (1 << 14)) return;
+    const int nfac = std::max(1, T.maxord);
+    const bool cw = !T.pireal;
+    const int nch = T.ncomp * (T.symreal ? 1 : 2);
+    const int cs = cw ? 2 : 1;
+    // ---- leaves per row, mirror partners folded for a real B
+    std::vector<int> partner, psign;
+    const bool fold = T.symreal && !getenv("ACEB200_NO_MIRROR_FOLD");
+    if (fold) mirror_partners(T, partner, psign);
+    std::vector<std::vector<BLeaf>> rows(T.nB);
+    for (int r = 0; r < T.nB; ++r) {
+        // (AA column -> value) of this row
+        std::map<int, const cplx*> ent;
+        for (int k = T.csr_ptr[r]; k < T.csr_ptr[r + 1]; ++k) ent[T.csr_col[k]] = &T.csr_val[(size_t)k * T.ncomp];
+        std::map<int, bool> done;
+        for (auto& kv : ent) {
+            const int aa = kv.first;
+            if (done[aa]) continue;
+            done[aa] = true;
+            BLeaf L;
+            double sg, fy;
+            aa_codes(T, aa, L.c0, L.c1, sg, fy);
+            const cplx* vp = nullptr;
+            double ps = 0.0;
+            if (fold && partner[aa] >= 0 && partner[aa] != aa) {
+                auto it = ent.find(partner[aa]);
+                if (it != ent.end()) { vp = it->second; ps = (double)psign[aa]; done[partner[aa]] = true; }
+            }
+            L.w.assign((size_t)nch * cs, 0.0);
+            for (int c = 0; c < T.ncomp; ++c) {
+                // value of this non-zero, with the mirror partner folded in:  v AA + v' s conj(AA) -> (p, q) on (Re AA, Im AA)
+                const cplx v = kv.second[c];
+                double pr = v.real(), qr = v.imag();            // Re(v X) = pr X.x - qr X.y
+                double pi = v.imag(), qi = -v.real();           // Im(v X) = pi X.x - qi X.y
+                if (vp) { const cplx v2 = vp[c]; pr += ps * v2.real(); qr -= ps * v2.imag(); }   // Re(v2 s conj X) = s (v2r X.x + v2i X.y)
+                if (T.pireal) { qr = 0.0; qi = 0.0; }           // AA = Re(prod A): the imaginary part of the product is dropped
+                auto put = [&](int chn, double pp, double qq) {
+                    L.w[(size_t)chn * cs] = sg * pp;
+                    if (cw) L.w[(size_t)chn * cs + 1] = -sg * fy * qq;       // the kernel adds w1 * Im: store -q
+                };
+                if (T.symreal) put(c, pr, qr);
+                else { put(2 * c, pr, qr); put(2 * c + 1, pi, qi); }
+            }
+            rows[r].push_back(L);
+        }
+    }
+    pack_bstream(m, rows, nfac, nch, cw, m->bs, "basis");
+}
+
+// The energy readout E_p = Re sum_k c~_{k,p} AA_k (src/evaluator.jl:137-143) as a k_basis_stream pass: the AA functions
+// (mirror partners folded) are dealt to one pseudo-row per warp; the per-warp partial sums are added by k_sum_partials.
+// Half the FP64 work of the Euler-identity pass of k_adjoint_stream, which forms the full complex sum per channel.
+static void upload_energy_stream(aceb200_model* m)
+{
+    HostTables& T = m->T;
+    m->es.nw = 0;
+    if (getenv("ACEB200_NO_ENERGY_BSTREAM")) return;
+    if (!T.symreal || T.maxord > 4 || T.nS + 1 >= (1 << 14)) return;
+    const int nfac = std::max(1, T.maxord), P = T.P;
+    const bool cw = m->cw;
+    const int cs = cw ? 2 : 1;
+    int QB, KB, W;
+    if (!basis_geom(nfac, P, cw, QB, KB, W)) return;
+    std::vector<int> partner, psign;
+    const bool fold = !getenv("ACEB200_NO_MIRROR_FOLD");
+    if (fold) mirror_partners(T, partner, psign);
+    std::vector<BLeaf> all;
+    std::vector<char> done(T.nAA, 0);
+    for (int aa = 0; aa < T.nAA; ++aa) {
+        if (done[aa]) continue;
+        done[aa] = 1;
+        BLeaf L;
+        double sg, fy;
+        aa_codes(T, aa, L.c0, L.c1, sg, fy);
+        int pa = -1;
+        if (fold && partner[aa] >= 0 && partner[aa] != aa && !done[partner[aa]]) { pa = partner[aa]; done[pa] = 1; }
+        L.w.assign((size_t)P * cs, 0.0);
+        bool any = false;
+        for (int pch = 0; pch < P; ++pch) {
+            cplx z = m->ctilde[(size_t)aa * P + pch];
+            if (pa >= 0) z += (double)psign[aa] * std::conj(m->ctilde[(size_t)pa * P + pch]);     // Re(z' s conj(AA)) = Re(s conj(z') AA)
+            L.w[(size_t)pch * cs] = sg * z.real();
+            if (cw) L.w[(size_t)pch * cs + 1] = -sg * fy * z.imag();
+            any |= (z != cplx(0, 0));
+        }
+        if (any) all.push_back(L);
+    }
+    // one pseudo-row per warp: pack_bstream keeps at most as many warps as rows, so make 16 equal rows
+    const int nrows = kBasisMaxWarps;
+    std::vector<std::vector<BLeaf>> rows(nrows);
+    for (size_t i = 0; i < all.size(); ++i) rows[(i * nrows) / std::max<size_t>(all.size(), 1)].push_back(all[i]);
+    pack_bstream(m, rows, nfac, P, cw, m->es, "energy");
+}
+
+// one k_basis_stream launch: pooled A (ws_Ac) -> out [ne][S.nrows][S.nch]
+static bool launch_bstream(aceb200_model* m, const BStream& S, long long ne, long long ldA, double* out)
+{
+    if (S.nw == 0) return false;
+    HostTables& T = m->T;
+    BasisParams p;
+    memset(&p, 0, sizeof(p));
+    p.nS = T.nS; p.nw = S.nw; p.nchunks = S.nchunks;
+    for (int w = 0; w < S.nw; ++w) { p.nblk[w] = S.nblk[w]; p.row0[w] = S.row0[w]; }
+    p.stream = S.buf.as<uint4>();
+    p.Ac = m->cur->ws_Ac.as<c2>(); p.ldA = ldA; p.out = out; p.rowlen = (long long)S.nrows * S.nch; p.nenv = ne;
+    const long long ntiles = (ne + 32 * S.epl - 1) / (32 * S.epl);
+    const int per_sm = std::max<int>(1, std::min<int>(2048 / (32 * p.nw), (int)((size_t)m->smem_optin / (S.smem + 1024))));
+    const int grid = (int)std::min<long long>(ntiles, (long long)m->sm_count * per_sm);
+    if (!launch_basis_inst(S.nfac, S.nch, S.cw, S.epl, p, grid, S.smem, m->cur->stream)) return false;
+    CU(cudaGetLastError());
+    m->launches++;
+    return true;
+}
+
+// B for a chunk: out [ne][nB][ncomp] (real or complex)
+static bool launch_basis(aceb200_model* m, long long ne, long long ldA, double* out) { return launch_bstream(m, m->bs, ne, ldA, out); }
+
+// E[e][p] = sum over the pseudo-rows of the energy stream
+__global__ void k_sum_partials(long long nenv, int nrows, int P, const double* part, double* E)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nenv * P) return;
+    const long long e = t / P;
+    const int pch = (int)(t - e * P);
+    const double* src = part + (size_t)e * nrows * P + pch;
+    double acc = 0.0;
+    for (int r = 0; r < nrows; ++r) acc += src[(size_t)r * P];
+    E[t] = acc;
+}
+
+// evaluate(model, cfg) for a chunk: energies only
+static bool launch_energy_bstream(aceb200_model* m, long long ne, long long ldA)
+{
+    const BStream& S = m->es;
+    if (S.nw == 0) return false;
+    Lane& L = *m->cur;
+    L.ws_part.reserve((size_t)ne * S.nrows * S.nch * sizeof(double));
+    if (!launch_bstream(m, S, ne, ldA, L.ws_part.as<double>())) return false;
+    auto kfn = k_sum_partials;
+    const long long n = ne * S.nch;
+    ACE_LAUNCH(kfn, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, L.stream, ne, S.nrows, S.nch, (const double*)L.ws_part.as<double>(), L.ws_E.as<double>());
+    CU(cudaGetLastError());
+    m->launches++;
+    return true;
+}
+
 static void upload_tables(aceb200_model* m)
 {
     HostTables& T = m->T;
@@ -656,6 +958,7 @@ static void upload_tables(aceb200_model* m)
     m->d_csr_val = upload(m->pool, val);
     for (int nu = 0; nu <= kMaxOrdDev; ++nu) memset(&m->list[nu], 0, sizeof(ListDev));
     for (int nu = 2; nu <= T.maxord; ++nu) m->list[nu].ptr = upload(m->pool, T.trees[nu].ptr);
+    upload_basis_stream(m);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -874,6 +1177,7 @@ static void launch_adjoint(aceb200_model* m, long long nenv, long long ldA, bool
         const long long ntiles = (nenv + 32 * m->stream_epl - 1) / (32 * m->stream_epl);
         const int per_sm = std::max<int>(1, std::min<int>(8, (int)((size_t)m->smem_optin / (smem + 1024))));
         const int grid = (int)std::min<long long>(ntiles, (long long)m->sm_count * per_sm);
+        if (!want_D && launch_energy_bstream(m, nenv, ldA)) return;          // energy only: the readout pass of k_basis_stream
         const bool eo = !want_D && m->e_stream_chunks > 0;       // energy only: the short stream
         for (const StreamPass& sp : (eo ? m->e_passes : m->passes)) {
             StreamParams p;
@@ -1068,8 +1372,9 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
     std::lock_guard<std::mutex> lock(m->mu);
     const int P = T.P, nA = T.nA, nAA = T.nAA, nB = T.nB, ncomp = T.ncomp;
     const int ca = T.pireal ? 1 : 2, cs = T.symreal ? 1 : 2;
-    const bool need_full_A = want & (W_A | W_AA | W_B | W_dA | W_dAA | W_dB | W_ADJ);
-    const bool need_AA = want & (W_AA | W_B | W_dAA | W_dB);
+    const bool fusedB = (want & W_B) && m->bs.nw > 0;       // B straight from the pooled A (k_basis_stream): AA never reaches HBM
+    const bool need_full_A = (want & (W_A | W_AA | W_dA | W_dAA | W_dB | W_ADJ)) || ((want & W_B) && !fusedB);
+    const bool need_AA = (want & (W_AA | W_dAA | W_dB)) || ((want & W_B) && !fusedB);
     const bool need_dA = want & (W_dA | W_dAA | W_dB);
     const bool need_dAA = want & (W_dAA | W_dB);
     const bool host = b->space == ACEB200_HOST;
@@ -1168,10 +1473,21 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
         } else {
             // basis values / Jacobians
             c2* dA_dev = nullptr; double* AA_dev = nullptr; double* dAA_dev = nullptr;
-            L.ws_A.reserve((size_t)ne * nA * sizeof(c2));
-            { auto kfn = k_expand_A;
-              ACE_LAUNCH(kfn, dim3(blocks_for(ne * nA, 256)), dim3(256), 0, L.stream, ne, nA, m->d_code, L.ws_Ac.as<c2>(), ldA, L.ws_A.as<c2>());
-              CU(cudaGetLastError()); m->launches++; }
+            double* B_dev = nullptr;
+            if (fusedB) {
+                CU(cudaEventRecord(L.evA, L.stream));
+                if (!host) B_dev = o.B + (size_t)c.e0 * nB * ncomp * cs;
+                else { L.ws_out.reserve((size_t)ne * nB * ncomp * 8 * cs); B_dev = L.ws_out.as<double>(); }
+                if (!launch_basis(m, ne, ldA, B_dev)) throw ModelError(ACEB200_ECUDA, "k_basis_stream: no instantiation for this basis");
+                CU(cudaEventRecord(L.evB, L.stream));
+                L.timed_ef = true;
+            }
+            if (need_full_A) {
+                L.ws_A.reserve((size_t)ne * nA * sizeof(c2));
+                auto kfn = k_expand_A;
+                ACE_LAUNCH(kfn, dim3(blocks_for(ne * nA, 256)), dim3(256), 0, L.stream, ne, nA, m->d_code, L.ws_Ac.as<c2>(), ldA, L.ws_A.as<c2>());
+                CU(cudaGetLastError()); m->launches++;
+            }
             if (want & W_ADJ) {
                 // adjoint_EVAL_D: pool dAw like A, contract through the product basis, apply A2Bmap
                 const double* Wdev = nullptr;
@@ -1210,8 +1526,7 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
                            (const c2*)L.ws_A.as<c2>(), T.pireal, AA_dev);
                 CU(cudaGetLastError()); m->launches++;
             }
-            double* B_dev = nullptr;
-            if (want & W_B) {
+            if ((want & W_B) && !fusedB) {
                 L.ws_out.reserve((size_t)ne * nB * ncomp * 8 * cs);
                 B_dev = L.ws_out.as<double>();
                 auto kfn = k_B;
@@ -1244,7 +1559,7 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
             CU(cudaEventRecord(L.ev1, L.stream));
             if (o.A) deliver(m, b, o.A + (size_t)c.e0 * nA * 2, L.ws_A.p, (size_t)ne * nA * sizeof(c2));
             if (o.AA) deliver(m, b, o.AA + (size_t)c.e0 * nAA * ca, AA_dev, (size_t)ne * nAA * 8 * ca);
-            if (o.B) deliver(m, b, o.B + (size_t)c.e0 * nB * ncomp * cs, B_dev, (size_t)ne * nB * ncomp * 8 * cs);
+            if (o.B && (host || !fusedB)) deliver(m, b, o.B + (size_t)c.e0 * nB * ncomp * cs, B_dev, (size_t)ne * nB * ncomp * 8 * cs);
             if (o.dA) deliver(m, b, o.dA + (size_t)c.j0 * nA * 6, dA_dev, (size_t)nj * nA * 3 * sizeof(c2));
             if (o.dAA) deliver(m, b, o.dAA + (size_t)c.j0 * nAA * 3 * ca, dAA_dev, (size_t)nj * nAA * 24 * ca);
             if (o.dB) deliver(m, b, o.dB + (size_t)c.j0 * nB * 3 * ncomp * cs, dB_dev, (size_t)nj * nB * 24 * ncomp * cs);
@@ -1519,7 +1834,7 @@ int aceb200_model_destroy(aceb200_model* m)
     if (!m) return ACEB200_OK;
     cudaSetDevice(m->device);
     for (DevBuf& b : m->pool) b.release();
-    m->d_w0.release(); m->d_w1.release(); m->d_ctl.release(); m->ws_err.release();
+    m->d_w0.release(); m->d_w1.release(); m->d_ctl.release(); m->ws_err.release(); m->bs.buf.release(); m->es.buf.release();
     for (StreamPass& sp : m->passes) { sp.blocks.release(); sp.tinfo.release(); sp.w0.release(); }
     for (StreamPass& sp : m->e_passes) { sp.blocks.release(); sp.tinfo.release(); sp.w0.release(); }
     m->e_ctl.release();

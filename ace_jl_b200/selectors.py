@@ -166,42 +166,43 @@ def init1pspec(B1p: Product1pBasis, Bsel: DownsetBasisSelector = None) -> Produc
 
 def gensparse(*, NU: int, maxvv: Sequence[int], admissible: Callable, filter: Callable,
               tup2b: Callable = lambda vv: vv, ordered: bool = True, minvv=None) -> List[tuple]:
-    """Depth-first enumeration of a down-set of (ordered) index tuples (sparsegrids.jl:69-148).
+    """All admissible index tuples of a down-set, in the order ``gensparse`` of the reference visits them
+    (src/sparsegrids.jl:55-148): lexicographic with the FIRST position most significant, ``vv[i] == 0`` = "no factor";
+    with ``ordered`` only non-decreasing tuples.  The order matters: it is the order of the AA functions.
 
-    ``vv[i] == 0`` means "no factor".  Returns the kept tuples in visiting order.
+    Written as a depth-first walk over prefixes.  For a fixed prefix, position ``p`` runs upwards from its start value
+    and stops at the first value whose *minimal completion* (the value repeated to the end if ``ordered``, zeros
+    otherwise) is inadmissible -- in a down-set every larger tuple is then inadmissible too, which is the property the
+    reference's increment / back-track loop relies on as well.
     """
-    minvv = [0] * NU if minvv is None else list(minvv)
-    vv = list(minvv)
-    spec: List[tuple] = []
+    start = [0] * NU if minvv is None else [int(v) for v in minvv]
+    limit = list(maxvv)
+    kept: List[tuple] = []
+
+    def ok(vv) -> bool:
+        return all(v <= mx for v, mx in zip(vv, limit)) and bool(admissible(tup2b(vv)))
+
     if NU == 0:
-        if all(v == 0 for v in minvv) and admissible(tup2b(vv)) and filter(tup2b(vv)):
-            spec.append(tuple(vv))
-        return spec
-    lastidx = 0
-    while True:
-        if any(v > mx for v, mx in zip(vv, maxvv)):
-            isadm = False
-            bb = None
-        else:
-            bb = tup2b(vv)
-            isadm = admissible(bb)
-        if isadm:
-            if filter(bb):
-                spec.append(tuple(vv))
-            lastidx = NU
-            vv[lastidx - 1] += 1
-        else:
-            if lastidx == 0:
-                raise RuntimeError("lastidx == 0 should never occur: the smallest basis function "
-                                   "is already inadmissible, the basis is empty")
-            if lastidx == 1:
-                break
-            vv[lastidx - 2] += 1
-            fill = vv[lastidx - 2] if ordered else 0
-            for k in range(lastidx - 1, NU):
-                vv[k] = fill
-            lastidx -= 1
+        return [()] if ok([]) and filter(tup2b([])) else kept
+    first = list(start)
+    if not ok(first):
+        raise ValueError("gensparse: the smallest index tuple is inadmissible, so the basis would be empty")
+
+    def walk(p: int, vv: list) -> None:
+        """vv[:p] is fixed and vv[p:] is the minimal completion of vv[p], already known to be admissible."""
+        while True:
+            if p == NU - 1:
+                if filter(tup2b(vv)):
+                    kept.append(tuple(vv))
+            else:
+                walk(p + 1, list(vv))
+            vv[p] += 1
+            for k in range(p + 1, NU):
+                vv[k] = vv[p] if ordered else 0
+            if not ok(vv):
+                return
+
+    walk(0, first)
     if ordered:
-        assert all(all(s[i] <= s[i + 1] for i in range(NU - 1)) for s in spec)
-        assert len(set(spec)) == len(spec)
-    return spec
+        assert all(all(t[i] <= t[i + 1] for i in range(NU - 1)) for t in kept) and len(set(kept)) == len(kept)
+    return kept
