@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libaceb200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 HOST, DEVICE = 0, 1
 MAX_COMP = 4
 
@@ -47,7 +47,7 @@ class Desc(C.Structure):
 class Batch(C.Structure):
     _fields_ = [
         ("nenv", C.c_int64), ("offsets", c_int64_p), ("R", c_double_p), ("species", c_int32_p),
-        ("space", C.c_int32), ("_pad", C.c_int32),
+        ("space", C.c_int32), ("_pad", C.c_int32), ("nJ", C.c_int64),
     ]
 
 
@@ -76,6 +76,7 @@ _VOIDPP = C.POINTER(C.c_void_p)
 SYMBOLS = [
     ("aceb200_device_count", C.c_int, []),
     ("aceb200_set_device", C.c_int, [C.c_int]),
+    ("aceb200_set_devices", C.c_int, [C.c_void_p, C.c_int, c_int32_p]),
     ("aceb200_last_error", C.c_int, [C.c_char_p, C.c_int]),
     ("aceb200_model_create", C.c_int, [C.POINTER(Desc), _VOIDPP]),
     ("aceb200_model_destroy", C.c_int, [C.c_void_p]),
@@ -91,6 +92,7 @@ SYMBOLS = [
     ("aceb200_eval_dB", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p]),
     ("aceb200_energy", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
     ("aceb200_energy_forces", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p]),
+    ("aceb200_energy_forces_dp", C.c_int, [C.c_void_p, C.POINTER(Batch), c_double_p, C.c_void_p, C.c_void_p]),
     ("aceb200_adjoint_eval_d", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p]),
     ("aceb200_structure_energy_forces", C.c_int, [C.c_void_p, C.POINTER(Structure), C.c_void_p, C.c_void_p, C.c_void_p]),
     ("aceb200_model_sizes", C.c_int, [C.c_void_p, C.POINTER(Sizes)]),
@@ -180,9 +182,10 @@ class DescHolder:
         return DescHolder(**kw)
 
 
-def make_batch(nenv: int, offsets_ptr: int, R_ptr: int, species_ptr: int, space: int) -> Batch:
+def make_batch(nenv: int, offsets_ptr: int, R_ptr: int, species_ptr: int, space: int, nJ: int = 0) -> Batch:
     b = Batch()
     b.nenv = int(nenv)
+    b.nJ = int(nJ)
     b.offsets = C.cast(C.c_void_p(offsets_ptr), c_int64_p)
     b.R = C.cast(C.c_void_p(R_ptr), c_double_p)
     b.species = C.cast(C.c_void_p(species_ptr or None), c_int32_p)

@@ -94,8 +94,9 @@ class B200Batch:
         return x.data_ptr() if self.device else x.ctypes.data
 
     def c_batch(self) -> L.Batch:
+        # nJ = len(R): known on the host even for a device-resident batch, so that the library need not read offsets back
         return L.make_batch(self.nenv, self._ptr(self.offsets), self._ptr(self.R), self._ptr(self.species),
-                            L.DEVICE if self.device else L.HOST)
+                            L.DEVICE if self.device else L.HOST, self.nJ)
 
     def empty(self, shape, complex_=False):
         if self.device:
@@ -131,6 +132,11 @@ class Handle:
                 self.ptr = C.c_void_p()
         except Exception:
             pass
+
+    def set_devices(self, devices):
+        """Evaluate HOST batches on these CUDA devices (must include the handle's own): aceb200_set_devices."""
+        d = np.ascontiguousarray(devices, dtype=np.int32)
+        L.check(self.lib.aceb200_set_devices(self.ptr, len(d), d.ctypes.data_as(L.c_int32_p)))
 
     def set_stream(self, stream_ptr: int):
         L.check(self.lib.aceb200_set_stream(self.ptr, C.c_void_p(stream_ptr)))
@@ -228,6 +234,21 @@ class Handle:
         self._call("aceb200_energy_forces", b, E, G)
         return E, G
 
+
+    def energy_forces_dp(self, b: B200Batch, dp):
+        """_rrule_evaluate(dp::SVector, model, cfg) (src/evaluator.jl:161-200): (E, sum_p dp[p] * grad of property p);
+        the gradient has shape (sum J, 3, ncomp)."""
+        dp = np.ascontiguousarray(dp, dtype=np.float64)
+        if dp.shape != (self.s.nprop,):
+            raise ValueError("dp must have one entry per property")
+        E = b.empty((b.nenv, self.s.nprop, self.s.ncomp), not self.s.symreal)
+        G = b.empty((b.nJ, 3, self.s.ncomp), not self.s.symreal)
+        if b.device:
+            self.use_current_torch_stream()
+        cb = b.c_batch()
+        L.check(self.lib.aceb200_energy_forces_dp(self.ptr, C.byref(cb), dp.ctypes.data_as(L.c_double_p),
+                                                  C.c_void_p(_out_ptr(E)), C.c_void_p(_out_ptr(G))))
+        return E, G
 
     def structure_energy_forces(self, st, virial: bool = True, E=None, F=None, W=None):
         """aceb200_structure_energy_forces: (Esite [natoms][nprop][ncomp], F [natoms][nprop][3][ncomp], W [nprop][3][3] or None).
@@ -440,6 +461,15 @@ class LinearACEModel:
             G = G[:, 0]
         return self._shape_val(E, single), G
 
+    def rrule_evaluate(self, dp, cfg):
+        """``_rrule_evaluate(dp, model, cfg)`` (src/evaluator.jl:161-200): the pullback of `evaluate` with respect to the
+        configuration for the output cotangent ``dp`` (one number per property): (J, 3[, ncomp])."""
+        b, _ = _as_batch(self, cfg)
+        h = self.evaluator.handle
+        dp = np.atleast_1d(np.asarray(dp, dtype=np.float64))
+        _, G = h.energy_forces_dp(b, dp)
+        return G[..., 0] if h.s.ncomp == 1 else G
+
     def energy_forces_virial(self, st, virial: bool = True):
         """JuLIP's energy / forces / virial of a whole structure (``B200Structure``) in one call: site energies
         (natoms[, nprop]), forces (natoms[, nprop], 3), virial ([nprop, ]3, 3)."""
@@ -470,6 +500,10 @@ class LinearACEModel:
 
 def grad_config(model: LinearACEModel, cfg):
     return model.grad_config(cfg)
+
+
+def rrule_evaluate(dp, model: LinearACEModel, cfg):
+    return model.rrule_evaluate(dp, cfg)
 
 
 def grad_params(model: LinearACEModel, cfg):

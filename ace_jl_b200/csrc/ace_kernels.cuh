@@ -626,6 +626,7 @@ __global__ void __launch_bounds__(32) k_adjoint(const AdjointParams p)
 // sum_a A_a dF_nu/dA_a = nu F_nu.
 constexpr unsigned kSegEnd = 8, kTgtEnd = 16, kTgtNeg = 32, kTgtOdd = 64, kSlotEnd = 128;
 constexpr unsigned kGroupEnd = 0x4000u;     // leaf code bit 14 (grouped form)
+constexpr unsigned kSubEnd = 0x4000u;       // second code word bit 14 (two-level grouped form, NF == 3)
 constexpr int kBlkLeaves = 4;               // leaves per block
 constexpr int kStreamWarps = 12;            // most warps a CTA of k_adjoint_stream can have (StreamGeom::NW); each walks its own
                                             // sub-stream over the same A tile
@@ -801,8 +802,9 @@ __global__ void __launch_bounds__(32 * StreamGeom<NF, PB, CW>::NW, (PB == 1 && !
         double E[PB][EPL];
         c2 D[PB][EPL], S[PB][EPL];
         c2 Tg[EPL];                      // GR: sum of w * (other factors) over the current group
+        c2 Ug[EPL];                      // GR, order 4: the same over the current sub-group
 #pragma unroll
-        for (int j = 0; j < EPL; ++j) Tg[j] = c2{0.0, 0.0};
+        for (int j = 0; j < EPL; ++j) { Tg[j] = c2{0.0, 0.0}; Ug[j] = c2{0.0, 0.0}; }
 #pragma unroll
         for (int q = 0; q < PB; ++q)
 #pragma unroll
@@ -845,6 +847,48 @@ __global__ void __launch_bounds__(32 * StreamGeom<NF, PB, CW>::NW, (PB == 1 && !
 #pragma unroll
                 for (int k = 0; k < kBlkLeaves; ++k) {
                     const unsigned c = code[k];
+                    if (GR && NF == 3) {
+                        // Two-level (Horner) form for correlation order 4: leaves are grouped by a shared factor a1 and,
+                        // inside a group, sub-grouped by a second shared factor a2:
+                        //     U += w * a3^{c3}                     per leaf        (one load, two FMAs)
+                        //     T += a2^{c2} * U,  U = 0             per sub-group   (kSubEnd, bit 14 of the second code word)
+                        //     S += a1^{c1} * T,  T = 0             per group       (kGroupEnd)
+                        // instead of one three-factor product per leaf.  Shared sub-products are formed once -- what the
+                        // reference's (disabled) recursive graph evaluator does (src/grapheval.jl; src/linearmodel.jl:50-51),
+                        // here in the order the stream is walked, with no intermediate storage.  Leaves of order 2 and 3 use the
+                        // same form with the slot of ones as the missing factors.
+                        const unsigned o3 = (code2[k] & 0x3fffu) << RSH, m3 = (code2[k] & 0x8000u) << 16;
+                        const double w = wb[k];
+#pragma unroll
+                        for (int j = 0; j < EPL; ++j) {
+                            c2 a3 = lds_c2(Ab + 512 * j, o3);
+                            a3.y = xor_hi(a3.y, m3);
+                            Ug[j].x += w * a3.x; Ug[j].y += w * a3.y;
+                        }
+                        if (code2[k] & kSubEnd) {
+                            const unsigned o2 = ((c >> 16) & 0x3fffu) << RSH, m2 = c & 0x80000000u;
+#pragma unroll
+                            for (int j = 0; j < EPL; ++j) {
+                                c2 a = lds_c2(Ab + 512 * j, o2);
+                                a.y = xor_hi(a.y, m2);
+                                Tg[j].x += a.x * Ug[j].x - a.y * Ug[j].y;
+                                Tg[j].y += a.x * Ug[j].y + a.y * Ug[j].x;
+                                Ug[j] = c2{0.0, 0.0};
+                            }
+                        }
+                        if (c & kGroupEnd) {
+                            const unsigned o1 = (c & 0x3fffu) << RSH, m1 = (c & 0x8000u) << 16;
+#pragma unroll
+                            for (int j = 0; j < EPL; ++j) {
+                                c2 a = lds_c2(Ab + 512 * j, o1);
+                                a.y = xor_hi(a.y, m1);
+                                S[0][j].x += a.x * Tg[j].x - a.y * Tg[j].y;
+                                S[0][j].y += a.x * Tg[j].y + a.y * Tg[j].x;
+                                Tg[j] = c2{0.0, 0.0};
+                            }
+                        }
+                        continue;
+                    }
                     if (GR) {
                         // T += w * a2^{c2} [* a3^{c3} * a4^{c4}];  at the group's last leaf  S += a1^{c1} * T
                         const unsigned o2 = ((c >> 16) & 0x3fffu) << RSH, m2 = c & 0x80000000u;
@@ -1028,8 +1072,11 @@ struct BasisGeom {
     static constexpr int CS = CW ? 2 : 1;
     static constexpr int CWORDS = (NFAC <= 2) ? 1 : 2;                   // code words per leaf
     static constexpr int QB = CWORDS + 2 * NCH * CS;                     // uint4 per block (4 leaves)
-    static constexpr int KB = (QB * 16 >= 512) ? 2 : ((QB * 16 >= 256) ? 4 : ((QB * 16 >= 128) ? 8 : 16));   // blocks per ring chunk
+    static constexpr int KB = (QB * 16 >= 1024) ? 1 : (QB * 16 >= 512) ? 2 : ((QB * 16 >= 256) ? 4 : ((QB * 16 >= 128) ? 8 : 16));   // blocks per ring chunk (~1 KB)
     static constexpr int CH = KB * QB;                                   // uint4 per chunk
+    static constexpr int NSLOT = 4;                                      // ring slots: three chunks in flight ahead of the one being read (a
+                                                                         // two-slot ring left the L2 latency of the ~1 KB chunks exposed: the
+                                                                         // mbarrier wait was the top stall of the 9- and 16-channel streams)
     static constexpr int ROWS = (NCH >= 9) ? 1 : (16 + NCH - 1) / NCH;   // rows staged per flush (>= 72 contiguous bytes per environment)
     static constexpr int W = ROWS * NCH;                                 // doubles staged per environment
     static constexpr int WP = W | 1;                                     // odd pitch: conflict-free staging
@@ -1052,25 +1099,25 @@ template <int NFAC, int NCH, bool CW, int EPL>
 __global__ void __launch_bounds__((EPL == 2 && NCH >= 9) ? 384 : 32 * kBasisMaxWarps, 1) k_basis_stream(const BasisParams p)
 {
     typedef BasisGeom<NFAC, NCH, CW> G;
-    constexpr int CS = G::CS, CH = G::CH, QB = G::QB, KB = G::KB, W = G::W, WP = G::WP;
+    constexpr int CS = G::CS, CH = G::CH, QB = G::QB, KB = G::KB, W = G::W, WP = G::WP, NSLOT = G::NSLOT;
     constexpr int TW = 32 * EPL;                                        // environments per tile
     constexpr int RSH = (EPL == 1) ? 9 : 10;                            // log2 of the tile row pitch in bytes
     const int NW = p.nw;
     ACE_DYN_SMEM(c2, As);                                               // [nS + 1][TW]; slot nS holds 1
-    uint4* rings = reinterpret_cast<uint4*>(As + (size_t)(p.nS + 1) * TW);   // [NW][2][CH]
-    double* stg_all = reinterpret_cast<double*>(rings + (size_t)NW * 2 * CH);  // [NW][TW][WP]
+    uint4* rings = reinterpret_cast<uint4*>(As + (size_t)(p.nS + 1) * TW);   // [NW][NSLOT][CH]
+    double* stg_all = reinterpret_cast<double*>(rings + (size_t)NW * NSLOT * CH);  // [NW][TW][WP]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint4* ring = rings + (size_t)warp * 2 * CH;
+    uint4* ring = rings + (size_t)warp * NSLOT * CH;
     double* stg = stg_all + (size_t)warp * TW * WP;
 #if ACEB200_TMA
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(stg_all + (size_t)NW * TW * WP);   // [1 + 2 NW]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(stg_all + (size_t)NW * TW * WP);   // [1 + NSLOT NW]
     unsigned long long* barA = bars;
-    unsigned long long* barR = bars + 1 + 2 * warp;
+    unsigned long long* barR = bars + 1 + NSLOT * warp;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 1 + 2 * NW; ++i) mbar_init(bars + i, 1);
+        for (int i = 0; i < 1 + NSLOT * NW; ++i) mbar_init(bars + i, 1);
         fence_barrier_init();
     }
-    unsigned phA = 0, phR0 = 0, phR1 = 0;
+    unsigned phA = 0, phR = 0;                  // bit s of phR: parity the next wait on ring slot s expects
 #endif
     if (warp == 0) {
 #pragma unroll
@@ -1089,13 +1136,11 @@ __global__ void __launch_bounds__((EPL == 2 && NCH >= 9) ? 384 : 32 * kBasisMaxW
             mbar_expect_tx(barA, (unsigned)(p.nS * TW * sizeof(c2)));
             for (int s = 0; s < p.nS; ++s) bulk_g2s(As + s * TW, p.Ac + (size_t)s * p.ldA + tile * TW, TW * sizeof(c2), barA);
         }
-        if (lane == 0 && nchw > 0) {
+        if (lane == 0) {
             fence_proxy_async();
-            mbar_expect_tx(barR, CH * sizeof(uint4));
-            bulk_g2s(ring, stream, CH * sizeof(uint4), barR);
-            if (nchw > 1) {
-                mbar_expect_tx(barR + 1, CH * sizeof(uint4));
-                bulk_g2s(ring + CH, stream + CH, CH * sizeof(uint4), barR + 1);
+            for (int c = 0; c < NSLOT - 1 && c < nchw; ++c) {
+                mbar_expect_tx(barR + c, CH * sizeof(uint4));
+                bulk_g2s(ring + c * CH, stream + (size_t)c * CH, CH * sizeof(uint4), barR + c);
             }
         }
         mbar_wait(barA, phA);
@@ -1105,7 +1150,7 @@ __global__ void __launch_bounds__((EPL == 2 && NCH >= 9) ? 384 : 32 * kBasisMaxW
 #pragma unroll
             for (int j = 0; j < EPL; ++j) As[s * TW + lane + 32 * j] = p.Ac[(size_t)s * p.ldA + tile * TW + lane + 32 * j];
         }
-        for (int c = 0; c < 2 && c < nchw; ++c)
+        for (int c = 0; c < NSLOT - 1 && c < nchw; ++c)
             for (int k = lane; k < CH; k += 32) ring[c * CH + k] = __ldg(stream + (size_t)c * CH + k);
         __syncthreads();
 #endif
@@ -1136,12 +1181,23 @@ __global__ void __launch_bounds__((EPL == 2 && NCH >= 9) ? 384 : 32 * kBasisMaxW
             pos = 0;
         };
         for (int ch = 0; ch < nchw; ++ch) {
-            const bool havepre = ch + 2 < nchw;
+            const int slot = ch % NSLOT;
+            // the slot chunk ch - 1 occupied is free (every lane passed the __syncwarp that ended it): refill it with
+            // chunk ch + NSLOT - 1, three chunks ahead of the one about to be read
+            const int pre = ch + NSLOT - 1, pslot = pre % NSLOT;
 #if ACEB200_TMA
-            if (ch & 1) { mbar_wait(barR + 1, phR1); phR1 ^= 1u; }
-            else { mbar_wait(barR, phR0); phR0 ^= 1u; }
+            if (pre < nchw && lane == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(barR + pslot, CH * sizeof(uint4));
+                bulk_g2s(ring + pslot * CH, stream + (size_t)pre * CH, CH * sizeof(uint4), barR + pslot);
+            }
+            mbar_wait(barR + slot, (phR >> slot) & 1u);
+            phR ^= 1u << slot;
+#else
+            if (pre < nchw) for (int k = lane; k < CH; k += 32) ring[pslot * CH + k] = __ldg(stream + (size_t)pre * CH + k);
+            __syncwarp();
 #endif
-            const uint4* rb = ring + (ch & 1) * CH;
+            const uint4* rb = ring + slot * CH;
             const int nb = (nblkw - ch * KB < KB) ? nblkw - ch * KB : KB;
             // One leaf per trip and NOT unrolled: the body (product + NCH channel updates for EPL environments + the
             // row-end path with its flush) is ~100-250 instructions; unrolled four times it overflowed the instruction
@@ -1195,16 +1251,6 @@ __global__ void __launch_bounds__((EPL == 2 && NCH >= 9) ? 384 : 32 * kBasisMaxW
                 }
             }
             __syncwarp();            // every lane is done reading this ring slot
-#if ACEB200_TMA
-            if (havepre && lane == 0) {
-                fence_proxy_async();
-                mbar_expect_tx(barR + (ch & 1), CH * sizeof(uint4));
-                bulk_g2s(ring + (ch & 1) * CH, stream + (size_t)(ch + 2) * CH, CH * sizeof(uint4), barR + (ch & 1));
-            }
-#else
-            if (havepre) for (int k = lane; k < CH; k += 32) ring[(ch & 1) * CH + k] = __ldg(stream + (size_t)(ch + 2) * CH + k);
-            __syncwarp();
-#endif
         }
         if (pos > 0) flush();
         __syncthreads();             // the A tile is free for the next tile's copies

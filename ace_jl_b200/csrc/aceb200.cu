@@ -7,9 +7,15 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <functional>
 #include <map>
+#include <atomic>
+#include <condition_variable>
+#include <memory>
 #include <mutex>
+#include <shared_mutex>
+#include <thread>
 #include <new>
 #include <string>
 #include <tuple>
@@ -67,7 +73,7 @@ constexpr int kLanes = 4;
 
 struct Lane {
     DevBuf ws_Ac, ws_Dt, ws_E, ws_G, ws_A, ws_AA, ws_dA, ws_dAA, ws_out;
-    DevBuf in_off, in_R, in_sp, in_w, ws_Aw, ws_A2, ws_part;
+    DevBuf in_off, in_R, in_sp, in_w, ws_Aw, ws_A2;
     cudaStream_t stream = nullptr;       // the stream this lane currently launches on
     cudaStream_t own_stream = nullptr;   // private non-blocking stream (host-batch pipeline)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
@@ -75,7 +81,7 @@ struct Lane {
     bool timed_ef = false;
     void release()
     {
-        DevBuf* bufs[] = {&ws_Ac, &ws_Dt, &ws_E, &ws_G, &ws_A, &ws_AA, &ws_dA, &ws_dAA, &ws_out, &in_off, &in_R, &in_sp, &in_w, &ws_Aw, &ws_A2, &ws_part};
+        DevBuf* bufs[] = {&ws_Ac, &ws_Dt, &ws_E, &ws_G, &ws_A, &ws_AA, &ws_dA, &ws_dAA, &ws_out, &in_off, &in_R, &in_sp, &in_w, &ws_Aw, &ws_A2};
         for (DevBuf* b : bufs) b->release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -84,6 +90,37 @@ struct Lane {
         if (own_stream) cudaStreamDestroy(own_stream);
     }
 };
+
+// Per-call state.  Evaluation calls on one handle may run concurrently from several host threads (the reference's
+// per-thread pools, src/utils/pools.jl:44-75): each call leases a context -- workspaces, pipeline lanes with their
+// streams and events, an error flag -- from the handle's pool (created on demand) and returns it when it is done.
+// The device tables are shared and read-only; set_params takes the handle exclusively.
+struct Ctx {
+    Lane lanes[kLanes];
+    DevBuf ws_err;             // device int: EEMPTY / ECATEGORY / EDESC raised by kernels; zero between calls
+    int* h_err = nullptr;      // pinned host copy
+    bool in_use = false;
+    void create()
+    {
+        for (Lane& L : lanes) {
+            CU(cudaEventCreate(&L.ev0)); CU(cudaEventCreate(&L.ev1)); CU(cudaEventCreate(&L.evA)); CU(cudaEventCreate(&L.evB));
+            CU(cudaStreamCreateWithFlags(&L.own_stream, cudaStreamNonBlocking));
+        }
+        ws_err.reserve(sizeof(int));
+        CU(cudaMemset(ws_err.p, 0, sizeof(int)));
+        CU(cudaMallocHost((void**)&h_err, sizeof(int)));
+        *h_err = 0;
+    }
+    void release()
+    {
+        for (Lane& L : lanes) L.release();
+        ws_err.release();
+        if (h_err) cudaFreeHost(h_err);
+        h_err = nullptr;
+    }
+};
+static thread_local Ctx* t_ctx = nullptr;     // the context the calling thread holds
+static thread_local Lane* t_cur = nullptr;    // the lane the calling thread is launching on
 
 struct StreamPass { DevBuf blocks, tinfo, w0; int pb0 = 0; };
 
@@ -116,9 +153,6 @@ struct aceb200_model {
     const ForceTile* d_force_tiles = nullptr;  // k_forces_mma column tiles (same column order)
     // k_basis_stream (fused B = A2Bmap . prod A): leaf stream per warp; depends on the tables only, not on c
     BStream bs;                                // B = A2Bmap . AA
-    // the same kernel as the energy readout of evaluate(model, cfg) (src/evaluator.jl:137-143): one pseudo-row per warp
-    // holding a share of the AA functions, weights c~ (rebuilt by set_params), channels = properties x components
-    BStream es;
     const int *d_orders = nullptr, *d_spec = nullptr;
     const int *d_csr_ptr = nullptr, *d_csr_col = nullptr;
     const c2* d_csr_val = nullptr;
@@ -137,10 +171,14 @@ struct aceb200_model {
     // per-call workspace (guarded by mu).  Three lanes: device-resident batches use lane 0 on the caller's
     // stream; host-resident batches are pipelined chunk by chunk over all lanes (H2D copy, kernels and D2H
     // copy of consecutive chunks overlap on the lanes' private streams).
-    std::mutex mu;
-    Lane lanes[kLanes];
-    Lane* cur = nullptr;
-    DevBuf ws_err;
+    std::shared_mutex params_mu;           // evaluation: shared; set_params: exclusive
+    std::mutex ctx_mu;
+    std::condition_variable ctx_cv;
+    std::vector<std::unique_ptr<Ctx>> ctxs;
+    std::mutex stat_mu;                    // last_ms / stage_ms
+    std::vector<double> c_host;            // the coefficients (for replicas on other devices)
+    std::vector<aceb200_model*> replicas;  // aceb200_set_devices: the same model on further GPUs
+    std::vector<int> devices;              // device of this handle followed by the replicas' 
     // structure path (aceb200_structure_energy_forces): inputs are copied on copy_stream, chunk by chunk, while
     // the evaluation of earlier chunks runs on the caller's stream
     std::mutex mu_s;
@@ -150,7 +188,7 @@ struct aceb200_model {
     cudaStream_t user_stream = nullptr;
     double last_ms = 0.0;
     double stage_ms[3] = {0.0, 0.0, 0.0};   // pool, adjoint, forces of the last energy(_forces) call
-    long long launches = 0;
+    std::atomic<long long> launches{0};
     int sm_count = 148;
     int smem_optin = 227 * 1024;
 };
@@ -194,7 +232,6 @@ static void fill_params(aceb200_model* m, const aceb200_desc& d)
 }
 
 static void upload_stream(aceb200_model* m, bool energy_only = false);
-static void upload_energy_stream(aceb200_model* m);
 
 // c~ and the weights that depend on it: order-0/1 weights and the leaf weights of every tree
 static void upload_weights(aceb200_model* m, const double* c)
@@ -240,7 +277,6 @@ static void upload_weights(aceb200_model* m, const double* c)
     }
     upload_stream(m);
     upload_stream(m, true);
-    upload_energy_stream(m);
 }
 
 // Host mirror of StreamGeom (ace_kernels.cuh)
@@ -385,6 +421,24 @@ static void upload_stream(aceb200_model* m, bool energy_only)
         L.sg = sg; L.aa = aa; L.mult = mult;
         return L;
     };
+    // two-level grouped form (NF == 3): group factor, sub-group factor (either may be absent: the slot of ones), leaf factor
+    auto make_leaf_nested = [&](int gkey, int skey, unsigned leafc, int aa, int mult, bool gend, bool send) {
+        unsigned slot[3] = {ONE, ONE, ONE}, cj[3] = {0u, 0u, 0u};
+        double sg = 1.0;
+        auto put = [&](int f, unsigned c) {
+            const unsigned neg = c & 1u, odd = (c >> 1) & 1u;
+            if (neg && odd) sg = -sg;
+            slot[f] = c >> 2; cj[f] = neg;
+        };
+        if (gkey >= 0) put(0, (unsigned)gkey);
+        if (skey >= 0) put(1, (unsigned)skey);
+        put(2, leafc);
+        Leaf L;
+        L.code = slot[0] | (gend ? kGroupEnd : 0u) | (cj[0] << 15) | (slot[1] << 16) | (cj[1] << 31);
+        L.code2 = slot[2] | (send ? kSubEnd : 0u) | (cj[2] << 15) | (ONE << 16);
+        L.sg = sg; L.aa = aa; L.mult = mult;
+        return L;
+    };
     // The block structure (codes, ctl, which target a tinfo record belongs to) is the same for every pass;
     // only the weights differ.  Build the structure once per sub-stream, then emit the passes.
     // energy-only: an AA function belongs to the target that is its first factor
@@ -452,17 +506,46 @@ static void upload_stream(aceb200_model* m, bool energy_only)
                             }
                             rest.swap(keepv);
                         }
+                        // the factors of each leaf of the group other than (one occurrence of) the group key
+                        std::vector<std::vector<uint16_t>> oth(grp.size());
                         for (size_t gi = 0; gi < grp.size(); ++gi) {
-                            const int i = grp[gi];
-                            const uint16_t* cd = &tr.codes[4 * (size_t)i];
-                            uint16_t ord[4] = {0, 0, 0, 0};
-                            int no = 0;
+                            const uint16_t* cd = &tr.codes[4 * (size_t)grp[gi]];
                             bool taken = false;
                             for (int f = 0; f < nf; ++f) {
                                 if (key >= 0 && !taken && cd[f] == key) { taken = true; continue; }
-                                ord[no++] = cd[f];
+                                oth[gi].push_back(cd[f]);
                             }
-                            per[nu].push_back(make_leaf_gr(key, ord, no, tr.laa[i], energy_only ? 1 : tr.lmult[i], gi + 1 == grp.size()));
+                        }
+                        if (NF == 3) {
+                            // two-level form: sub-group the group's leaves by a second shared factor (greedy, as above)
+                            std::vector<size_t> rest2(grp.size());
+                            for (size_t gi = 0; gi < grp.size(); ++gi) rest2[gi] = gi;
+                            while (!rest2.empty()) {
+                                int skey = -1;
+                                std::vector<size_t> sub, keep2;
+                                if (oth[rest2[0]].size() < 2) sub.swap(rest2);          // order 2 / 3: a single factor left, one sub-group
+                                else {
+                                    std::map<int, int> cnt;
+                                    for (size_t gi : rest2) { cnt[oth[gi][0]]++; if (oth[gi][1] != oth[gi][0]) cnt[oth[gi][1]]++; }
+                                    int bestc = 0;
+                                    for (auto& kv : cnt) if (kv.second > bestc) { bestc = kv.second; skey = kv.first; }
+                                    for (size_t gi : rest2) ((oth[gi][0] == skey || oth[gi][1] == skey) ? sub : keep2).push_back(gi);
+                                    rest2.swap(keep2);
+                                }
+                                for (size_t si = 0; si < sub.size(); ++si) {
+                                    const size_t gi = sub[si];
+                                    unsigned leafc = oth[gi][0];
+                                    if (skey >= 0) leafc = (oth[gi][0] == skey) ? oth[gi][1] : oth[gi][0];
+                                    const bool send = si + 1 == sub.size(), gend = send && rest2.empty();
+                                    per[nu].push_back(make_leaf_nested(key, skey, leafc, tr.laa[grp[gi]], energy_only ? 1 : tr.lmult[grp[gi]], gend, send));
+                                }
+                            }
+                        } else {
+                            for (size_t gi = 0; gi < grp.size(); ++gi) {
+                                uint16_t ord[4] = {0, 0, 0, 0};
+                                for (size_t f = 0; f < oth[gi].size(); ++f) ord[f] = oth[gi][f];
+                                per[nu].push_back(make_leaf_gr(key, ord, (int)oth[gi].size(), tr.laa[grp[gi]], energy_only ? 1 : tr.lmult[grp[gi]], gi + 1 == grp.size()));
+                            }
                         }
                     }
                 }
@@ -660,8 +743,8 @@ static bool pack_bstream(aceb200_model* m, std::vector<std::vector<BLeaf>>& rows
         nleaves += r.size();
     }
     auto smem_of = [&](int nw, int epl) {
-        return (size_t)(T.nS + 1) * 32 * epl * sizeof(c2) + (size_t)nw * 2 * KB * QB * 16 + (size_t)nw * 32 * epl * (W | 1) * sizeof(double)
-             + (size_t)(1 + 2 * nw) * 8;
+        return (size_t)(T.nS + 1) * 32 * epl * sizeof(c2) + (size_t)nw * 4 * KB * QB * 16 + (size_t)nw * 32 * epl * (W | 1) * sizeof(double)
+             + (size_t)(1 + 4 * nw) * 8;
     };
     // The kernel is latency-bound (dependent FP64 chains): what counts is warps per SM, so take as many as fit in shared
     // memory (and in the register file: 12 for the 9-channel, two-environment variant, which needs 168 registers).
@@ -771,51 +854,6 @@ static void upload_basis_stream(aceb200_model* m)
     pack_bstream(m, rows, nfac, nch, cw, m->bs, "basis");
 }
 
-// The energy readout E_p = Re sum_k c~_{k,p} AA_k (src/evaluator.jl:137-143) as a k_basis_stream pass: the AA functions
-// (mirror partners folded) are dealt to one pseudo-row per warp; the per-warp partial sums are added by k_sum_partials.
-// Half the FP64 work of the Euler-identity pass of k_adjoint_stream, which forms the full complex sum per channel.
-static void upload_energy_stream(aceb200_model* m)
-{
-    HostTables& T = m->T;
-    m->es.nw = 0;
-    if (getenv("ACEB200_NO_ENERGY_BSTREAM")) return;
-    if (!T.symreal || T.maxord > 4 || T.nS + 1 >= (1 << 14)) return;
-    const int nfac = std::max(1, T.maxord), P = T.P;
-    const bool cw = m->cw;
-    const int cs = cw ? 2 : 1;
-    int QB, KB, W;
-    if (!basis_geom(nfac, P, cw, QB, KB, W)) return;
-    std::vector<int> partner, psign;
-    const bool fold = !getenv("ACEB200_NO_MIRROR_FOLD");
-    if (fold) mirror_partners(T, partner, psign);
-    std::vector<BLeaf> all;
-    std::vector<char> done(T.nAA, 0);
-    for (int aa = 0; aa < T.nAA; ++aa) {
-        if (done[aa]) continue;
-        done[aa] = 1;
-        BLeaf L;
-        double sg, fy;
-        aa_codes(T, aa, L.c0, L.c1, sg, fy);
-        int pa = -1;
-        if (fold && partner[aa] >= 0 && partner[aa] != aa && !done[partner[aa]]) { pa = partner[aa]; done[pa] = 1; }
-        L.w.assign((size_t)P * cs, 0.0);
-        bool any = false;
-        for (int pch = 0; pch < P; ++pch) {
-            cplx z = m->ctilde[(size_t)aa * P + pch];
-            if (pa >= 0) z += (double)psign[aa] * std::conj(m->ctilde[(size_t)pa * P + pch]);     // Re(z' s conj(AA)) = Re(s conj(z') AA)
-            L.w[(size_t)pch * cs] = sg * z.real();
-            if (cw) L.w[(size_t)pch * cs + 1] = -sg * fy * z.imag();
-            any |= (z != cplx(0, 0));
-        }
-        if (any) all.push_back(L);
-    }
-    // one pseudo-row per warp: pack_bstream keeps at most as many warps as rows, so make 16 equal rows
-    const int nrows = kBasisMaxWarps;
-    std::vector<std::vector<BLeaf>> rows(nrows);
-    for (size_t i = 0; i < all.size(); ++i) rows[(i * nrows) / std::max<size_t>(all.size(), 1)].push_back(all[i]);
-    pack_bstream(m, rows, nfac, P, cw, m->es, "energy");
-}
-
 // one k_basis_stream launch: pooled A (ws_Ac) -> out [ne][S.nrows][S.nch]
 static bool launch_bstream(aceb200_model* m, const BStream& S, long long ne, long long ldA, double* out)
 {
@@ -826,11 +864,11 @@ static bool launch_bstream(aceb200_model* m, const BStream& S, long long ne, lon
     p.nS = T.nS; p.nw = S.nw; p.nchunks = S.nchunks;
     for (int w = 0; w < S.nw; ++w) { p.nblk[w] = S.nblk[w]; p.row0[w] = S.row0[w]; }
     p.stream = S.buf.as<uint4>();
-    p.Ac = m->cur->ws_Ac.as<c2>(); p.ldA = ldA; p.out = out; p.rowlen = (long long)S.nrows * S.nch; p.nenv = ne;
+    p.Ac = t_cur->ws_Ac.as<c2>(); p.ldA = ldA; p.out = out; p.rowlen = (long long)S.nrows * S.nch; p.nenv = ne;
     const long long ntiles = (ne + 32 * S.epl - 1) / (32 * S.epl);
     const int per_sm = std::max<int>(1, std::min<int>(2048 / (32 * p.nw), (int)((size_t)m->smem_optin / (S.smem + 1024))));
     const int grid = (int)std::min<long long>(ntiles, (long long)m->sm_count * per_sm);
-    if (!launch_basis_inst(S.nfac, S.nch, S.cw, S.epl, p, grid, S.smem, m->cur->stream)) return false;
+    if (!launch_basis_inst(S.nfac, S.nch, S.cw, S.epl, p, grid, S.smem, t_cur->stream)) return false;
     CU(cudaGetLastError());
     m->launches++;
     return true;
@@ -838,35 +876,6 @@ static bool launch_bstream(aceb200_model* m, const BStream& S, long long ne, lon
 
 // B for a chunk: out [ne][nB][ncomp] (real or complex)
 static bool launch_basis(aceb200_model* m, long long ne, long long ldA, double* out) { return launch_bstream(m, m->bs, ne, ldA, out); }
-
-// E[e][p] = sum over the pseudo-rows of the energy stream
-__global__ void k_sum_partials(long long nenv, int nrows, int P, const double* part, double* E)
-{
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nenv * P) return;
-    const long long e = t / P;
-    const int pch = (int)(t - e * P);
-    const double* src = part + (size_t)e * nrows * P + pch;
-    double acc = 0.0;
-    for (int r = 0; r < nrows; ++r) acc += src[(size_t)r * P];
-    E[t] = acc;
-}
-
-// evaluate(model, cfg) for a chunk: energies only
-static bool launch_energy_bstream(aceb200_model* m, long long ne, long long ldA)
-{
-    const BStream& S = m->es;
-    if (S.nw == 0) return false;
-    Lane& L = *m->cur;
-    L.ws_part.reserve((size_t)ne * S.nrows * S.nch * sizeof(double));
-    if (!launch_bstream(m, S, ne, ldA, L.ws_part.as<double>())) return false;
-    auto kfn = k_sum_partials;
-    const long long n = ne * S.nch;
-    ACE_LAUNCH(kfn, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, L.stream, ne, S.nrows, S.nch, (const double*)L.ws_part.as<double>(), L.ws_E.as<double>());
-    CU(cudaGetLastError());
-    m->launches++;
-    return true;
-}
 
 static void upload_tables(aceb200_model* m)
 {
@@ -1003,6 +1012,14 @@ static void validate_batch(const aceb200_batch* b)
     if (b->nenv < 0) throw ModelError(ACEB200_EDESC, "negative nenv");
     if (b->nenv > 0 && (!b->offsets || !b->R)) throw ModelError(ACEB200_EDESC, "null offsets / R");
     if (b->space != ACEB200_HOST && b->space != ACEB200_DEVICE) throw ModelError(ACEB200_EDESC, "batch.space must be HOST or DEVICE");
+    if (b->space == ACEB200_HOST && b->nenv > 0) {
+        // every offset, not only the chunk boundaries: a malformed interior offset would make the kernels read out of bounds
+        const int64_t* off = b->offsets;
+        bool ok = off[0] >= 0;
+        for (int64_t e = 0; e < b->nenv; ++e) ok &= off[e + 1] >= off[e];
+        if (!ok) throw ModelError(ACEB200_EDESC, "offsets must be non-decreasing");
+        if (b->nJ > 0 && off[b->nenv] - off[0] != b->nJ) throw ModelError(ACEB200_EDESC, "batch.nJ does not match offsets");
+    }
 }
 
 // boundary offsets for chunks of `step` environments
@@ -1013,13 +1030,13 @@ static std::vector<long long> boundary_offsets(aceb200_model* m, const aceb200_b
     if (b->space == ACEB200_HOST) {
         for (long long i = 0; i <= nb; ++i) out[i] = b->offsets[std::min(i * step, (long long)b->nenv)];
     } else {
-        m->cur->ws_out.reserve((nb + 1) * sizeof(long long));
+        t_cur->ws_out.reserve((nb + 1) * sizeof(long long));
         auto kfn = k_gather_offsets;
-        ACE_LAUNCH(kfn, dim3((unsigned)((nb + 1 + 127) / 128)), dim3(128), 0, m->cur->stream, reinterpret_cast<const long long*>(b->offsets), (long long)b->nenv, step, nb, m->cur->ws_out.as<long long>());
+        ACE_LAUNCH(kfn, dim3((unsigned)((nb + 1 + 127) / 128)), dim3(128), 0, t_cur->stream, reinterpret_cast<const long long*>(b->offsets), (long long)b->nenv, step, nb, t_cur->ws_out.as<long long>());
         CU(cudaGetLastError());
         m->launches++;
-        CU(cudaMemcpyAsync(out.data(), m->cur->ws_out.p, (nb + 1) * sizeof(long long), cudaMemcpyDeviceToHost, m->cur->stream));
-        CU(cudaStreamSynchronize(m->cur->stream));
+        CU(cudaMemcpyAsync(out.data(), t_cur->ws_out.p, (nb + 1) * sizeof(long long), cudaMemcpyDeviceToHost, t_cur->stream));
+        CU(cudaStreamSynchronize(t_cur->stream));
     }
     for (long long i = 0; i < nb; ++i)
         if (out[i + 1] < out[i]) throw ModelError(ACEB200_EDESC, "offsets must be non-decreasing");
@@ -1037,17 +1054,17 @@ static Staged stage_chunk(aceb200_model* m, const aceb200_batch* b, const Chunk&
         s.jbase = c.j0;
         return s;
     }
-    m->cur->in_off.reserve((ne + 1) * sizeof(long long));
-    m->cur->in_R.reserve(std::max<long long>(nj, 1) * 3 * sizeof(double));
-    CU(cudaMemcpyAsync(m->cur->in_off.p, b->offsets + c.e0, (ne + 1) * sizeof(long long), cudaMemcpyHostToDevice, m->cur->stream));
-    if (nj > 0) CU(cudaMemcpyAsync(m->cur->in_R.p, b->R + 3 * c.j0, nj * 3 * sizeof(double), cudaMemcpyHostToDevice, m->cur->stream));
-    s.off = m->cur->in_off.as<long long>();
-    s.R = m->cur->in_R.as<double>();
+    t_cur->in_off.reserve((ne + 1) * sizeof(long long));
+    t_cur->in_R.reserve(std::max<long long>(nj, 1) * 3 * sizeof(double));
+    CU(cudaMemcpyAsync(t_cur->in_off.p, b->offsets + c.e0, (ne + 1) * sizeof(long long), cudaMemcpyHostToDevice, t_cur->stream));
+    if (nj > 0) CU(cudaMemcpyAsync(t_cur->in_R.p, b->R + 3 * c.j0, nj * 3 * sizeof(double), cudaMemcpyHostToDevice, t_cur->stream));
+    s.off = t_cur->in_off.as<long long>();
+    s.R = t_cur->in_R.as<double>();
     s.species = nullptr;
     if (b->species) {
-        m->cur->in_sp.reserve(std::max<long long>(nj, 1) * sizeof(int));
-        if (nj > 0) CU(cudaMemcpyAsync(m->cur->in_sp.p, b->species + c.j0, nj * sizeof(int), cudaMemcpyHostToDevice, m->cur->stream));
-        s.species = m->cur->in_sp.as<int>();
+        t_cur->in_sp.reserve(std::max<long long>(nj, 1) * sizeof(int));
+        if (nj > 0) CU(cudaMemcpyAsync(t_cur->in_sp.p, b->species + c.j0, nj * sizeof(int), cudaMemcpyHostToDevice, t_cur->stream));
+        s.species = t_cur->in_sp.as<int>();
     }
     s.jbase = c.j0;
     return s;
@@ -1071,7 +1088,7 @@ static bool launch_pool_mma(aceb200_model* m, const BatchDev& B, long long nJ, l
     if (off || T.nQ != 1 || B.species || m->n_pool_tiles == 0) return false;
     PoolMmaParams p;
     p.rp = m->rp; p.ap = m->ap; p.B = B;
-    p.Ac = m->cur->ws_Ac.as<c2>(); p.ldA = ldA; p.errflag = m->ws_err.as<int>();
+    p.Ac = t_cur->ws_Ac.as<c2>(); p.ldA = ldA; p.errflag = t_ctx->ws_err.as<int>();
     p.tiles = m->d_pool_tiles; p.ntiles = m->n_pool_tiles;
     p.nP = (T.Lused + 1) * (T.Lused + 2) / 2;
     // environments per CTA: a multiple of the whole environments one 128-row sub-tile holds, so that the last
@@ -1083,7 +1100,7 @@ static bool launch_pool_mma(aceb200_model* m, const BatchDev& B, long long nJ, l
     const size_t smem = (size_t)kMmaPitch * (2 * p.nP + m->rp.N) * sizeof(double) + (size_t)p.ntiles * sizeof(PoolTile)
                       + (kPoolTEmax + 1) * sizeof(int);
     if (smem > (size_t)m->smem_optin) return false;
-    launch_pool_mma_inst(m->NMAX, p.ap.L <= kStaticL, p, (unsigned)((B.nenv + p.TE - 1) / p.TE), smem, m->cur->stream);
+    launch_pool_mma_inst(m->NMAX, p.ap.L <= kStaticL, p, (unsigned)((B.nenv + p.TE - 1) / p.TE), smem, t_cur->stream);
     CU(cudaGetLastError());
     m->launches++;
     return true;
@@ -1095,7 +1112,7 @@ static void launch_pool(aceb200_model* m, const BatchDev& B, long long nJ, long 
     if (launch_pool_mma(m, B, nJ, ldA)) return;
     PoolParams p;
     p.rp = m->rp; p.ap = m->ap; p.C = m->C; p.B = B;
-    p.Ac = m->cur->ws_Ac.as<c2>(); p.ldA = ldA; p.errflag = m->ws_err.as<int>();
+    p.Ac = t_cur->ws_Ac.as<c2>(); p.ldA = ldA; p.errflag = t_ctx->ws_err.as<int>();
     if (m->n_pool_blk > kPoolThreads * kPoolBItems || T.nS >= 0xffff || T.nQ > 0xffff)
         throw ModelError(ACEB200_EUNSUPPORTED, "one-particle basis too large for k_pool (more than 256 slot blocks)");
     p.blk = m->d_pool_blk; p.nblk = m->n_pool_blk;
@@ -1114,7 +1131,7 @@ static void launch_pool(aceb200_model* m, const BatchDev& B, long long nJ, long 
     p.nP = (T.Lused + 1) * (T.Lused + 2) / 2;
     const size_t smem = (size_t)kPoolPitch * (p.nP * sizeof(c2) + m->rp.N * sizeof(double)) + (kPoolThreads + kPoolTEmax + 1) * sizeof(int);
     dim3 grid((unsigned)((B.nenv + p.TE - 1) / p.TE));
-    launch_pool_inst(m->NMAX, p.B.species != nullptr, p.ap.L <= kStaticL, p, grid.x, smem, m->cur->stream);
+    launch_pool_inst(m->NMAX, p.B.species != nullptr, p.ap.L <= kStaticL, p, grid.x, smem, t_cur->stream);
     CU(cudaGetLastError());
     m->launches++;
 }
@@ -1125,12 +1142,12 @@ static void launch_pool_w_t(aceb200_model* m, const PoolWParams& p, dim3 grid, s
     if (p.B.species) {
         auto kfn = k_pool_w<NMAX, true>;
         CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ACE_LAUNCH(kfn, grid, dim3(kPoolThreads), smem, m->cur->stream, p);
+        ACE_LAUNCH(kfn, grid, dim3(kPoolThreads), smem, t_cur->stream, p);
         return;
     }
     auto kfn = k_pool_w<NMAX, false>;
     CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ACE_LAUNCH(kfn, grid, dim3(kPoolThreads), smem, m->cur->stream, p);
+    ACE_LAUNCH(kfn, grid, dim3(kPoolThreads), smem, t_cur->stream, p);
 }
 
 static void launch_pool_w(aceb200_model* m, const BatchDev& B, const double* W, long long ldA)
@@ -1138,7 +1155,7 @@ static void launch_pool_w(aceb200_model* m, const BatchDev& B, const double* W, 
     HostTables& T = m->T;
     PoolWParams p;
     p.rp = m->rp; p.ap = m->ap; p.C = m->C; p.B = B; p.W = W;
-    p.Aw = m->cur->ws_Aw.as<c2>(); p.ldA = ldA; p.TE = 8;
+    p.Aw = t_cur->ws_Aw.as<c2>(); p.ldA = ldA; p.TE = 8;
     p.nP = (T.Lused + 1) * (T.Lused + 2) / 2;
     const size_t rowbytes = (size_t)2 * (p.nP * sizeof(c2) + m->rp.N * sizeof(double)), misc = (kPoolThreads + kPoolTEmax + 1) * sizeof(int);
     p.rows = kPoolThreads;
@@ -1165,7 +1182,7 @@ static void launch_adjoint_t(aceb200_model* m, const AdjointParams& p, int grid,
 {
     auto kfn = k_adjoint<PB, CW>;
     CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ACE_LAUNCH(kfn, dim3(grid), dim3(32), smem, m->cur->stream, p);
+    ACE_LAUNCH(kfn, dim3(grid), dim3(32), smem, t_cur->stream, p);
 }
 
 static void launch_adjoint(aceb200_model* m, long long nenv, long long ldA, bool want_D)
@@ -1177,7 +1194,6 @@ static void launch_adjoint(aceb200_model* m, long long nenv, long long ldA, bool
         const long long ntiles = (nenv + 32 * m->stream_epl - 1) / (32 * m->stream_epl);
         const int per_sm = std::max<int>(1, std::min<int>(8, (int)((size_t)m->smem_optin / (smem + 1024))));
         const int grid = (int)std::min<long long>(ntiles, (long long)m->sm_count * per_sm);
-        if (!want_D && launch_energy_bstream(m, nenv, ldA)) return;          // energy only: the readout pass of k_basis_stream
         const bool eo = !want_D && m->e_stream_chunks > 0;       // energy only: the short stream
         for (const StreamPass& sp : (eo ? m->e_passes : m->passes)) {
             StreamParams p;
@@ -1186,8 +1202,8 @@ static void launch_adjoint(aceb200_model* m, long long nenv, long long ldA, bool
             for (int w = 0; w < kStreamWarps; ++w) p.nblk[w] = eo ? m->e_stream_nblk[w] : m->stream_nblk[w];
             p.P = T.P; p.pb0 = sp.pb0;
             p.stream = sp.blocks.as<uint4>(); p.ctl = (eo ? m->e_ctl : m->d_ctl).as<unsigned>(); p.tinfo = sp.tinfo.as<uint4>(); p.w0 = sp.w0.as<double>();
-            p.Ac = m->cur->ws_Ac.as<c2>(); p.ldA = ldA; p.Dt = m->cur->ws_Dt.as<c2>(); p.E = m->cur->ws_E.as<double>(); p.nenv = nenv;
-            launch_stream_inst(m->stream_nf, m->stream_pb, m->cw, m->stream_epl, p, grid, smem, m->cur->stream);
+            p.Ac = t_cur->ws_Ac.as<c2>(); p.ldA = ldA; p.Dt = t_cur->ws_Dt.as<c2>(); p.E = t_cur->ws_E.as<double>(); p.nenv = nenv;
+            launch_stream_inst(m->stream_nf, m->stream_pb, m->cw, m->stream_epl, p, grid, smem, t_cur->stream);
             CU(cudaGetLastError());
             m->launches++;
         }
@@ -1199,7 +1215,7 @@ static void launch_adjoint(aceb200_model* m, long long nenv, long long ldA, bool
     p.slot_pos = m->d_slot_pos; p.slot_neg = m->d_slot_neg; p.code = m->d_code;
     p.w1 = m->d_w1.as<double>(); p.w0 = m->d_w0.as<double>();
     for (int nu = 2; nu <= T.maxord; ++nu) p.list[nu] = m->list[nu];
-    p.Ac = m->cur->ws_Ac.as<c2>(); p.ldA = ldA; p.Dt = m->cur->ws_Dt.as<c2>(); p.E = m->cur->ws_E.as<double>(); p.nenv = nenv;
+    p.Ac = t_cur->ws_Ac.as<c2>(); p.ldA = ldA; p.Dt = t_cur->ws_Dt.as<c2>(); p.E = t_cur->ws_E.as<double>(); p.nenv = nenv;
     size_t smem = (size_t)T.nS * 32 * sizeof(c2);
     if (smem > (size_t)m->smem_optin)
         throw ModelError(ACEB200_EUNSUPPORTED, "one-particle basis too large for the shared-memory tile of k_adjoint");
@@ -1230,7 +1246,7 @@ static bool launch_forces_mma(aceb200_model* m, const BatchDev& B, long long nJ,
     if (!on || T.P != 1 || T.nQ != 1 || B.species || m->n_pool_tiles == 0) return false;
     ForceMmaParams p;
     p.rp = m->rp; p.ap = m->ap; p.B = B;
-    p.Dt = m->cur->ws_Dt.as<c2>(); p.ldA = ldA; p.nS = T.nS; p.dpitch = T.nS | 1; p.G = G;
+    p.Dt = t_cur->ws_Dt.as<c2>(); p.ldA = ldA; p.nS = T.nS; p.dpitch = T.nS | 1; p.G = G;
     p.tiles = m->d_force_tiles; p.ntiles = m->n_pool_tiles;
     p.nP = (T.Lused + 1) * (T.Lused + 2) / 2;
     const double Jbar = std::max(1.0, (double)nJ / (double)std::max<long long>(1, B.nenv));
@@ -1240,20 +1256,39 @@ static bool launch_forces_mma(aceb200_model* m, const BatchDev& B, long long nJ,
     const size_t smem = (size_t)kMmaPitch * (2 * m->rp.N + 3 * p.nP + 2 * (T.Lused + 1) + 9) * sizeof(double)
                       + (size_t)kFmmaEnvs * p.dpitch * sizeof(c2) + (size_t)p.ntiles * sizeof(ForceTile) + (kForceTEmax + 1) * sizeof(int);
     if (smem > (size_t)m->smem_optin) return false;
-    launch_forces_mma_inst(m->NMAX, p.ap.L <= kStaticL, p, (unsigned)((B.nenv + p.TE - 1) / p.TE), smem, m->cur->stream);
+    launch_forces_mma_inst(m->NMAX, p.ap.L <= kStaticL, p, (unsigned)((B.nenv + p.TE - 1) / p.TE), smem, t_cur->stream);
     CU(cudaGetLastError());
     m->launches++;
     return true;
 }
 
-static void launch_forces(aceb200_model* m, const BatchDev& B, long long nJ, long long ldA, double* G)
+// D2[s][comp][e] = sum_prop dp[prop] * D[s][prop * ncomp + comp][e]: the pullback of _rrule_evaluate(dp::SVector, ...)
+// (src/evaluator.jl:183, contract(dp, c~)) applied after the adjoint pass, so that ONE force field is assembled
+struct DpVec { double v[32]; };
+__global__ void k_contract_D(int nS, int nprop, int ncomp, long long ldA, long long nenv, DpVec dp, const c2* D, c2* D2)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int sc = blockIdx.y, s = sc / ncomp, comp = sc - s * ncomp;
+    if (e >= nenv) return;
+    c2 acc = c2{0.0, 0.0};
+    for (int pr = 0; pr < nprop; ++pr) {
+        const c2 d = D[((size_t)s * nprop * ncomp + pr * ncomp + comp) * ldA + e];
+        acc.x += dp.v[pr] * d.x; acc.y += dp.v[pr] * d.y;
+    }
+    D2[((size_t)s * ncomp + comp) * ldA + e] = acc;
+}
+
+// contracted == true: D~ has been contracted over the properties (k_contract_D): ncomp channels, one "property"
+static void launch_forces(aceb200_model* m, const BatchDev& B, long long nJ, long long ldA, double* G, bool contracted = false)
 {
     if (nJ == 0) return;
-    if (launch_forces_mma(m, B, nJ, ldA, G)) return;
+    if (!contracted && launch_forces_mma(m, B, nJ, ldA, G)) return;
     ForceParams p;
     p.rp = m->rp; p.ap = m->ap; p.C = m->C; p.B = B;
-    p.Dt = m->cur->ws_Dt.as<c2>(); p.ldA = ldA; p.P = m->T.P; p.nprop = m->T.nprop; p.ncomp = m->T.ncomp; p.G = G;
-    const int pb = m->PB == 1 ? 1 : (m->PB == 3 ? 3 : 2);
+    p.Dt = contracted ? t_cur->ws_A2.as<c2>() : t_cur->ws_Dt.as<c2>(); p.ldA = ldA;
+    p.P = contracted ? m->T.ncomp : m->T.P; p.nprop = contracted ? 1 : m->T.nprop; p.ncomp = m->T.ncomp; p.G = G;
+    const int pbm = contracted ? pick_pb(m->T.ncomp) : m->PB;
+    const int pb = pbm == 1 ? 1 : (pbm == 3 ? 3 : 2);
     p.dpitch = (m->T.nS * pb) | 1;
     // environments per CTA: the largest TE (within shared memory for 5 CTAs per SM, and leaving two waves of
     // CTAs) whose neighbours waste the fewest lanes of the last pass over kForceThreads
@@ -1275,7 +1310,7 @@ static void launch_forces(aceb200_model* m, const BatchDev& B, long long nJ, lon
     if (smem > (size_t)m->smem_optin)
         throw ModelError(ACEB200_EUNSUPPORTED, "one-particle basis too large for the shared-memory staging of k_forces");
     const unsigned grid = (unsigned)((B.nenv + p.TE - 1) / p.TE);
-    launch_forces_inst(m->NMAX, pb, sp, p.ap.L <= kStaticL, p, grid, smem, m->cur->stream);
+    launch_forces_inst(m->NMAX, pb, sp, p.ap.L <= kStaticL, p, grid, smem, t_cur->stream);
     CU(cudaGetLastError());
     m->launches++;
 }
@@ -1284,7 +1319,7 @@ template <int NMAX>
 static void launch_dA_t(aceb200_model* m, const dAParams& p)
 {
     auto kfn = k_dA<NMAX>;
-    ACE_LAUNCH(kfn, dim3((unsigned)((p.nJ + 127) / 128)), dim3(128), 0, m->cur->stream, p);
+    ACE_LAUNCH(kfn, dim3((unsigned)((p.nJ + 127) / 128)), dim3(128), 0, t_cur->stream, p);
 }
 
 static void launch_dA(aceb200_model* m, const BatchDev& B, long long nJ, c2* dA)
@@ -1308,29 +1343,79 @@ static void launch_dA(aceb200_model* m, const BatchDev& B, long long nJ, c2* dA)
 
 static unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
-static void check_errflag(aceb200_model* m)
+constexpr int kMaxCtx = 16;
+
+// RAII lease of a context; nested use by the same thread (run_structure -> run) shares the outer lease
+struct CtxLease {
+    aceb200_model* m;
+    bool owner = false;
+    explicit CtxLease(aceb200_model* mm) : m(mm)
+    {
+        if (t_ctx) return;
+        std::unique_lock<std::mutex> lk(m->ctx_mu);
+        for (;;) {
+            for (auto& c : m->ctxs) if (!c->in_use) { c->in_use = true; t_ctx = c.get(); break; }
+            if (t_ctx) break;
+            if ((int)m->ctxs.size() < kMaxCtx) {
+                std::unique_ptr<Ctx> c(new Ctx());
+                c->create();
+                c->in_use = true;
+                t_ctx = c.get();
+                m->ctxs.push_back(std::move(c));
+                break;
+            }
+            m->ctx_cv.wait(lk);
+        }
+        owner = true;
+        t_cur = &t_ctx->lanes[0];
+    }
+    ~CtxLease()
+    {
+        if (!owner) return;
+        if (std::uncaught_exceptions() > 0) {
+            // the call is failing: nothing of it may still be in flight or flagged when the context is leased again
+            cudaDeviceSynchronize();
+            cudaMemset(t_ctx->ws_err.p, 0, sizeof(int));
+            *t_ctx->h_err = 0;
+            for (Lane& L : t_ctx->lanes) L.busy = false;
+        }
+        { std::lock_guard<std::mutex> lk(m->ctx_mu); t_ctx->in_use = false; }
+        t_ctx = nullptr; t_cur = nullptr;
+        m->ctx_cv.notify_one();
+    }
+};
+
+static void throw_errflag(int flag)
 {
-    int flag = 0;
-    CU(cudaMemcpyAsync(&flag, m->ws_err.p, sizeof(int), cudaMemcpyDeviceToHost, m->cur->stream));
-    CU(cudaStreamSynchronize(m->cur->stream));
+    if (flag == 1) throw ModelError(ACEB200_EDESC, "offsets must be non-decreasing and within the neighbour arrays");
     if (flag == 5) throw ModelError(ACEB200_EEMPTY, "Product1pBasis can only be evaluated with non-empty configurations");
     if (flag == 6) throw ModelError(ACEB200_ECATEGORY, "species code not found in the category list");
+}
+
+// every environment of a DEVICE batch: off[e] <= off[e+1], all within [off[0], off[0] + nJ] when nJ is known
+__global__ void k_check_offsets(const long long* off, long long nenv, long long nJ, int* errflag)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nenv) return;
+    const long long a = off[e], b = off[e + 1];
+    if (b < a || a < off[0] || (nJ > 0 && b - off[0] > nJ)) atomicMax(errflag, 1);
 }
 
 // Copy `bytes` of a result to the user's buffer (host or device space).
 static void deliver(aceb200_model* m, const aceb200_batch* b, void* user, const void* dev, size_t bytes)
 {
     if (!user || bytes == 0 || user == dev) return;
-    CU(cudaMemcpyAsync(user, dev, bytes, b->space == ACEB200_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, m->cur->stream));
+    CU(cudaMemcpyAsync(user, dev, bytes, b->space == ACEB200_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, t_cur->stream));
 }
 
 // ----------------------------------------------------------------------------------------------
 // the evaluation driver
 // ----------------------------------------------------------------------------------------------
-enum Want { W_A = 1, W_AA = 2, W_B = 4, W_dA = 8, W_dAA = 16, W_dB = 32, W_E = 64, W_G = 128, W_ADJ = 256 };
+enum Want { W_A = 1, W_AA = 2, W_B = 4, W_dA = 8, W_dAA = 16, W_dB = 32, W_E = 64, W_G = 128, W_ADJ = 256, W_DP = 512 };
 
 struct Outputs {
     const double* w = nullptr;      // adjoint_EVAL_D: [sum J][3], same space as the batch
+    const double* dp = nullptr;     // W_DP: [nprop] host, the property contraction of the pullback
     double* adj = nullptr;          // adjoint_EVAL_D: [nenv][nB][ncomp] complex
     double *A = nullptr, *AA = nullptr, *B = nullptr, *dA = nullptr, *dAA = nullptr, *dB = nullptr, *E = nullptr, *G = nullptr;
 };
@@ -1369,7 +1454,9 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
         throw ModelError(ACEB200_EUNSUPPORTED, "energy / forces need a real symmetric basis (SymmetricBasis.real === real)");
     if (b->nenv == 0) return;
     CU(cudaSetDevice(m->device));
-    std::lock_guard<std::mutex> lock(m->mu);
+    std::shared_lock<std::shared_mutex> plock(m->params_mu, std::defer_lock);
+    if (!t_ctx) plock.lock();                      // (a nested call runs under its caller's lock and lease)
+    CtxLease lease(m);
     const int P = T.P, nA = T.nA, nAA = T.nAA, nB = T.nB, ncomp = T.ncomp;
     const int ca = T.pireal ? 1 : 2, cs = T.symreal ? 1 : 2;
     const bool fusedB = (want & W_B) && m->bs.nw > 0;       // B straight from the pooled A (k_basis_stream): AA never reaches HBM
@@ -1382,8 +1469,8 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
     // lanes: a device-resident batch runs on the caller's stream; a host-resident batch is pipelined
     int nlanes = host ? kLanes : 1;
     if (host) if (const char* ov = getenv("ACEB200_LANES")) nlanes = std::max(1, std::min(kLanes, atoi(ov)));
-    for (int l = 0; l < kLanes; ++l) { m->lanes[l].stream = host ? m->lanes[l].own_stream : m->user_stream; m->lanes[l].busy = false; }
-    m->cur = &m->lanes[0];
+    for (int l = 0; l < kLanes; ++l) { t_ctx->lanes[l].stream = host ? t_ctx->lanes[l].own_stream : m->user_stream; t_ctx->lanes[l].busy = false; }
+    t_cur = &t_ctx->lanes[0];
 
     // workspace bytes per environment (J-dependent parts use the batch average, bounded below)
     auto bounds = [&](long long stp) {
@@ -1395,8 +1482,15 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
         }
         return boundary_offsets(m, b, stp);
     };
-    std::vector<long long> ends = bounds(b->nenv);   // total neighbour count
-    const long long nJ_tot = ends[1] - ends[0];
+    // total neighbour count: from the host offsets, from the caller (batch.nJ, offsets[0] = 0) or -- the only case that
+    // costs a device -> host round trip before any kernel is launched -- read back from a DEVICE batch
+    long long nJ_tot, j_first = 0;
+    bool offsets_known = true;
+    if (host) { j_first = b->offsets[0]; nJ_tot = b->offsets[b->nenv] - j_first; }
+    else if (hints && hints->host_offsets) { j_first = hints->host_offsets[0]; nJ_tot = hints->host_offsets[b->nenv] - j_first; }
+    else if (b->nJ > 0) nJ_tot = b->nJ;
+    else { std::vector<long long> ends = bounds(b->nenv); j_first = ends[0]; nJ_tot = ends[1] - ends[0]; offsets_known = false; }
+    (void)offsets_known;
     const double Jav = std::max(1.0, (double)nJ_tot / (double)b->nenv);
     size_t per_env = (size_t)T.nS * 16 + 64;
     if (want & W_G) per_env += (size_t)T.nS * P * 16 + (size_t)(Jav * (4 + 24.0 * P));
@@ -1424,22 +1518,26 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
     }
     // chunk boundaries in environments (uniform; ramping the first and last chunks of a host batch down to step/8 was
     // measured and changes nothing: 23.6 ms vs 23.5 ms per 10^6 environments, the link itself is the bound)
-    std::vector<long long> bo = bounds(step);
+    std::vector<long long> bo;
+    if (step >= b->nenv) bo = {j_first, j_first + nJ_tot};          // one chunk: nothing to look up
+    else bo = bounds(step);
     std::vector<long long> eb;
     for (long long e = 0; e < b->nenv; e += step) eb.push_back(e);
     eb.push_back(b->nenv);
-
-    m->ws_err.reserve(sizeof(int));
-    if (!(hints && hints->defer_errflag)) {
-        CU(cudaMemsetAsync(m->ws_err.p, 0, sizeof(int), m->lanes[0].stream));
-        CU(cudaStreamSynchronize(m->lanes[0].stream));
+    if (!host && !(hints && hints->host_offsets)) {
+        // a DEVICE batch: its offsets are checked where they live (no synchronisation); the flag is read with the results
+        auto kfn = k_check_offsets;
+        ACE_LAUNCH(kfn, dim3((unsigned)((b->nenv + 255) / 256)), dim3(256), 0, t_ctx->lanes[0].stream,
+                   reinterpret_cast<const long long*>(b->offsets), (long long)b->nenv, nJ_tot, t_ctx->ws_err.as<int>());
+        CU(cudaGetLastError());
+        m->launches++;
     }
     double kernel_ms = 0.0;
     double stage_ms[3] = {0.0, 0.0, 0.0};
     const long long nchunks = (long long)eb.size() - 1;
     for (long long ic = 0; ic < nchunks; ++ic) {
-        Lane& L = m->lanes[ic % nlanes];
-        m->cur = &L;
+        Lane& L = t_ctx->lanes[ic % nlanes];
+        t_cur = &L;
         if (!(hints && hints->defer_errflag && !host)) harvest(m, L, kernel_ms, stage_ms);      // the lane's previous chunk must be done before its buffers are
                                                       // reused (a deferred device batch runs on one stream: stream order suffices)
         Chunk c;
@@ -1460,16 +1558,25 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
             CU(cudaEventRecord(L.evA, L.stream));
             launch_adjoint(m, ne, ldA, (want & W_G) != 0);
             CU(cudaEventRecord(L.evB, L.stream));
+            const size_t gper = (size_t)((want & W_DP) ? ncomp : P) * 3;      // doubles of gradient per neighbour
             if (want & W_G) {
-                const size_t gper = (size_t)P * 3;
                 if (!host) Gdev = o.G + (size_t)c.j0 * gper;
                 else { L.ws_G.reserve(std::max<long long>(nj, 1) * gper * sizeof(double)); Gdev = L.ws_G.as<double>(); }
-                launch_forces(m, B, nj, ldA, Gdev);
+                if (want & W_DP) {
+                    DpVec dv;
+                    for (int i = 0; i < 32; ++i) dv.v[i] = i < T.nprop ? o.dp[i] : 0.0;
+                    L.ws_A2.reserve((size_t)T.nS * ncomp * ldA * sizeof(c2));
+                    auto kfn = k_contract_D;
+                    ACE_LAUNCH(kfn, dim3(blocks_for(ne, 128), (unsigned)(T.nS * ncomp)), dim3(128), 0, L.stream, T.nS, T.nprop, ncomp, ldA, ne, dv,
+                               (const c2*)L.ws_Dt.as<c2>(), L.ws_A2.as<c2>());
+                    CU(cudaGetLastError()); m->launches++;
+                }
+                launch_forces(m, B, nj, ldA, Gdev, (want & W_DP) != 0);
             }
             CU(cudaEventRecord(L.ev1, L.stream));
             if (o.E) deliver(m, b, o.E + (size_t)c.e0 * P, L.ws_E.p, (size_t)ne * P * sizeof(double));
             if ((want & W_G) && host)
-                deliver(m, b, o.G + (size_t)c.j0 * P * 3, Gdev, (size_t)nj * P * 3 * sizeof(double));
+                deliver(m, b, o.G + (size_t)c.j0 * gper, Gdev, (size_t)nj * gper * sizeof(double));
         } else {
             // basis values / Jacobians
             c2* dA_dev = nullptr; double* AA_dev = nullptr; double* dAA_dev = nullptr;
@@ -1566,12 +1673,27 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
         }
         L.busy = true;
     }
-    if (hints && hints->defer_errflag) { for (int l = 0; l < nlanes; ++l) m->lanes[l].busy = false; }
-    else for (int l = 0; l < nlanes; ++l) harvest(m, m->lanes[l], kernel_ms, stage_ms);
-    m->cur = &m->lanes[0];
-    m->last_ms = kernel_ms;
-    for (int i = 0; i < 3; ++i) m->stage_ms[i] = stage_ms[i];
-    if (!(hints && hints->defer_errflag)) check_errflag(m);
+    t_cur = &t_ctx->lanes[0];
+    if (hints && hints->defer_errflag) { for (int l = 0; l < nlanes; ++l) t_ctx->lanes[l].busy = false; return; }
+    // One synchronisation per lane ends the call.  The error flag travels with it: for a single-stream (DEVICE) call
+    // its copy and reset are enqueued behind the kernels before that synchronisation; a pipelined HOST call reads it
+    // once every lane has finished.
+    if (!host) {
+        CU(cudaMemcpyAsync(t_ctx->h_err, t_ctx->ws_err.p, sizeof(int), cudaMemcpyDeviceToHost, t_cur->stream));
+        CU(cudaMemsetAsync(t_ctx->ws_err.p, 0, sizeof(int), t_cur->stream));
+    }
+    for (int l = 0; l < nlanes; ++l) harvest(m, t_ctx->lanes[l], kernel_ms, stage_ms);
+    if (host) {
+        CU(cudaMemcpyAsync(t_ctx->h_err, t_ctx->ws_err.p, sizeof(int), cudaMemcpyDeviceToHost, t_cur->stream));
+        CU(cudaMemsetAsync(t_ctx->ws_err.p, 0, sizeof(int), t_cur->stream));
+    }
+    CU(cudaStreamSynchronize(t_cur->stream));
+    const int flag = *t_ctx->h_err;
+    *t_ctx->h_err = 0;
+    { std::lock_guard<std::mutex> lk(m->stat_mu);
+      m->last_ms = kernel_ms;
+      for (int i = 0; i < 3; ++i) m->stage_ms[i] = stage_ms[i]; }
+    throw_errflag(flag);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1590,7 +1712,9 @@ static void run_structure(aceb200_model* m, const aceb200_structure* s, double* 
     if (s->natoms == 0) return;
     if (!s->X || !s->first || (s->npairs > 0 && !s->nbr) || !F) throw ModelError(ACEB200_EDESC, "null X / first / nbr / F");
     CU(cudaSetDevice(m->device));
-    std::lock_guard<std::mutex> lock(m->mu_s);
+    std::lock_guard<std::mutex> lock(m->mu_s);                          // the structure buffers (s_*) are per handle
+    std::shared_lock<std::shared_mutex> plock(m->params_mu);
+    CtxLease lease(m);                                                   // held across the deferred per-chunk evaluations
     const bool host = s->space == ACEB200_HOST;
     const long long na = s->natoms, np = s->npairs;
     const int P = T.P, K = P * 3;
@@ -1602,6 +1726,8 @@ static void run_structure(aceb200_model* m, const aceb200_structure* s, double* 
     std::vector<long long> cut{0};
     if (host) {
         if (s->first[0] != 0 || s->first[na] != np) throw ModelError(ACEB200_EDESC, "first[0] must be 0 and first[natoms] = npairs");
+        for (long long i = 0; i < na; ++i)
+            if (s->first[i + 1] < s->first[i]) throw ModelError(ACEB200_EDESC, "structure.first must be non-decreasing");
         const double pair_bytes = 4.0 + (s->image ? 3.0 : 0.0);
         double chunk_mb = 64.0;
         if (const char* ov = getenv("ACEB200_STRUCT_MB")) chunk_mb = std::max(0.001, atof(ov));
@@ -1664,8 +1790,7 @@ static void run_structure(aceb200_model* m, const aceb200_structure* s, double* 
         dE = Esite ? Esite : m->s_E.as<double>(); dF = F; dW = W;
     }
 
-    m->ws_err.reserve(sizeof(int));
-    CU(cudaMemsetAsync(m->ws_err.p, 0, sizeof(int), st));
+    CU(cudaMemsetAsync(t_ctx->ws_err.p, 0, sizeof(int), st));
     CU(cudaEventRecord(m->s_ev[nch + 1], st));         // the whole device-side sequence is timed as one interval
     double kernel_ms = 0.0, stage_ms[3] = {0.0, 0.0, 0.0};
     for (size_t k = 0; k < nch; ++k) {
@@ -1677,7 +1802,7 @@ static void run_structure(aceb200_model* m, const aceb200_structure* s, double* 
           CU(cudaGetLastError()); m->launches++; }
         aceb200_batch sub;
         sub.nenv = a1 - a0; sub.offsets = reinterpret_cast<const int64_t*>(dfirst + a0); sub.R = m->s_R.as<double>();
-        sub.species = species ? m->s_sp.as<int>() : nullptr; sub.space = ACEB200_DEVICE; sub._pad = 0;
+        sub.species = species ? m->s_sp.as<int>() : nullptr; sub.space = ACEB200_DEVICE; sub._pad = 0; sub.nJ = 0;
         Outputs o; o.E = dE + (size_t)a0 * P; o.G = m->s_G.as<double>();
         RunHints hints;
         hints.host_offsets = host ? reinterpret_cast<const long long*>(s->first) + a0 : nullptr;
@@ -1718,14 +1843,90 @@ static void run_structure(aceb200_model* m, const aceb200_structure* s, double* 
     }
     int eflag = 0;
     CU(cudaMemcpyAsync(&flag, m->s_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(&eflag, m->ws_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&eflag, t_ctx->ws_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemsetAsync(t_ctx->ws_err.p, 0, sizeof(int), st));
     CU(cudaStreamSynchronize(st));
     { float ms = 0.f; CU(cudaEventElapsedTime(&ms, m->s_ev[nch + 1], m->s_ev[nch + 2])); kernel_ms = ms; }
-    m->last_ms = kernel_ms;
-    for (int i = 0; i < 3; ++i) m->stage_ms[i] = stage_ms[i];
+    { std::lock_guard<std::mutex> lk(m->stat_mu);
+      m->last_ms = kernel_ms;
+      for (int i = 0; i < 3; ++i) m->stage_ms[i] = stage_ms[i]; }
     if (flag) throw ModelError(ACEB200_EDESC, "structure: neighbour or reverse-pair index out of range");
-    if (eflag == 5) throw ModelError(ACEB200_EEMPTY, "Product1pBasis can only be evaluated with non-empty configurations");
-    if (eflag == 6) throw ModelError(ACEB200_ECATEGORY, "species code not found in the category list");
+    throw_errflag(eflag);
+}
+
+// ----------------------------------------------------------------------------------------------
+// several GPUs behind one handle (aceb200_set_devices): environments are independent, so a HOST batch is cut into
+// contiguous shards balanced by neighbour count, one per device, each evaluated by a replica of the model on its own
+// host thread, streams and pinned pipeline; every shard writes its slice of the caller's buffers.  No collective is
+// involved: per-environment outputs need none, and a total energy is a host-side sum of what was just copied back.
+// ----------------------------------------------------------------------------------------------
+static aceb200_model* clone_on_device(const aceb200_model* m, int dev)
+{
+    aceb200_model* r = new aceb200_model();
+    try {
+        r->device = dev;
+        CU(cudaSetDevice(dev));
+        r->T = m->T; r->rp = m->rp; r->ap = m->ap;
+        r->NMAX = m->NMAX; r->PB = m->PB; r->Ppad = m->Ppad;
+        CU(cudaDeviceGetAttribute(&r->sm_count, cudaDevAttrMultiProcessorCount, dev));
+        CU(cudaDeviceGetAttribute(&r->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        CU(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
+        r->devices.assign(1, dev);
+        upload_tables(r);
+        upload_weights(r, m->c_host.empty() ? nullptr : m->c_host.data());
+        r->c_host = m->c_host;
+    } catch (...) { aceb200_model_destroy(r); throw; }
+    return r;
+}
+
+static void run_any(aceb200_model* m, const aceb200_batch* b, int want, const Outputs& o)
+{
+    const size_t ndev = 1 + m->replicas.size();
+    if (ndev == 1 || !b || b->space != ACEB200_HOST || b->nenv < (int64_t)(2 * ndev)) { run(m, b, want, o); return; }
+    validate_batch(b);
+    HostTables& T = m->T;
+    const int64_t* off = b->offsets;
+    const int64_t j0 = off[0], nJ = off[b->nenv] - j0;
+    std::vector<int64_t> cut(ndev + 1, b->nenv);
+    cut[0] = 0;
+    for (size_t k = 1; k < ndev; ++k) {
+        const int64_t target = j0 + (int64_t)((double)nJ * (double)k / (double)ndev);
+        int64_t e = std::lower_bound(off, off + b->nenv + 1, target) - off;
+        cut[k] = std::max(cut[k - 1], std::min<int64_t>(e, b->nenv));
+    }
+    const int ca = T.pireal ? 1 : 2, cs = T.symreal ? 1 : 2;
+    std::vector<int> codes(ndev, ACEB200_OK);
+    std::vector<std::string> msgs(ndev);
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < ndev; ++k) {
+        const int64_t e0 = cut[k], e1 = cut[k + 1];
+        if (e1 <= e0) continue;
+        aceb200_model* mk = k == 0 ? m : m->replicas[k - 1];
+        th.emplace_back([=, &codes, &msgs]() {
+            try {
+                aceb200_batch sub = *b;
+                sub.nenv = e1 - e0; sub.offsets = off + e0; sub.nJ = 0;
+                Outputs oo = o;                       // neighbour-indexed outputs (G, dA, dAA, dB, w) use absolute offsets
+                if (o.E) oo.E = o.E + (size_t)e0 * T.P;
+                if (o.A) oo.A = o.A + (size_t)e0 * T.nA * 2;
+                if (o.AA) oo.AA = o.AA + (size_t)e0 * T.nAA * ca;
+                if (o.B) oo.B = o.B + (size_t)e0 * T.nB * T.ncomp * cs;
+                if (o.adj) oo.adj = o.adj + (size_t)e0 * T.nB * T.ncomp * 2;
+                run(mk, &sub, want, oo);
+            } catch (const ModelError& e) { codes[k] = e.code; msgs[k] = e.what(); }
+            catch (const std::exception& e) { codes[k] = ACEB200_EDESC; msgs[k] = e.what(); }
+        });
+    }
+    for (std::thread& t : th) t.join();
+    double ms = 0.0, st[3] = {0.0, 0.0, 0.0};
+    for (size_t k = 0; k < ndev; ++k) {
+        aceb200_model* mk = k == 0 ? m : m->replicas[k - 1];
+        std::lock_guard<std::mutex> lk(mk->stat_mu);
+        ms = std::max(ms, mk->last_ms);
+        for (int i = 0; i < 3; ++i) st[i] = std::max(st[i], mk->stage_ms[i]);
+    }
+    { std::lock_guard<std::mutex> lk(m->stat_mu); m->last_ms = ms; for (int i = 0; i < 3; ++i) m->stage_ms[i] = st[i]; }
+    for (size_t k = 0; k < ndev; ++k) if (codes[k] != ACEB200_OK) throw ModelError(codes[k], msgs[k]);
 }
 
 // FP64 FMA throughput probe: 8 independent dependent-FMA chains per thread.  The roofline
@@ -1790,6 +1991,31 @@ int aceb200_set_device(int device)
     API_END
 }
 
+int aceb200_set_devices(aceb200_model* m, int n, const int* devices)
+{
+    API_BEGIN
+    if (!m || n < 1 || !devices) throw ModelError(ACEB200_EDESC, "set_devices: null argument or empty device list");
+    const int ndev = aceb200_device_count();
+    bool has_own = false;
+    for (int i = 0; i < n; ++i) {
+        if (devices[i] < 0 || devices[i] >= ndev) throw ModelError(ACEB200_ECUDA, "set_devices: no such CUDA device");
+        for (int k = 0; k < i; ++k) if (devices[k] == devices[i]) throw ModelError(ACEB200_EDESC, "set_devices: duplicate device");
+        has_own |= devices[i] == m->device;
+    }
+    if (!has_own) throw ModelError(ACEB200_EDESC, "set_devices: the list must contain the device the model was created on");
+    std::unique_lock<std::shared_mutex> lock(m->params_mu);
+    for (aceb200_model* r : m->replicas) aceb200_model_destroy(r);
+    m->replicas.clear();
+    m->devices.assign(1, m->device);
+    for (int i = 0; i < n; ++i) {
+        if (devices[i] == m->device) continue;
+        m->replicas.push_back(clone_on_device(m, devices[i]));
+        m->devices.push_back(devices[i]);
+    }
+    CU(cudaSetDevice(m->device));
+    API_END
+}
+
 int aceb200_last_error(char* buf, int n)
 {
     if (!buf || n <= 0) return ACEB200_EDESC;
@@ -1814,14 +2040,11 @@ int aceb200_model_create(const aceb200_desc* desc, aceb200_model** out)
         m->Ppad = ((m->T.P + m->PB - 1) / m->PB) * m->PB;
         CU(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, m->device));
         CU(cudaDeviceGetAttribute(&m->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
-        for (Lane& L : m->lanes) {
-            CU(cudaEventCreate(&L.ev0)); CU(cudaEventCreate(&L.ev1)); CU(cudaEventCreate(&L.evA)); CU(cudaEventCreate(&L.evB));
-            CU(cudaStreamCreateWithFlags(&L.own_stream, cudaStreamNonBlocking));
-        }
-        m->cur = &m->lanes[0];
+        m->devices.assign(1, m->device);
         CU(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
         upload_tables(m);
         upload_weights(m, desc->c);
+        if (desc->c) m->c_host.assign(desc->c, desc->c + (size_t)m->T.nB * m->T.nprop);
         *out = m;
     } catch (const ModelError& e) { delete m; return fail(e.code, e.what()); }
     catch (const std::bad_alloc&) { delete m; return fail(ACEB200_ENOMEM, "host out of memory"); }
@@ -1832,14 +2055,17 @@ int aceb200_model_create(const aceb200_desc* desc, aceb200_model** out)
 int aceb200_model_destroy(aceb200_model* m)
 {
     if (!m) return ACEB200_OK;
+    for (aceb200_model* r : m->replicas) aceb200_model_destroy(r);
+    m->replicas.clear();
     cudaSetDevice(m->device);
     for (DevBuf& b : m->pool) b.release();
-    m->d_w0.release(); m->d_w1.release(); m->d_ctl.release(); m->ws_err.release(); m->bs.buf.release(); m->es.buf.release();
+    m->d_w0.release(); m->d_w1.release(); m->d_ctl.release(); m->bs.buf.release();
     for (StreamPass& sp : m->passes) { sp.blocks.release(); sp.tinfo.release(); sp.w0.release(); }
     for (StreamPass& sp : m->e_passes) { sp.blocks.release(); sp.tinfo.release(); sp.w0.release(); }
     m->e_ctl.release();
     for (int nu = 0; nu <= kMaxOrdDev; ++nu) m->d_lw[nu].release();
-    for (Lane& L : m->lanes) L.release();
+    for (auto& c : m->ctxs) c->release();
+    m->ctxs.clear();
     { DevBuf* bufs[] = {&m->s_X, &m->s_first, &m->s_nbr, &m->s_img, &m->s_spc, &m->s_rev, &m->s_R, &m->s_sp, &m->s_G, &m->s_E,
                         &m->s_F, &m->s_W, &m->s_part, &m->s_err};
       for (DevBuf* b : bufs) b->release(); }
@@ -1855,8 +2081,10 @@ int aceb200_set_params(aceb200_model* m, const double* c, int64_t n)
     if (!m || !c) throw ModelError(ACEB200_EDESC, "null argument");
     if (n != (int64_t)m->T.nB * m->T.nprop) throw ModelError(ACEB200_EDESC, "set_params: expected nB*nprop coefficients");
     CU(cudaSetDevice(m->device));
-    std::lock_guard<std::mutex> lock(m->mu);
-    upload_weights(m, c);
+    { std::unique_lock<std::shared_mutex> lock(m->params_mu);       // waits for running evaluations (src/evaluator.jl:35-38 mutates in place)
+      upload_weights(m, c);
+      m->c_host.assign(c, c + n); }
+    for (aceb200_model* r : m->replicas) { const int rc = aceb200_set_params(r, c, n); if (rc != ACEB200_OK) return rc; }
     API_END
 }
 
@@ -1875,7 +2103,7 @@ int aceb200_set_stream(aceb200_model* m, void* cuda_stream)
     return ACEB200_OK;
 }
 
-int64_t aceb200_launch_count(const aceb200_model* m) { return m ? m->launches : 0; }
+int64_t aceb200_launch_count(const aceb200_model* m) { return m ? (int64_t)m->launches.load() : 0; }
 
 int aceb200_model_sizes(const aceb200_model* m, aceb200_sizes* out)
 {
@@ -1963,31 +2191,36 @@ int aceb200_measure_dmma(double* tflops)
 #define NEED(m, b) if (!(m) || !(b)) throw ModelError(ACEB200_EDESC, "null argument")
 
 int aceb200_eval_A(aceb200_model* m, const aceb200_batch* b, double* A)
-{ API_BEGIN NEED(m, b); Outputs o; o.A = A; run(m, b, W_A, o); API_END }
+{ API_BEGIN NEED(m, b); Outputs o; o.A = A; run_any(m, b, W_A, o); API_END }
 
 int aceb200_eval_AA(aceb200_model* m, const aceb200_batch* b, double* AA)
-{ API_BEGIN NEED(m, b); Outputs o; o.AA = AA; run(m, b, W_AA, o); API_END }
+{ API_BEGIN NEED(m, b); Outputs o; o.AA = AA; run_any(m, b, W_AA, o); API_END }
 
 int aceb200_eval_B(aceb200_model* m, const aceb200_batch* b, double* B)
-{ API_BEGIN NEED(m, b); Outputs o; o.B = B; run(m, b, W_B, o); API_END }
+{ API_BEGIN NEED(m, b); Outputs o; o.B = B; run_any(m, b, W_B, o); API_END }
 
 int aceb200_eval_dA(aceb200_model* m, const aceb200_batch* b, double* A, double* dA)
-{ API_BEGIN NEED(m, b); Outputs o; o.A = A; o.dA = dA; run(m, b, W_dA | (A ? W_A : 0), o); API_END }
+{ API_BEGIN NEED(m, b); Outputs o; o.A = A; o.dA = dA; run_any(m, b, W_dA | (A ? W_A : 0), o); API_END }
 
 int aceb200_eval_dAA(aceb200_model* m, const aceb200_batch* b, double* AA, double* dAA)
-{ API_BEGIN NEED(m, b); Outputs o; o.AA = AA; o.dAA = dAA; run(m, b, W_dAA | (AA ? W_AA : 0), o); API_END }
+{ API_BEGIN NEED(m, b); Outputs o; o.AA = AA; o.dAA = dAA; run_any(m, b, W_dAA | (AA ? W_AA : 0), o); API_END }
 
 int aceb200_eval_dB(aceb200_model* m, const aceb200_batch* b, double* B, double* dB)
-{ API_BEGIN NEED(m, b); Outputs o; o.B = B; o.dB = dB; run(m, b, W_dB | (B ? W_B : 0), o); API_END }
+{ API_BEGIN NEED(m, b); Outputs o; o.B = B; o.dB = dB; run_any(m, b, W_dB | (B ? W_B : 0), o); API_END }
 
 int aceb200_adjoint_eval_d(aceb200_model* m, const aceb200_batch* b, const double* w, double* out)
-{ API_BEGIN NEED(m, b); if (!w || !out) throw ModelError(ACEB200_EDESC, "null argument"); Outputs o; o.w = w; o.adj = out; run(m, b, W_ADJ, o); API_END }
+{ API_BEGIN NEED(m, b); if (!w || !out) throw ModelError(ACEB200_EDESC, "null argument"); Outputs o; o.w = w; o.adj = out; run_any(m, b, W_ADJ, o); API_END }
 
 int aceb200_energy(aceb200_model* m, const aceb200_batch* b, double* E)
-{ API_BEGIN NEED(m, b); Outputs o; o.E = E; run(m, b, W_E, o); API_END }
+{ API_BEGIN NEED(m, b); Outputs o; o.E = E; run_any(m, b, W_E, o); API_END }
 
 int aceb200_energy_forces(aceb200_model* m, const aceb200_batch* b, double* E, double* G)
-{ API_BEGIN NEED(m, b); if (!G) throw ModelError(ACEB200_EDESC, "null G"); Outputs o; o.E = E; o.G = G; run(m, b, W_E | W_G, o); API_END }
+{ API_BEGIN NEED(m, b); if (!G) throw ModelError(ACEB200_EDESC, "null G"); Outputs o; o.E = E; o.G = G; run_any(m, b, W_E | W_G, o); API_END }
+
+int aceb200_energy_forces_dp(aceb200_model* m, const aceb200_batch* b, const double* dp, double* E, double* G)
+{ API_BEGIN NEED(m, b); if (!G || !dp) throw ModelError(ACEB200_EDESC, "null G / dp");
+  if (m->T.nprop > 32) throw ModelError(ACEB200_EUNSUPPORTED, "energy_forces_dp: more than 32 properties");
+  Outputs o; o.E = E; o.G = G; o.dp = dp; run_any(m, b, W_E | W_G | W_DP, o); API_END }
 
 int aceb200_structure_energy_forces(aceb200_model* m, const aceb200_structure* s, double* Esite, double* F, double* W)
 { API_BEGIN if (!m) throw ModelError(ACEB200_EDESC, "null argument"); run_structure(m, s, Esite, F, W); API_END }

@@ -15,11 +15,11 @@ static void basis_go(const BasisParams& p, int grid, size_t smem, cudaStream_t s
 template <int NFAC>
 static bool basis_nfac(int nch, bool cw, int epl, const BasisParams& p, int grid, size_t smem, cudaStream_t st)
 {
-    // two environments per lane up to 18 accumulator pairs (9 channels, or 16 with real weights); beyond that one
-#define ACE_B(N, C) if (nch == N && cw == C) { constexpr bool E2 = (N <= 9) || (!C && N <= 16);                         \
+    // two environments per lane up to 9 channels (18 accumulators per lane); 18 channels keep one
+#define ACE_B(N, C) if (nch == N && cw == C) { constexpr bool E2 = (N <= 9);                                            \
                                                if (epl == 2 && E2) basis_go<NFAC, N, C, (E2 ? 2 : 1)>(p, grid, smem, st);  \
                                                else basis_go<NFAC, N, C, 1>(p, grid, smem, st); return true; }
-    ACE_B(1, false) ACE_B(2, false) ACE_B(3, false) ACE_B(4, false) ACE_B(8, false) ACE_B(16, false)
+    ACE_B(1, false) ACE_B(2, false)
     ACE_B(1, true) ACE_B(2, true) ACE_B(3, true) ACE_B(6, true) ACE_B(9, true) ACE_B(18, true)
 #undef ACE_B
     return false;
@@ -39,16 +39,15 @@ bool launch_basis_inst(int nfac, int nch, bool cw, int epl, const BasisParams& p
 bool basis_geom(int nfac, int nch, bool cw, int& QB, int& KB, int& W)
 {
     const int cs = cw ? 2 : 1, cwords = nfac <= 2 ? 1 : 2;
-    if (!((!cw && (nch == 1 || nch == 2 || nch == 3 || nch == 4 || nch == 8 || nch == 16))
-          || (cw && (nch == 1 || nch == 2 || nch == 3 || nch == 6 || nch == 9 || nch == 18)))) return false;
+    if (!((nch == 1 || nch == 2) || (cw && (nch == 3 || nch == 6 || nch == 9 || nch == 18)))) return false;
     if (nfac < 1 || nfac > 4) return false;
     QB = cwords + 2 * nch * cs;
-    KB = (QB * 16 >= 512) ? 2 : ((QB * 16 >= 256) ? 4 : ((QB * 16 >= 128) ? 8 : 16));
+    KB = (QB * 16 >= 1024) ? 1 : (QB * 16 >= 512) ? 2 : ((QB * 16 >= 256) ? 4 : ((QB * 16 >= 128) ? 8 : 16));
     W = (nch >= 9 ? 1 : (16 + nch - 1) / nch) * nch;
     return true;
 }
 
 // measured (config 4b, 9 complex-weight channels): one environment per lane x 16 warps beats two x 12 (3.07 vs 2.71 x 10^7 env/s)
-bool basis_epl2(int nch, bool cw) { return nch <= 6 || (!cw && nch <= 16); }
+bool basis_epl2(int nch, bool cw) { (void)cw; return nch <= 6; }
 
 }  // namespace aceb200

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ACEB200_ABI_VERSION 1
+#define ACEB200_ABI_VERSION 2
 
 /* error codes */
 #define ACEB200_OK            0
@@ -118,6 +118,9 @@ typedef struct aceb200_batch {
     const int32_t *species;     /* [offsets[nenv]] 1-based category index (val2i, src/discrete1pbasis.jl:33), or NULL */
     int32_t space;              /* ACEB200_HOST or ACEB200_DEVICE: where offsets/R/species AND the outputs live     */
     int32_t _pad;
+    int64_t nJ;                 /* total neighbour count offsets[nenv] (= length of R) if the caller knows it, else 0.  A
+                                   DEVICE batch with nJ > 0 is evaluated without any device -> host round trip before
+                                   the kernels are launched; with nJ = 0 the library reads offsets[nenv] back first.       */
 } aceb200_batch;
 
 /* ---- lifecycle -------------------------------------------------------------------------- */
@@ -126,6 +129,13 @@ typedef struct aceb200_batch {
 int aceb200_device_count(void);
 /* device used by models created afterwards from this host thread (default 0) */
 int aceb200_set_device(int device);
+/* Evaluate HOST batches of this model on several GPUs: `devices` lists n distinct CUDA devices and must contain the one
+ * the model was created on.  The tables are replicated once; every later HOST-batch call cuts the batch into n contiguous
+ * shards balanced by neighbour count, evaluates them concurrently (one host thread, stream set and copy pipeline per
+ * device) and writes each shard's slice of the caller's buffers.  DEVICE batches and structures stay on the model's own
+ * device (their memory lives there).  n = 1 with the model's device drops the replicas.  (in the
+ * reference the same effect needs `Threads.@threads` over configurations, src/utils/pools.jl:44-75.) */
+int aceb200_set_devices(aceb200_model *m, int n, const int *devices);
 /* copy `n` bytes of the calling thread's last error message */
 int aceb200_last_error(char *buf, int n);
 
@@ -172,6 +182,12 @@ int aceb200_energy(aceb200_model *m, const aceb200_batch *b, double *E);
 /* evaluate + grad_config (src/evaluator.jl:150-200): G [sum J][nprop][3][ncomp] (component fastest),
  * real if symreal else complex; E may be NULL */
 int aceb200_energy_forces(aceb200_model *m, const aceb200_batch *b, double *E, double *G);
+/* _rrule_evaluate(dp::SVector{nprop}, m, V, cfg) (src/evaluator.jl:161-200; `contract(dp, c~[iAA])` at :183; the
+ * benchmark's call, benchmark/bm_linear.jl:92-93): the pullback of a multi-property model contracted over the
+ * properties,  G [sum J][3][ncomp] = sum_p dp[p] * (gradient of property p).  The adjoint pass runs over all properties,
+ * its result is contracted on the device, and ONE force field is assembled (for 16 properties: 1/16 of the force work and
+ * of the output bytes of aceb200_energy_forces).  dp: [nprop] HOST doubles (nprop <= 32); E [nenv][nprop][ncomp] may be NULL. */
+int aceb200_energy_forces_dp(aceb200_model *m, const aceb200_batch *b, const double *dp, double *E, double *G);
 /* grad_params(m, cfg) (src/linearmodel.jl:114-123) is eval_B; grad_params_config (:127) is eval_dB. */
 /* adjoint_EVAL_D(m, cfg, w) (src/evaluator.jl:204-244; src/linearmodel.jl:133-134):
  * out_k = A2Bmap * real?( sum_t (sum_j w_j . grad phi_{v_t}(r_j)) prod_{s != t} A_{v_s} ), i.e. sum_j w_j . dB_k/dr_j

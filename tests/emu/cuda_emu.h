@@ -138,7 +138,7 @@ enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaDevAttrMultiProcesso
        cudaDevAttrMaxSharedMemoryPerBlockOptin = 97, cudaEventDefault = 0, cudaHostAllocDefault = 0 };
 inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
 inline cudaError_t cudaGetLastError() { return 0; }
-inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return 0; }
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 2; return 0; }   // two pretend devices: exercises aceb200_set_devices
 inline cudaError_t cudaSetDevice(int) { return 0; }
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
 inline cudaError_t cudaDeviceGetAttribute(int* v, int attr, int) {

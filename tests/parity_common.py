@@ -35,6 +35,10 @@ def compare_all(basis, nprop, Js, seed=7, jacobians=True, tol=TOL):
         Eo, Go = o.energy_forces(R, off, sp)
         errs["E"], errs["G"] = relerr(E, Eo), relerr(G, Go)
         errs["E_only"] = relerr(h.energy(b), Eo)
+        # the property-contracted pullback, _rrule_evaluate(dp::SVector, ...) (src/evaluator.jl:183)
+        dp = rng.standard_normal(nprop)
+        Edp, Gdp = h.energy_forces_dp(b, dp)
+        errs["E_dp"], errs["G_dp"] = relerr(Edp, Eo), relerr(Gdp, np.einsum("p,jpxc->jxc", dp, Go))
     else:   # a complex symmetric basis: values and Jacobians only; the model calls must refuse loudly
         import pytest
         from ace_jl_b200._lib import AceB200Error

@@ -124,3 +124,39 @@ def test_emulated_many_chunks(emu, monkeypatch):
     monkeypatch.setenv("ACEB200_CHUNK_ENVS", "64")
     rng = np.random.default_rng(5)
     compare_all(make_basis("inv_simple_3_6"), 1, [int(j) for j in rng.integers(1, 7, 700)], seed=23, jacobians=False)
+
+
+def test_emulated_multi_device_sharding(emu):
+    """aceb200_set_devices: a HOST batch cut into per-device shards (two pretend devices in the emulation) gives bit for
+    bit the single-device results, for environment-indexed (E, B) and neighbour-indexed (G, dB) outputs, ragged batches,
+    and errors raised inside a shard reach the caller."""
+    import numpy as np
+    import ace_jl_b200 as ace
+    from ace_jl_b200.utils import philox, rand_envs
+    from conftest import rn_of
+    basis = make_basis("inv_simple_3_6")
+    rng = philox(41)
+    c = rng.random((len(basis), 2)) - 0.5
+    h = ace.LinearACEModel(basis, c).evaluator.handle
+    Js = [3, 9, 1, 14, 7, 2, 5, 11, 6]
+    R, off, _ = rand_envs(rng, rn_of(basis), len(Js), Js)
+    b = ace.B200Batch(R, off)
+    E1, G1 = h.energy_forces(b)
+    B1, dB1 = h.eval_dB(b)
+    h.set_devices([0, 1])
+    E2, G2 = h.energy_forces(b)
+    B2, dB2 = h.eval_dB(b)
+    assert np.array_equal(E1, E2) and np.array_equal(G1, G2) and np.array_equal(B1, B2) and np.array_equal(dB1, dB2)
+    c2 = rng.random((len(basis), 2)) - 0.5
+    h.set_params(c2)                                    # reaches the replica too
+    h1 = ace.LinearACEModel(basis, c2).evaluator.handle
+    assert np.array_equal(h.energy(b), h1.energy(b))
+    off_bad = off.copy()
+    off_bad[-2] = off_bad[-1]                           # the last environment (second shard) is empty
+    with pytest.raises(_lib.AceB200Error) as ei:
+        h.energy(ace.B200Batch(R, off_bad))
+    assert ei.value.code == -5
+    with pytest.raises(_lib.AceB200Error):
+        h.set_devices([1])                              # must contain the model's own device
+    h.set_devices([0])
+    assert np.array_equal(h.energy(b), h1.energy(b))
