@@ -1288,17 +1288,25 @@ constexpr int kForceTEmax = 32;      // environments per CTA (ForceParams::TE), 
 #else
 #define ACE_DR_LOAD(p) (*reinterpret_cast<const volatile double*>(p))
 #endif
-template <int NMAX, int STRIDE>
+// REALONLY (the m = 0 columns: Y_l^0 and e^{i 0 phi} are real, and the azimuthal term carries the factor m = 0): only
+// Re u and Re v are ever used, so only Re D~ is loaded (8 bytes instead of 16) and two of the four FMAs are issued --
+// 34 of the 74 slots of config 2 (measured: 3.45 -> 3.41 ms; the kernel is issue-bound, not FP64-bound).
+template <int NMAX, int STRIDE, bool REALONLY>
 __device__ __forceinline__ void column_dot(const c2* D, int cnt, const double (&Rn)[NMAX], const double* dRs,
                                            double& ur, double& ui, double& vr, double& vi)
 {
 #define ACE_TERM(n)                                                                      \
     case (n) + 1:                                                                        \
         if ((n) < NMAX) {                                                                \
-            const c2 d = D[(size_t)(n) * STRIDE];                                        \
             const double dr = ACE_DR_LOAD(dRs + (n) * kForceThreads);                    \
-            ur += d.x * Rn[(n) < NMAX ? (n) : 0]; ui += d.y * Rn[(n) < NMAX ? (n) : 0];      \
-            vr += d.x * dr; vi += d.y * dr;                                              \
+            if (REALONLY) {                                                              \
+                const double dx = D[(size_t)(n) * STRIDE].x;                             \
+                ur += dx * Rn[(n) < NMAX ? (n) : 0]; vr += dx * dr;                      \
+            } else {                                                                     \
+                const c2 d = D[(size_t)(n) * STRIDE];                                    \
+                ur += d.x * Rn[(n) < NMAX ? (n) : 0]; ui += d.y * Rn[(n) < NMAX ? (n) : 0];  \
+                vr += d.x * dr; vi += d.y * dr;                                          \
+            }                                                                            \
         }
     switch (cnt < NMAX ? cnt : NMAX) {      // the clamp tells ptxas that the cases above NMAX are dead (-1.4 % on k_forces)
         ACE_TERM(31) ACE_TERM(30) ACE_TERM(29) ACE_TERM(28) ACE_TERM(27) ACE_TERM(26) ACE_TERM(25) ACE_TERM(24)
@@ -1368,14 +1376,20 @@ __global__ void __launch_bounds__(kForceThreads, ACE_FORCE_MINB) k_forces(const 
 #pragma unroll
                 for (int c = 0; c < PB; ++c) {
                     double ur = 0.0, ui = 0.0, vr = 0.0, vi = 0.0;
-                    column_dot<NMAX, PB>(Dj + base * PB + c, cnt, Rn, dRs, ur, ui, vr, vi);
-                    // z = u * ep ;  Re(v * ep)   (ep is real for m = 0)
-                    const double zr = (m == 0) ? ur * epr : ur * epr - ui * epi;
-                    const double zi = (m == 0) ? ui * epr : ur * epi + ui * epr;
-                    const double ve = (m == 0) ? vr * epr : vr * epr - vi * epi;
-                    S0[c] += f0 * ve;          // radial:   rhat * Re(v Y)
-                    S1[c] += f1 * zi;          // azimuth:  m Pt Im(u ep)
-                    S2[c] += dP * zr;          // polar:    dP Re(u ep)
+                    if (m == 0) {              // (compile-time in the statically unrolled walk)
+                        column_dot<NMAX, PB, true>(Dj + base * PB + c, cnt, Rn, dRs, ur, ui, vr, vi);
+                        S0[c] += f0 * (vr * epr);  // radial:   rhat * Re(v Y),  ep real
+                        S2[c] += dP * (ur * epr);  // polar:    dP Re(u ep);  the azimuthal term has the factor m = 0
+                    } else {
+                        column_dot<NMAX, PB, false>(Dj + base * PB + c, cnt, Rn, dRs, ur, ui, vr, vi);
+                        // z = u * ep ;  Re(v * ep)
+                        const double zr = ur * epr - ui * epi;
+                        const double zi = ur * epi + ui * epr;
+                        const double ve = vr * epr - vi * epi;
+                        S0[c] += f0 * ve;          // radial:   rhat * Re(v Y)
+                        S1[c] += f1 * zi;          // azimuth:  m Pt Im(u ep)
+                        S2[c] += dP * zr;          // polar:    dP Re(u ep)
+                    }
                 }
             });
             // g = rhat S0 + (1/r) [ sphi S1 + cphi cth S2,  -cphi S1 + sphi cth S2,  -sth S2 ]
