@@ -16,7 +16,7 @@ from .pibasis import PIBasis, PIBasisSpec  # noqa: F401
 from .symmbasis import SparseCSC, SymmetricBasis  # noqa: F401
 from .api import (ACEConfig, B200Batch, B200Evaluator, LinearACEModel, adjoint_EVAL_D, evaluate, evaluate_d,  # noqa: F401
                   evaluate_ed, grad_config, grad_params, grad_params_config, rrule_evaluate, set_params)
-from .structure import B200Structure, neighbourlist, reverse_pairs  # noqa: F401
+from .structure import B200Structure, neighbourlist, pack_neighbours, reverse_pairs  # noqa: F401
 from . import utils  # noqa: F401
 from . import fio  # noqa: F401
 from .fio import load_model, read_dict, save_model, write_dict  # noqa: F401

@@ -55,8 +55,11 @@ class Structure(C.Structure):
     _fields_ = [
         ("natoms", C.c_int64), ("npairs", C.c_int64), ("X", c_double_p), ("first", c_int64_p), ("nbr", c_int32_p),
         ("image", C.POINTER(C.c_int8)), ("species", c_int32_p), ("rev", c_int32_p), ("cell", C.c_double * 9),
-        ("space", C.c_int32), ("_pad", C.c_int32),
+        ("space", C.c_int32), ("flags", C.c_int32),
     ]
+
+
+NBR_PACKED = 1  # aceb200_structure.flags: ACEB200_NBR_PACKED
 
 
 class Sizes(C.Structure):

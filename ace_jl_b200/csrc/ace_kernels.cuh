@@ -2011,8 +2011,14 @@ constexpr int kPairAtoms = 32;      // centres per CTA of k_build_pairs
 struct CellDev { double c[9]; };
 
 // R_p = X[nbr_p] + S_p . cell - X[i(p)],  species_p = species[nbr_p]   for the pairs of centres [a0, a0 + na)
+// Packed neighbour words (aceb200_structure.flags & ACEB200_NBR_PACKED): bits 0..25 the neighbour index, bits 26..31 the
+// image shift, two bits per component holding S + 1 (S in {-1, 0, 1}): 4 bytes per pair over PCIe instead of 7.
+constexpr unsigned kNbrMask = 0x03ffffffu;
+__device__ __forceinline__ long long nbr_index(int w, int packed) { return packed ? (long long)((unsigned)w & kNbrMask) : (long long)w; }
+__device__ __forceinline__ int nbr_shift(int w, int k) { return (int)(((unsigned)w >> (26 + 2 * k)) & 3u) - 1; }
+
 static __global__ void k_build_pairs(long long a0, long long na, long long natoms, const long long* first, const int* nbr,
-                                     const signed char* image, const CellDev cell, const double* X, const int* spc, double* R, int* sp,
+                                     const signed char* image, int packed, const CellDev cell, const double* X, const int* spc, double* R, int* sp,
                                      int* errflag)
 {
     ACE_DYN_SMEM(long long, f);                 // [kPairAtoms + 1]
@@ -2025,11 +2031,14 @@ static __global__ void k_build_pairs(long long a0, long long na, long long natom
         int lo = 0, hi = nc;                       // centre of pair p: the last c with f[c] <= p
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (f[mid] <= p) lo = mid; else hi = mid; }
         const long long i = c0 + lo;
-        long long j = nbr[p];
+        const int wj = nbr[p];
+        long long j = nbr_index(wj, packed);
         if (j < 0 || j >= natoms) { atomicMax(errflag, 1); j = i; }
         double x = X[3 * j] - X[3 * i], y = X[3 * j + 1] - X[3 * i + 1], z = X[3 * j + 2] - X[3 * i + 2];
-        if (image) {
-            const double s0 = (double)image[3 * p], s1 = (double)image[3 * p + 1], s2 = (double)image[3 * p + 2];
+        if (image || packed) {
+            const double s0 = packed ? (double)nbr_shift(wj, 0) : (double)image[3 * p];
+            const double s1 = packed ? (double)nbr_shift(wj, 1) : (double)image[3 * p + 1];
+            const double s2 = packed ? (double)nbr_shift(wj, 2) : (double)image[3 * p + 2];
             x += s0 * cell.c[0] + s1 * cell.c[3] + s2 * cell.c[6];
             y += s0 * cell.c[1] + s1 * cell.c[4] + s2 * cell.c[7];
             z += s0 * cell.c[2] + s1 * cell.c[5] + s2 * cell.c[8];
@@ -2042,7 +2051,7 @@ static __global__ void k_build_pairs(long long a0, long long na, long long natom
 // rev[p] for the pairs of 32 centres per CTA: scan the pair list of j = nbr[p] for (neighbour i, image -S).  The table is
 // symmetric, so only one pair of each (p, rev p) couple searches -- the one whose (centre, image) is smaller than its
 // reverse's -- and writes both entries; rev is pre-set to -1 (no reverse pair) by the caller.
-static __global__ void k_find_rev(long long natoms, const long long* first, const int* nbr, const signed char* image, int* rev)
+static __global__ void k_find_rev(long long natoms, const long long* first, const int* nbr, const signed char* image, int packed, int* rev)
 {
     ACE_DYN_SMEM(long long, f);                 // [kPairAtoms + 1]
     const long long c0 = (long long)blockIdx.x * kPairAtoms;
@@ -2054,10 +2063,14 @@ static __global__ void k_find_rev(long long natoms, const long long* first, cons
         int lo = 0, hi = nc;
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (f[mid] <= p) lo = mid; else hi = mid; }
         const int i = (int)(c0 + lo);
-        const long long j = __ldg(nbr + p);
+        const int wj = __ldg(nbr + p);
+        const long long j = nbr_index(wj, packed);
         if (j < 0 || j >= natoms) continue;
         int s0 = 0, s1 = 0, s2 = 0;             // the reverse pair's image
         if (image) { s0 = -__ldg(image + 3 * p); s1 = -__ldg(image + 3 * p + 1); s2 = -__ldg(image + 3 * p + 2); }
+        if (packed) { s0 = -nbr_shift(wj, 0); s1 = -nbr_shift(wj, 1); s2 = -nbr_shift(wj, 2); }
+        // packed: the reverse pair is one exact word (neighbour i, shift -S)
+        const int wrev = (int)((unsigned)i | ((unsigned)(s0 + 1) << 26) | ((unsigned)(s1 + 1) << 28) | ((unsigned)(s2 + 1) << 30));
         // who searches: the pair with the smaller centre; for a self-image pair (i == j) the one whose image is
         // lexicographically smaller than its reverse's (a pair that is its own reverse cannot occur: S = 0 means r = 0)
         if (j < i) continue;
@@ -2071,16 +2084,18 @@ static __global__ void k_find_rev(long long natoms, const long long* first, cons
         // entry >= i and walk the (few) images of i; an unsorted list falls back to the linear scan below
         long long lo2 = __ldg(first + j), hi2 = __ldg(first + j + 1);
         const long long qb = lo2, qe = hi2;
-        while (lo2 < hi2) { const long long mid = (lo2 + hi2) >> 1; if (__ldg(nbr + mid) < i) lo2 = mid + 1; else hi2 = mid; }
-        for (long long q = lo2; q < qe && __ldg(nbr + q) == i; ++q) {
+        while (lo2 < hi2) { const long long mid = (lo2 + hi2) >> 1; if (nbr_index(__ldg(nbr + mid), packed) < i) lo2 = mid + 1; else hi2 = mid; }
+        for (long long q = lo2; q < qe && nbr_index(__ldg(nbr + q), packed) == i; ++q) {
             if (image && (__ldg(image + 3 * q) != s0 || __ldg(image + 3 * q + 1) != s1 || __ldg(image + 3 * q + 2) != s2)) continue;
+            if (packed && __ldg(nbr + q) != wrev) continue;
             found = (int)q;
             break;
         }
         if (found < 0) {
             for (long long q = qb; q < qe; ++q) {
-                if (__ldg(nbr + q) != i) continue;
+                if (nbr_index(__ldg(nbr + q), packed) != i) continue;
                 if (image && (__ldg(image + 3 * q) != s0 || __ldg(image + 3 * q + 1) != s1 || __ldg(image + 3 * q + 2) != s2)) continue;
+                if (packed && __ldg(nbr + q) != wrev) continue;
                 found = (int)q;
                 break;
             }

@@ -1709,6 +1709,9 @@ static void run_structure(aceb200_model* m, const aceb200_structure* s, double* 
     if (W && T.ncomp != 1) throw ModelError(ACEB200_EUNSUPPORTED, "the virial is defined for scalar (ncomp = 1) properties");
     if (T.has_cat && !s->species) throw ModelError(ACEB200_EDESC, "the model has a categorical basis: structure.species is required");
     if (s->npairs >= (1ll << 31)) throw ModelError(ACEB200_EUNSUPPORTED, "structure: npairs must be below 2^31");
+    const int packed = (s->flags & ACEB200_NBR_PACKED) ? 1 : 0;
+    if (packed && s->image) throw ModelError(ACEB200_EDESC, "structure: packed neighbour words carry the image shift; image must be NULL");
+    if (packed && s->natoms > (1ll << 26)) throw ModelError(ACEB200_EUNSUPPORTED, "structure: packed neighbour words address at most 2^26 atoms");
     if (s->natoms == 0) return;
     if (!s->X || !s->first || (s->npairs > 0 && !s->nbr) || !F) throw ModelError(ACEB200_EDESC, "null X / first / nbr / F");
     CU(cudaSetDevice(m->device));
@@ -1754,7 +1757,7 @@ static void run_structure(aceb200_model* m, const aceb200_structure* s, double* 
     if (host || !s->rev) m->s_rev.reserve(std::max<long long>(np, 1) * sizeof(int));
     const double* dX; const long long* dfirst; const int* dnbr; const signed char* dimg; const int* dspc; const int* drev;
     CellDev cell;
-    for (int i = 0; i < 9; ++i) cell.c[i] = s->image ? s->cell[i] : 0.0;
+    for (int i = 0; i < 9; ++i) cell.c[i] = (s->image || packed) ? s->cell[i] : 0.0;
     double *dE, *dF, *dW;
     if (host) {
         m->s_X.reserve(na * 3 * sizeof(double));
@@ -1797,7 +1800,7 @@ static void run_structure(aceb200_model* m, const aceb200_structure* s, double* 
         const long long a0 = cut[k], a1 = cut[k + 1];
         if (host) CU(cudaStreamWaitEvent(st, m->s_ev[k], 0));
         { auto kfn = k_build_pairs;
-          ACE_LAUNCH(kfn, dim3(blocks_for(a1 - a0, kPairAtoms)), dim3(128), (kPairAtoms + 1) * sizeof(long long), st, a0, a1 - a0, na, dfirst, dnbr, dimg, cell, dX, dspc,
+          ACE_LAUNCH(kfn, dim3(blocks_for(a1 - a0, kPairAtoms)), dim3(128), (kPairAtoms + 1) * sizeof(long long), st, a0, a1 - a0, na, dfirst, dnbr, dimg, packed, cell, dX, dspc,
                      m->s_R.as<double>(), species ? m->s_sp.as<int>() : (int*)nullptr, m->s_err.as<int>());
           CU(cudaGetLastError()); m->launches++; }
         aceb200_batch sub;
@@ -1816,7 +1819,7 @@ static void run_structure(aceb200_model* m, const aceb200_structure* s, double* 
         // is slower: the kernels contend for the same SMs, 21 ms vs 17 ms end to end on the benchmark structure.)
         CU(cudaMemsetAsync(m->s_rev.p, 0xff, std::max<long long>(np, 1) * sizeof(int), st));      // -1: no reverse pair
         auto kfn = k_find_rev;
-        ACE_LAUNCH(kfn, dim3(blocks_for(na, kPairAtoms)), dim3(128), (kPairAtoms + 1) * sizeof(long long), st, na, dfirst, dnbr, dimg, m->s_rev.as<int>());
+        ACE_LAUNCH(kfn, dim3(blocks_for(na, kPairAtoms)), dim3(128), (kPairAtoms + 1) * sizeof(long long), st, na, dfirst, dnbr, dimg, packed, m->s_rev.as<int>());
         CU(cudaGetLastError()); m->launches++;
         drev = m->s_rev.as<int>();
     }

@@ -36,7 +36,11 @@ class B200Structure:
     neighbour list returns them: i, j, S), species (natoms) 1-based categories, rev (npairs) int32 reverse-pair
     table (-1: none).  numpy arrays = host, CUDA torch tensors = device (cell always numpy)."""
 
-    def __init__(self, X, first, nbr, image=None, cell=None, species=None, rev=None):
+    def __init__(self, X, first, nbr, image=None, cell=None, species=None, rev=None, packed=False):
+        """``packed=True``: ``nbr`` already holds packed words (``pack_neighbours``) and ``image`` is None."""
+        self.packed = bool(packed)
+        if self.packed and image is not None:
+            raise ValueError("packed neighbour words carry the image shift: pass image=None")
         self.device = _is_torch(X)
         if self.device:
             cv = lambda a, dt: None if a is None else a.contiguous().to(dt)   # noqa: E731
@@ -50,7 +54,7 @@ class B200Structure:
             self.first, self.nbr = cv(first, np.int64), cv(nbr, np.int32)
             self.image = None if image is None else cv(image, np.int8).reshape(-1, 3)
             self.species, self.rev = cv(species, np.int32), cv(rev, np.int32)
-        if self.image is not None and cell is None:
+        if (self.image is not None or self.packed) and cell is None:
             raise ValueError("periodic images need a cell")
         self.cell = np.zeros((3, 3)) if cell is None else np.ascontiguousarray(cell, dtype=np.float64).reshape(3, 3)
         self.natoms, self.npairs = int(self.X.shape[0]), int(self.nbr.shape[0])
@@ -74,6 +78,7 @@ class B200Structure:
         for i, v in enumerate(self.cell.ravel()):
             s.cell[i] = float(v)
         s.space = L.DEVICE if self.device else L.HOST
+        s.flags = L.NBR_PACKED if self.packed else 0
         return s
 
     def empty(self, shape):
@@ -87,11 +92,27 @@ class B200Structure:
         if self.device:
             raise ValueError("environments() is a host-side helper")
         centre = np.repeat(np.arange(self.natoms), np.diff(self.first))
-        R = self.X[self.nbr] - self.X[centre]
-        if self.image is not None:
-            R = R + self.image.astype(np.float64) @ self.cell
-        sp = None if self.species is None else self.species[self.nbr]
+        nbr, image = self.nbr, self.image
+        if self.packed:
+            w = self.nbr.view(np.uint32).astype(np.int64)
+            nbr = (w & 0x03ffffff).astype(np.int32)
+            image = np.stack([((w >> (26 + 2 * k)) & 3) - 1 for k in range(3)], axis=1).astype(np.int8)
+        R = self.X[nbr] - self.X[centre]
+        if image is not None:
+            R = R + image.astype(np.float64) @ self.cell
+        sp = None if self.species is None else self.species[nbr]
         return R, self.first.copy(), sp, centre
+
+
+def pack_neighbours(nbr, image) -> np.ndarray:
+    """int32 words ``j | (S0 + 1) << 26 | (S1 + 1) << 28 | (S2 + 1) << 30`` (ACEB200_NBR_PACKED): 4 instead of 7 bytes per
+    pair cross PCIe.  Needs j < 2^26 and S in {-1, 0, 1} (any cell wider than the cutoff)."""
+    nbr = np.asarray(nbr, dtype=np.int64)
+    S = np.asarray(image, dtype=np.int64).reshape(-1, 3)
+    if nbr.size and (nbr.max() >= (1 << 26) or nbr.min() < 0 or np.abs(S).max() > 1):
+        raise ValueError("pack_neighbours: needs 0 <= j < 2^26 and image shifts in {-1, 0, 1}")
+    w = nbr | ((S[:, 0] + 1) << 26) | ((S[:, 1] + 1) << 28) | ((S[:, 2] + 1) << 30)
+    return w.astype(np.uint32).view(np.int32)
 
 
 def reverse_pairs(first, nbr, image=None) -> np.ndarray:

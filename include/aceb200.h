@@ -204,6 +204,8 @@ int aceb200_adjoint_eval_d(aceb200_model *m, const aceb200_batch *b, const doubl
  * gradients never leave it: per pair the interface moves 4 B (+ 3 B with periodic images, + 4 B with a
  * reverse table) instead of the 48 B of aceb200_energy_forces.  The neighbour list must be a FULL list (every
  * pair appears under both of its centres), as JuLIP's is. */
+#define ACEB200_NBR_PACKED 1
+
 typedef struct aceb200_structure {
     int64_t natoms;
     int64_t npairs;           /* < 2^31 */
@@ -217,7 +219,9 @@ typedef struct aceb200_structure {
                                  none (the neighbour is not a centre); NULL = found on the device by searching j's pairs */
     double cell[9];           /* lattice vectors as rows, HOST memory in either space; unused when image is NULL   */
     int32_t space;            /* ACEB200_HOST or ACEB200_DEVICE: where every pointer above AND the outputs live   */
-    int32_t _pad;
+    int32_t flags;            /* 0, or ACEB200_NBR_PACKED: nbr[p] = j | (S0+1) << 26 | (S1+1) << 28 | (S2+1) << 30 with image = NULL
+                                 (natoms <= 2^26, S in {-1, 0, 1}: any cell wider than the cutoff): 4 instead of 7 bytes per
+                                 pair cross PCIe, which is what bounds this call when several GPUs share one host          */
 } aceb200_structure;
 
 /* Site energies, atomic forces and the virial of a structure for a real (symreal) model:

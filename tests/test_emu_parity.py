@@ -93,6 +93,11 @@ def test_emulated_structure_path(emu, monkeypatch):
         # a neighbour list that is NOT sorted within a centre: the device-side reverse search falls back to a scan
         perm = np.concatenate([first[i] + rng.permutation(first[i + 1] - first[i]) for i in range(len(X))])
         E, F, W = model.evaluator.handle.structure_energy_forces(B200Structure(X, first, nbr[perm], image[perm], cell, species))
+        if np.abs(image).max() <= 1:        # packed neighbour words: the image shift rides in the upper bits of nbr
+            from ace_jl_b200.structure import pack_neighbours
+            Ek, Fk, Wk = model.evaluator.handle.structure_energy_forces(
+                B200Structure(X, first, pack_neighbours(nbr, image)[perm], None, cell, species, None, packed=True))
+            assert relerr(Ek, Eo) < 1e-12 and relerr(Fk, Fo) < 1e-12 and relerr(Wk, Wo) < 1e-12
         assert relerr(E, Eo) < 1e-12 and relerr(F, Fo) < 1e-12 and relerr(W, Wo) < 1e-12
 
 

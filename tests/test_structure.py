@@ -140,6 +140,14 @@ def test_structure_matches_oracle(kind, nprop, periodic, use_rev, monkeypatch):
     Ep, Fp, Wp = model.evaluator.handle.structure_energy_forces(
         B200Structure(X, first, nbr[perm], None if image is None else image[perm], cell, species))
     assert relerr(Ep, Eo) < TOL and relerr(Fp, Fo) < TOL and relerr(Wp, Wo) < TOL
+    # packed neighbour words (ACEB200_NBR_PACKED: image shift in the upper six bits, 4 B per pair): same bits out, with the
+    # caller's reverse table and with the device-side search, sorted and unsorted
+    if periodic and np.abs(image).max() <= 1:
+        from ace_jl_b200.structure import pack_neighbours
+        wp = pack_neighbours(nbr, image)
+        for r, w_ in ((rev if use_rev else None, wp), (None, wp[perm])):
+            Ek, Fk, Wk = model.evaluator.handle.structure_energy_forces(B200Structure(X, first, w_, None, cell, species, r, packed=True))
+            assert relerr(Ek, Eo) < TOL and relerr(Fk, Fo) < TOL and relerr(Wk, Wo) < TOL
     # the model-level wrapper squeezes like evaluate / grad_config
     E1, F1, W1 = model.energy_forces_virial(st)
     assert E1.shape == ((len(X),) if nprop == 1 else (len(X), nprop)) and F1.shape[-1] == 3
