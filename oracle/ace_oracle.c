@@ -12,8 +12,13 @@
  *   - closed-form distance transforms (test/transforms/test_transforms.jl:21,34,49),
  *   - the one-hot categorical basis (test/test_discrete.jl:38-45),
  *   - and the reference's randomised identities (finite differences, A(cfg)=sum_j A(X_j),
- *     naive == product evaluator, rotation / permutation invariance).
- * For everything else: "parity unpinned by the reference".
+ *     naive == product evaluator, rotation / permutation invariance),
+ * and, independently of this repository's reading of the reference, by third-party arithmetic
+ * (tests/test_oracle_independent.py): Y_l^m for all l <= 8 against scipy.special.sph_harm_y and mpmath at 50 digits,
+ * grad Y_l^m against mpmath derivatives, and one whole model (A, AA, B, E, forces) re-evaluated with mpmath at 50 digits
+ * from the same tables.  tests/golden/export_golden.jl dumps the same quantities from a real ACE.jl installation;
+ * tests/test_julia_golden.py checks this oracle (and the CUDA path) against such dumps when they are present.
+ * Until one is: "parity unpinned by the reference" for Rn, A, AA, B, energies and forces.
  *
  * Every function follows the reference line by line, INCLUDING its inefficiencies (the full
  * (maxL+1)^2 harmonics, the materialised dA matrix, atan/sincos) -- this is what the reference's
