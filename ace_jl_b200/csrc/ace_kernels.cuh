@@ -78,7 +78,10 @@ struct BatchDev {
     const double* R;         // neighbour positions, indexed by ABSOLUTE neighbour index minus jbase
     const int* species;      // same indexing, or null
     long long jbase;         // absolute index of R[0]
+    const int* gate;         // the call's error flag: 1 = the offsets of a DEVICE batch failed k_check_offsets, so no
+                             // kernel may index with them (every offset-consuming kernel returns at once)
 };
+#define ACE_GATE(B) do { if ((B).gate && *(B).gate == 1) return; } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // k_pool: A_{slot}[env] for a chunk of environments
@@ -125,6 +128,7 @@ __global__ void __launch_bounds__(kPoolThreads) k_pool(const PoolParams p)
     const int N = p.rp.N, nblk = p.nblk, nbp = p.nbp;
     const long long e0 = (long long)blockIdx.x * p.TE;
     if (e0 >= p.B.nenv) return;
+    ACE_GATE(p.B);
     const int ne = (int)((p.B.nenv - e0) < p.TE ? (p.B.nenv - e0) : p.TE);
     const long long jbeg = p.B.off[e0];
     if (tid <= ne) joff[tid] = (int)(p.B.off[e0 + tid] - jbeg);
@@ -347,6 +351,7 @@ __global__ void __launch_bounds__(kPoolMmaThreads) k_pool_mma(const PoolMmaParam
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long e0 = (long long)blockIdx.x * p.TE;
     if (e0 >= p.B.nenv) return;
+    ACE_GATE(p.B);
     const int ne = (int)((p.B.nenv - e0) < p.TE ? (p.B.nenv - e0) : p.TE);
     const long long jbeg = p.B.off[e0];
     if (tid <= ne) joff[tid] = (int)(p.B.off[e0 + tid] - jbeg);
@@ -1330,6 +1335,7 @@ __global__ void __launch_bounds__(kForceThreads, ACE_FORCE_MINB) k_forces(const 
     const int tid = threadIdx.x;
     const long long e0 = (long long)blockIdx.x * TE;
     if (e0 >= p.B.nenv) return;
+    ACE_GATE(p.B);
     const int ne = (int)((p.B.nenv - e0) < TE ? (p.B.nenv - e0) : TE);
     const long long jbeg = p.B.off[e0];
     const int nS = p.C.nS, ncol = p.C.nQ * p.C.nPused;
@@ -1573,6 +1579,7 @@ __global__ void __launch_bounds__(kFmmaThreads) k_forces_mma(const ForceMmaParam
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long e0 = (long long)blockIdx.x * p.TE;
     if (e0 >= p.B.nenv) return;
+    ACE_GATE(p.B);
     const int ne = (int)((p.B.nenv - e0) < p.TE ? (p.B.nenv - e0) : p.TE);
     const long long jbeg = p.B.off[e0];
     if (tid <= ne) joff[tid] = (int)(p.B.off[e0 + tid] - jbeg);
@@ -1753,6 +1760,7 @@ __global__ void __launch_bounds__(kPoolThreads) k_pool_w(const PoolWParams p)
     const int N = p.rp.N, nS = p.C.nS, nP = p.nP;
     const long long e0 = (long long)blockIdx.x * p.TE;
     if (e0 >= p.B.nenv) return;
+    ACE_GATE(p.B);
     const int ne = (int)((p.B.nenv - e0) < p.TE ? (p.B.nenv - e0) : p.TE);
     const long long jbeg = p.B.off[e0];
     if (tid <= ne) joff[tid] = (int)(p.B.off[e0 + tid] - jbeg);
@@ -1894,6 +1902,7 @@ __global__ void __launch_bounds__(128) k_dA(const dAParams p)
 {
     const long long jl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (jl >= p.nJ) return;
+    ACE_GATE(p.B);
     const long long jabs = p.B.off[0] + jl;
     const double* r = p.B.R + 3 * (jabs - p.B.jbase);
     const double x = r[0], y = r[1], z = r[2];
@@ -1942,10 +1951,11 @@ __global__ void __launch_bounds__(128) k_dA(const dAParams p)
 // dAA[j][i][:] = real?(sum_t (prod_{s != t} A_{v_s}) dA[j][v_t][:])  (src/pibasis.jl:402-432)
 constexpr int kMaxOrdDevK = 8;
 static __global__ void k_dAA(long long nenv, const long long* off, int nA, int nAA, int maxord, const int* orders, const int* spec,
-                      const c2* A, const c2* dA, int pireal, double* dAA)
+                      const c2* A, const c2* dA, int pireal, double* dAA, const int* gate)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nenv * nAA) return;
+    if (gate && *gate == 1) return;
     const long long e = t / nAA;
     const int i = (int)(t % nAA);
     const c2* Ae = A + (size_t)e * nA;

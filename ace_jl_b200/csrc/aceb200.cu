@@ -1032,7 +1032,8 @@ static std::vector<long long> boundary_offsets(aceb200_model* m, const aceb200_b
     } else {
         t_cur->ws_out.reserve((nb + 1) * sizeof(long long));
         auto kfn = k_gather_offsets;
-        ACE_LAUNCH(kfn, dim3((unsigned)((nb + 1 + 127) / 128)), dim3(128), 0, t_cur->stream, reinterpret_cast<const long long*>(b->offsets), (long long)b->nenv, step, nb, t_cur->ws_out.as<long long>());
+        long long* dst = t_cur->ws_out.as<long long>();
+        ACE_LAUNCH(kfn, dim3((unsigned)((nb + 1 + 127) / 128)), dim3(128), 0, t_cur->stream, reinterpret_cast<const long long*>(b->offsets), (long long)b->nenv, step, nb, dst);
         CU(cudaGetLastError());
         m->launches++;
         CU(cudaMemcpyAsync(out.data(), t_cur->ws_out.p, (nb + 1) * sizeof(long long), cudaMemcpyDeviceToHost, t_cur->stream));
@@ -1074,6 +1075,7 @@ static BatchDev batch_dev(const Staged& s, const Chunk& c)
 {
     BatchDev B;
     B.nenv = c.e1 - c.e0; B.off = s.off; B.R = s.R; B.species = s.species; B.jbase = s.jbase;
+    B.gate = t_ctx ? t_ctx->ws_err.as<int>() : nullptr;
     return B;
 }
 
@@ -1527,8 +1529,9 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
     if (!host && !(hints && hints->host_offsets)) {
         // a DEVICE batch: its offsets are checked where they live (no synchronisation); the flag is read with the results
         auto kfn = k_check_offsets;
+        int* flagp = t_ctx->ws_err.as<int>();
         ACE_LAUNCH(kfn, dim3((unsigned)((b->nenv + 255) / 256)), dim3(256), 0, t_ctx->lanes[0].stream,
-                   reinterpret_cast<const long long*>(b->offsets), (long long)b->nenv, nJ_tot, t_ctx->ws_err.as<int>());
+                   reinterpret_cast<const long long*>(b->offsets), (long long)b->nenv, nJ_tot, flagp);
         CU(cudaGetLastError());
         m->launches++;
     }
@@ -1650,8 +1653,9 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
                 L.ws_dAA.reserve(std::max<long long>(nj, 1) * nAA * 24 * ca);
                 dAA_dev = L.ws_dAA.as<double>();
                 auto kfn = k_dAA;
+                const int* gate = t_ctx->ws_err.as<int>();      // (a local: launch arguments are evaluated by the launching thread)
                 ACE_LAUNCH(kfn, dim3(blocks_for(ne * nAA, 128)), dim3(128), 0, L.stream, ne, st.off, nA, nAA, std::max(1, T.maxord), m->d_orders, m->d_spec,
-                           (const c2*)L.ws_A.as<c2>(), (const c2*)dA_dev, T.pireal, dAA_dev);
+                           (const c2*)L.ws_A.as<c2>(), (const c2*)dA_dev, T.pireal, dAA_dev, gate);
                 CU(cudaGetLastError()); m->launches++;
             }
             double* dB_dev = nullptr;

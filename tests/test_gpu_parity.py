@@ -267,3 +267,28 @@ def test_config2_sampled_oracle_parity_and_properties():
     # (e) evaluate(model, cfg) alone walks the energy-only stream (every AA function once): same energies
     Eonly = h.energy(ace.B200Batch(Rd, offd)).cpu().numpy()
     assert relerr(Eonly, E) < TOL
+
+
+def test_malformed_offsets_are_rejected_not_dereferenced():
+    """A malformed interior offset (e.g. [0, 100, 5, 10]) must come back as an EDESC error from both the HOST path
+    (validated on the host) and the DEVICE path (validated by a kernel; every offset-consuming kernel is gated on it),
+    and the handle must stay usable."""
+    import torch
+    basis = make_basis("inv_simple_3_6")
+    rng = philox(61)
+    h = ace.LinearACEModel(basis, rng.random(len(basis)) - 0.5).evaluator.handle
+    R, off, _ = rand_envs(rng, rn_of(basis), 3, [4, 3, 3])
+    good = h.energy_forces(ace.B200Batch(R, off))
+    bad = np.array([0, 100, 5, 10], dtype=np.int64)
+    hb = ace.B200Batch(R, off)
+    hb.offsets = bad                                       # bypass the Python-side check
+    with pytest.raises(_lib.AceB200Error) as ei:
+        h.energy_forces(hb)
+    assert ei.value.code == -1
+    db = ace.B200Batch(torch.from_numpy(R).cuda(), torch.from_numpy(bad).cuda())
+    for call in (h.energy_forces, h.eval_B, h.eval_dB):
+        with pytest.raises(_lib.AceB200Error) as ei:
+            call(db)
+        assert ei.value.code == -1
+    again = h.energy_forces(ace.B200Batch(torch.from_numpy(R).cuda(), torch.from_numpy(off).cuda()))
+    assert np.array_equal(again[0].cpu().numpy(), good[0]) and np.array_equal(again[1].cpu().numpy(), good[1])
