@@ -202,9 +202,11 @@ class Handle:
         self._call("aceb200_eval_dAA", b, AA, dAA)
         return AA, dAA
 
-    def eval_dB(self, b: B200Batch):
-        B = b.empty((b.nenv, self.s.nB, self.s.ncomp), not self.s.symreal)
-        dB = b.empty((b.nJ, self.s.nB, 3, self.s.ncomp), not self.s.symreal)
+    def eval_dB(self, b: B200Batch, B=None, dB=None):
+        if B is None:
+            B = b.empty((b.nenv, self.s.nB, self.s.ncomp), not self.s.symreal)
+        if dB is None:
+            dB = b.empty((b.nJ, self.s.nB, 3, self.s.ncomp), not self.s.symreal)
         self._call("aceb200_eval_dB", b, B, dB)
         return B, dB
 

@@ -1892,8 +1892,9 @@ struct dAParams {
     BatchDev B;
     const int* slot_pos; const int* slot_neg;
     int nA;
-    c2* dA;                  // [neighbour][nA][3], chunk-relative
+    c2* dA;                  // [neighbour][nA][3], chunk-relative; canon: [neighbour][nS][3] over the canonical slots (m >= 0)
     long long nJ;
+    int canon;
 };
 
 // dA[j][iA][:] = grad phi_iA(r_j) (src/product_1pbasis.jl:169-221), one thread per neighbour
@@ -1911,9 +1912,10 @@ __global__ void __launch_bounds__(128) k_dA(const dAParams p)
     const Spher sp = cart2spher(x, y, z);
     double Rn[NMAX], dRn[NMAX];
     radial_ed<NMAX>(p.rp, sp.r, Rn, dRn);
-    c2* out = p.dA + (size_t)jl * p.nA * 3;
-    // functions of other species are identically zero for this neighbour
-    for (int a = 0; a < p.nA * 3; ++a) out[a] = c2{0.0, 0.0};
+    const int width = p.canon ? p.C.nS : p.nA;
+    c2* out = p.dA + (size_t)jl * width * 3;
+    // functions of other species are identically zero for this neighbour (one species: every canonical slot is written below)
+    if (!p.canon || p.C.nQ > 1) for (int a = 0; a < width * 3; ++a) out[a] = c2{0.0, 0.0};
     const int* cmap = p.C.colmap + (size_t)q * p.C.nPused;
     const double rx = x * sp.rinv, ry = y * sp.rinv, rz = z * sp.rinv;
     for_each_lm_ed(p.ap, sp, [&](int l, int m, double Pt, double dP, double epr, double epi) {
@@ -1938,6 +1940,7 @@ __global__ void __launch_bounds__(128) k_dA(const dAParams p)
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
                     g[k] = c2{dRn[n] * rh[k] * Y.x + Rn[n] * gY[k].x, dRn[n] * rh[k] * Y.y + Rn[n] * gY[k].y};
+                if (p.canon) { for (int k = 0; k < 3; ++k) out[(size_t)(base + n) * 3 + k] = g[k]; continue; }
                 if (apos >= 0) for (int k = 0; k < 3; ++k) out[(size_t)apos * 3 + k] = g[k];
                 if (aneg >= 0) {
                     const double sg = (m & 1) ? -1.0 : 1.0;
@@ -2008,6 +2011,151 @@ static __global__ void k_dB(long long nJ, int nB, int nAA, int ncomp, const int*
         if (!symreal) o[1] = bi;
     }
 }
+
+// dB straight from A and dA -- dAA (|AA| x J x 3, 549 KB per environment for config 1) is never materialised
+// [src/pibasis.jl:402-432 + src/symmbasis.jl:330-334 in one pass].  Written as a sparse matrix applied to the one-particle
+// Jacobian:
+//     dB[j][row][xyz][c] = Re( sum_a W_e[row][a][c] * dA[j][a][xyz] ),
+//     W_e[row][a][c] = sum_{k in row, t : v_t(k) = a}  A2B[row,k][c] * prod_{s != t} A_e[v_s(k)]       (Re(A2B) if the PI basis is real)
+// The sparsity pattern of W (entries = distinct (row, a), contributions = (k, t)) is static and packed on the host (DbPack);
+// its values depend on the environment only, not on the neighbour, so they are computed once per environment and row tile
+// (phase W, one thread per entry) and then applied to all neighbours (phase D): one CTA per environment, lane = neighbour,
+// warp = group of RW consecutive rows.  dA of the <= 32 neighbours of a pass lives in shared memory as planes [slot][xyz][lane]
+// over the canonical slots (pitch 33: the transposing store and the lane-contiguous LDS.128 of phase D are both
+// conflict-free); the weight of an entry is one broadcast LDS.128.  A warp stages the results of its group in a private
+// strip of shared memory and writes them out itself, several neighbours' contiguous (RW x 3 x NC) runs per instruction, so
+// phase D needs no CTA barrier: the warps of a tile run decoupled, groups dealt longest-first.
+// Bound: shared-memory bandwidth -- 48 B of dA per lane and entry for 6 NC DFMAs.
+struct DbEnvParams {
+    long long nenv; const long long* off; const int* gate;
+    int nA, nS, nB, nT, maxf, pireal, ET;
+    const int* tile_grp;      // [nT + 1] position of each row tile's first group in grp_list
+    const int* tile_ent;      // [nT + 1] first entry of each row tile (<= ET entries per tile)
+    const int* grp_list;      // first row of each group, dealt longest-first within a tile (warp w takes w, w + nwarps, ...)
+    const int* row_ent;       // [nB + 1] entries of each row
+    const int* ent_a;         // [nE] canonical slot of the entry
+    const int* ent_con;       // [nE + 1] contributions of each entry
+    const int* con_k;         // [nC] 4 * (non-zero of A2Bmap) + the neg / odd bits of the A-code of the differentiated factor
+    const int* con_f;         // [nC][maxf] the other factors of the product (index into A), -1 = none
+    const c2* val; const c2* A; const c2* dA; double* dB;
+};
+constexpr int kDbPitch = 33;
+ACE_HD constexpr int db_threads(int NC) { return NC == 1 ? 1024 : 512; }   // one CTA per SM (the dA planes fill shared memory): as many warps as the registers allow
+ACE_HD constexpr int db_rows(int NC) { return NC == 1 ? 2 : 1; }           // rows per group
+ACE_HD constexpr int db_strip(int NC) { return (db_rows(NC) * 3 * NC) | 1; }   // doubles per lane in a warp's staging strip
+inline size_t db_env_fixed_smem(int nA, int nS, int NC)
+{
+    return ((size_t)nS * 3 * kDbPitch + nA) * sizeof(c2) + (size_t)(db_threads(NC) / 32) * 32 * db_strip(NC) * sizeof(double);
+}
+inline size_t db_env_smem(int nA, int nS, int ET, int NC) { return db_env_fixed_smem(nA, nS, NC) + (size_t)ET * (NC * sizeof(c2) + sizeof(int)); }
+
+template <int NC>
+__global__ void __launch_bounds__(db_threads(NC), 1) k_dB_env(const DbEnvParams p)
+{
+    constexpr int RW = db_rows(NC), L = RW * 3 * NC, SP = db_strip(NC), JPER = 32 / L;
+    ACE_DYN_SMEM(c2, planes);                                   // [nS * 3][kDbPitch]
+    const long long e = blockIdx.x;
+    if (e >= p.nenv) return;
+    if (p.gate && *p.gate == 1) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    c2* As = planes + (size_t)p.nS * 3 * kDbPitch;              // [nA]
+    c2* Ws = As + p.nA;                                         // [ET][NC]  (m0, m1): Re(w dA) = m0 Re dA_slot + m1 Im dA_slot
+    double* strip = reinterpret_cast<double*>(Ws + (size_t)p.ET * NC) + (size_t)warp * 32 * SP;    // [32][SP], private to the warp
+    int* Ea = reinterpret_cast<int*>(reinterpret_cast<double*>(Ws + (size_t)p.ET * NC) + (size_t)nwarps * 32 * SP);   // [ET] plane offset of the entry
+    const int nS3 = p.nS * 3;
+    const long long j0 = p.off[e] - p.off[0];
+    const int J = (int)(p.off[e + 1] - p.off[e]);
+    for (int a = tid; a < p.nA; a += blockDim.x) As[a] = p.A[(size_t)e * p.nA + a];
+    for (int jt = 0; jt < J; jt += 32) {
+        const int nj = (J - jt < 32) ? (J - jt) : 32;
+        __syncthreads();                                         // the planes of the previous pass are no longer read
+        for (int j = warp; j < 32; j += nwarps) {
+            if (j < nj) {
+                const c2* src = p.dA + (size_t)(j0 + jt + j) * nS3;
+                for (int x = lane; x < nS3; x += 32) planes[(size_t)x * kDbPitch + j] = src[x];
+            } else {
+                for (int x = lane; x < nS3; x += 32) planes[(size_t)x * kDbPitch + j] = c2{0.0, 0.0};
+            }
+        }
+        for (int t = 0; t < p.nT; ++t) {
+            const int g0 = __ldg(p.tile_grp + t), g1 = __ldg(p.tile_grp + t + 1);
+            const int e0 = __ldg(p.tile_ent + t), e1 = __ldg(p.tile_ent + t + 1);
+            __syncthreads();                                     // planes / A visible; the weights of the previous tile consumed
+            // phase W: one thread per entry
+            for (int i = e0 + tid; i < e1; i += blockDim.x) {
+                double m0[NC], m1[NC];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) { m0[c] = 0.0; m1[c] = 0.0; }
+                const int q1 = __ldg(p.ent_con + i + 1);
+                for (int q = __ldg(p.ent_con + i); q < q1; ++q) {
+                    c2 g = c2{1.0, 0.0};
+                    for (int f = 0; f < p.maxf; ++f) {
+                        const int a = __ldg(p.con_f + (size_t)q * p.maxf + f);
+                        if (a >= 0) g = cmul(g, As[a]);
+                    }
+                    const int kc = __ldg(p.con_k + q);
+                    // the differentiated factor is decode_A(slot value): Re flips for odd negative m, Im for even negative m
+                    const double sx = (kc & 2) ? -1.0 : 1.0, sy = ((kc & 1) && !(kc & 2)) ? -1.0 : 1.0;
+                    const c2* v = p.val + (size_t)(kc >> 2) * NC;
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        const c2 vc = v[c];
+                        double wr, wi;
+                        if (p.pireal) { wr = vc.x * g.x; wi = vc.x * g.y; }
+                        else { wr = vc.x * g.x - vc.y * g.y; wi = vc.x * g.y + vc.y * g.x; }
+                        m0[c] += sx * wr; m1[c] -= sy * wi;
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < NC; ++c) Ws[(size_t)(i - e0) * NC + c] = c2{m0[c], m1[c]};
+                Ea[i - e0] = __ldg(p.ent_a + i) * 3 * kDbPitch;
+            }
+            __syncthreads();
+            // phase D: one warp per group of RW rows, one lane per neighbour; no CTA barrier inside
+            for (int pos = g0 + warp; pos < g1; pos += nwarps) {
+                const int r0 = __ldg(p.grp_list + pos);
+                const int nr = (p.nB - r0 < RW) ? (p.nB - r0) : RW;
+                for (int rr = 0; rr < nr; ++rr) {
+                    double acc[3][NC];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) acc[d][c] = 0.0;
+                    const int i1 = __ldg(p.row_ent + r0 + rr + 1) - e0;
+#pragma unroll 2
+                    for (int i = __ldg(p.row_ent + r0 + rr) - e0; i < i1; ++i) {
+                        const c2* pl = planes + Ea[i] + lane;
+                        const c2 x0 = pl[0], x1 = pl[kDbPitch], x2 = pl[2 * kDbPitch];
+                        const c2* wr = Ws + (size_t)i * NC;
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) {
+                            const c2 w = wr[c];
+                            acc[0][c] = fma(w.x, x0.x, fma(w.y, x0.y, acc[0][c]));
+                            acc[1][c] = fma(w.x, x1.x, fma(w.y, x1.y, acc[1][c]));
+                            acc[2][c] = fma(w.x, x2.x, fma(w.y, x2.y, acc[2][c]));
+                        }
+                    }
+                    double* o = strip + lane * SP + rr * 3 * NC;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) o[d * NC + c] = acc[d][c];
+                }
+                __syncwarp();
+                // JPER neighbours' contiguous runs of (nr x 3 x NC) doubles per store instruction
+                const int len = nr * 3 * NC, jj = lane / L, x = lane - jj * L;
+                if (jj < JPER && x < len) {
+                    for (int jb = jj; jb < nj; jb += JPER)
+                        p.dB[((size_t)(j0 + jt + jb) * p.nB + r0) * 3 * NC + x] = strip[jb * SP + x];
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+
+
 
 // ------------------------------------------------------------------------------------------------
 // caller side of the path: an atomic structure + neighbour list in, site energies and

@@ -153,6 +153,9 @@ struct aceb200_model {
     const ForceTile* d_force_tiles = nullptr;  // k_forces_mma column tiles (same column order)
     // k_basis_stream (fused B = A2Bmap . prod A): leaf stream per warp; depends on the tables only, not on c
     BStream bs;                                // B = A2Bmap . AA
+    // k_dB_env (dB = W_e . dA): static sparsity pattern of W; depends on the tables only
+    struct DbPack { bool ok = false; int nT = 0, maxf = 0, ET = 0; size_t smem = 0;
+                    const int *tile_grp = nullptr, *tile_ent = nullptr, *grp_list = nullptr, *row_ent = nullptr, *ent_a = nullptr, *ent_con = nullptr, *con_k = nullptr, *con_f = nullptr; } db;
     const int *d_orders = nullptr, *d_spec = nullptr;
     const int *d_csr_ptr = nullptr, *d_csr_col = nullptr;
     const c2* d_csr_val = nullptr;
@@ -877,6 +880,74 @@ static bool launch_bstream(aceb200_model* m, const BStream& S, long long ne, lon
 // B for a chunk: out [ne][nB][ncomp] (real or complex)
 static bool launch_basis(aceb200_model* m, long long ne, long long ldA, double* out) { return launch_bstream(m, m->bs, ne, ldA, out); }
 
+// k_dB_env's view of the tables: for every row of A2Bmap the distinct one-particle indices a that any of its products
+// contains (an "entry"), and for every entry the (non-zero k, position t) pairs that contribute
+// A2B[row,k] * prod_{s != t} A[v_s(k)] to its weight.  Row tiles are cut so that the weights and the staged results of
+// one tile fit beside the dA planes in shared memory.
+static void upload_db_pack(aceb200_model* m)
+{
+    const auto& T = m->T;
+    m->db = aceb200_model::DbPack();
+    if (!T.symreal || T.nB == 0 || T.maxord < 1 || !(T.ncomp == 1 || T.ncomp == 3 || T.ncomp == 9)) return;
+    const int NC = T.ncomp, maxf = std::max(1, T.maxord - 1);
+    const size_t base = db_env_fixed_smem(T.nA, T.nS, NC);
+    const size_t limit = (size_t)m->smem_optin - 1024;
+    if (base + 8192 > limit) return;                         // the planes leave no room: the generic k_dAA + k_dB path runs
+    std::vector<int> row_ent(1, 0), ent_a, ent_con(1, 0), con_k, con_f;
+    int emax = 0;
+    for (int r = 0; r < T.nB; ++r) {
+        std::map<int, std::vector<std::pair<int, int>>> by_a;            // canonical slot -> (k, t), ascending, contributions in (k, t) order
+        for (int k = T.csr_ptr[r]; k < T.csr_ptr[r + 1]; ++k) {
+            const int i = T.csr_col[k];
+            for (int t = 0; t < T.orders[i]; ++t) by_a[T.iA_code[T.spec[(size_t)i * T.maxord + t]] >> 2].push_back({k, t});
+        }
+        for (auto& kv : by_a) {
+            ent_a.push_back(kv.first);
+            for (auto& kt : kv.second) {
+                const int i = T.csr_col[kt.first];
+                con_k.push_back(kt.first * 4 + (T.iA_code[T.spec[(size_t)i * T.maxord + kt.second]] & 3));
+                int nf = 0;
+                for (int s2 = 0; s2 < T.orders[i]; ++s2) if (s2 != kt.second) { con_f.push_back(T.spec[(size_t)i * T.maxord + s2]); ++nf; }
+                for (; nf < maxf; ++nf) con_f.push_back(-1);
+            }
+            ent_con.push_back((int)con_k.size());
+        }
+        row_ent.push_back((int)ent_a.size());
+        emax = std::max(emax, row_ent[r + 1] - row_ent[r]);
+    }
+    const int RW = db_rows(NC), nw = db_threads(NC) / 32, ngrp = (T.nB + RW - 1) / RW;
+    const int ET = (int)std::min<size_t>((limit - base) / (NC * sizeof(c2) + sizeof(int)), std::max<size_t>(ent_a.size(), 1));
+    auto gent = [&](int g) { return row_ent[std::min(T.nB, (g + 1) * RW)] - row_ent[g * RW]; };
+    std::vector<int> tile_grp(1, 0), tile_ent(1, 0), grp_list;
+    for (int g = 0; g < ngrp;) {
+        int g1 = g;
+        while (g1 < ngrp && row_ent[std::min(T.nB, (g1 + 1) * RW)] - row_ent[g * RW] <= ET) ++g1;
+        if (g1 == g) return;                                  // one group's weights do not fit: generic path
+        // deal the groups of the tile to the warps longest-first, in snake order: position w + k nw belongs to warp w
+        std::vector<int> order(g1 - g);
+        for (int i = 0; i < g1 - g; ++i) order[i] = g + i;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return gent(x) > gent(y); });
+        for (size_t i = 0; i < order.size(); ++i) {
+            const size_t round = i / nw, k = i % nw;
+            const size_t src = round * nw + ((round & 1) ? std::min<size_t>(order.size() - round * nw, nw) - 1 - k : k);
+            grp_list.push_back(order[src] * RW);
+        }
+        tile_grp.push_back(g1);
+        tile_ent.push_back(row_ent[std::min(T.nB, g1 * RW)]);
+        g = g1;
+    }
+    auto& D = m->db;
+    D.nT = (int)tile_grp.size() - 1; D.maxf = maxf; D.ET = std::max(ET, 1);
+    D.smem = db_env_smem(T.nA, T.nS, D.ET, NC);
+    D.tile_grp = upload(m->pool, tile_grp); D.tile_ent = upload(m->pool, tile_ent); D.grp_list = upload(m->pool, grp_list);
+    D.row_ent = upload(m->pool, row_ent);
+    if (ent_a.empty()) ent_a.push_back(0);
+    if (con_k.empty()) { con_k.push_back(0); con_f.assign(maxf, -1); }
+    D.ent_a = upload(m->pool, ent_a); D.ent_con = upload(m->pool, ent_con);
+    D.con_k = upload(m->pool, con_k); D.con_f = upload(m->pool, con_f);
+    D.ok = true;
+}
+
 static void upload_tables(aceb200_model* m)
 {
     HostTables& T = m->T;
@@ -968,6 +1039,7 @@ static void upload_tables(aceb200_model* m)
     for (int nu = 0; nu <= kMaxOrdDev; ++nu) memset(&m->list[nu], 0, sizeof(ListDev));
     for (int nu = 2; nu <= T.maxord; ++nu) m->list[nu].ptr = upload(m->pool, T.trees[nu].ptr);
     upload_basis_stream(m);
+    upload_db_pack(m);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1324,12 +1396,12 @@ static void launch_dA_t(aceb200_model* m, const dAParams& p)
     ACE_LAUNCH(kfn, dim3((unsigned)((p.nJ + 127) / 128)), dim3(128), 0, t_cur->stream, p);
 }
 
-static void launch_dA(aceb200_model* m, const BatchDev& B, long long nJ, c2* dA)
+static void launch_dA(aceb200_model* m, const BatchDev& B, long long nJ, c2* dA, bool canon = false)
 {
     if (nJ == 0) return;
     dAParams p;
     p.rp = m->rp; p.ap = m->ap; p.C = m->C; p.B = B; p.slot_pos = m->d_slot_pos; p.slot_neg = m->d_slot_neg;
-    p.nA = m->T.nA; p.dA = dA; p.nJ = nJ;
+    p.nA = m->T.nA; p.dA = dA; p.nJ = nJ; p.canon = canon ? 1 : 0;
     switch (m->NMAX) {
     case 4: launch_dA_t<4>(m, p); break;
     case 8: launch_dA_t<8>(m, p); break;
@@ -1463,7 +1535,8 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
     const int ca = T.pireal ? 1 : 2, cs = T.symreal ? 1 : 2;
     const bool fusedB = (want & W_B) && m->bs.nw > 0;       // B straight from the pooled A (k_basis_stream): AA never reaches HBM
     const bool need_full_A = (want & (W_A | W_AA | W_dA | W_dAA | W_dB | W_ADJ)) || ((want & W_B) && !fusedB);
-    const bool need_AA = (want & (W_AA | W_dAA | W_dB)) || ((want & W_B) && !fusedB);
+    const bool dB_fusable = (want & W_dB) && !(want & (W_dAA | W_dA)) && m->db.ok && !getenv("ACEB200_NO_FUSED_DB");   // k_dB_env: dB from A and dA, no AA / dAA
+    const bool need_AA = (want & (W_AA | W_dAA)) || ((want & W_dB) && !dB_fusable) || ((want & W_B) && !fusedB);
     const bool need_dA = want & (W_dA | W_dAA | W_dB);
     const bool need_dAA = want & (W_dAA | W_dB);
     const bool host = b->space == ACEB200_HOST;
@@ -1501,8 +1574,8 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
     if (need_AA) per_env += (size_t)nAA * 8 * ca;
     if (want & W_B) per_env += (size_t)nB * ncomp * 8 * cs;
     if (need_dA) per_env += (size_t)(Jav * nA * 48.0);
-    if (need_dAA) per_env += (size_t)(Jav * nAA * 24.0 * ca);
-    if (want & W_dB) per_env += (size_t)(Jav * nB * 24.0 * ncomp * cs);
+    if (need_dAA && !dB_fusable) per_env += (size_t)(Jav * nAA * 24.0 * ca);
+    if ((want & W_dB) && (host || !dB_fusable)) per_env += (size_t)(Jav * nB * 24.0 * ncomp * cs);
     if (want & W_ADJ) per_env += (size_t)T.nS * 16 + (size_t)nA * 16 + (size_t)nAA * 16 + (size_t)nB * ncomp * 16 + (size_t)(Jav * 24.0);
     if (host) per_env += (size_t)(Jav * 28.0) + 8;
     long long step = chunk_envs(b->nenv, per_env, (size_t)8 << 30);
@@ -1647,9 +1720,28 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
             if (need_dA) {
                 L.ws_dA.reserve(std::max<long long>(nj, 1) * nA * 3 * sizeof(c2));
                 dA_dev = L.ws_dA.as<c2>();
-                launch_dA(m, B, nj, dA_dev);
+                launch_dA(m, B, nj, dA_dev, dB_fusable);          // k_dB_env reads the canonical slots only
             }
-            if (need_dAA) {
+            double* dB_dev = nullptr;
+            const bool fused_dB = dB_fusable && nj > 0;
+            if (fused_dB) {
+                // dB without dAA in HBM (k_dB_env): one CTA per environment; a DEVICE batch is written in place
+                if (!host) dB_dev = o.dB + (size_t)c.j0 * nB * 3 * ncomp * cs;
+                else { L.ws_G.reserve((size_t)nj * nB * 24 * ncomp * cs); dB_dev = L.ws_G.as<double>(); }
+                DbEnvParams q;
+                q.nenv = ne; q.off = st.off; q.gate = t_ctx->ws_err.as<int>();
+                q.nA = nA; q.nS = T.nS; q.nB = nB; q.nT = m->db.nT; q.maxf = m->db.maxf; q.pireal = T.pireal; q.ET = m->db.ET;
+                q.tile_grp = m->db.tile_grp; q.tile_ent = m->db.tile_ent; q.grp_list = m->db.grp_list; q.row_ent = m->db.row_ent; q.ent_a = m->db.ent_a; q.ent_con = m->db.ent_con;
+                q.con_k = m->db.con_k; q.con_f = m->db.con_f;
+                q.val = m->d_csr_val; q.A = L.ws_A.as<c2>(); q.dA = dA_dev; q.dB = dB_dev;
+                const size_t smem = m->db.smem;
+#define ACE_DBF(NCV) { auto kfn = k_dB_env<NCV>; CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                ACE_LAUNCH(kfn, dim3((unsigned)ne), dim3(db_threads(NCV)), smem, L.stream, q); }
+                if (ncomp == 1) ACE_DBF(1) else if (ncomp == 3) ACE_DBF(3) else ACE_DBF(9)
+#undef ACE_DBF
+                CU(cudaGetLastError()); m->launches++;
+            }
+            if (need_dAA && !dB_fusable) {
                 L.ws_dAA.reserve(std::max<long long>(nj, 1) * nAA * 24 * ca);
                 dAA_dev = L.ws_dAA.as<double>();
                 auto kfn = k_dAA;
@@ -1658,8 +1750,7 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
                            (const c2*)L.ws_A.as<c2>(), (const c2*)dA_dev, T.pireal, dAA_dev, gate);
                 CU(cudaGetLastError()); m->launches++;
             }
-            double* dB_dev = nullptr;
-            if ((want & W_dB) && nj > 0) {
+            if ((want & W_dB) && nj > 0 && !dB_fusable) {
                 L.ws_G.reserve((size_t)nj * nB * 24 * ncomp * cs);
                 dB_dev = L.ws_G.as<double>();
                 auto kfn = k_dB;

@@ -61,6 +61,10 @@ WORKLOADS: Dict[str, Workload] = {
                    lambda: sparse_basis(Invariant(), 3, 12, species=4), "EF", 16, 40, 100_000, nspecies=4, seed=20247, cache_key="sp_3_12"),
 }
 WORKLOADS["4b"] = WORKLOADS["4"]
+# the Jacobian of config 1: evaluate_d(basis, cfg) = dB (266 x 30 x 3 per environment, 191 KB), the training-side call
+# (benchmark/bm_basis.jl:64-70 "evaluate_d"; profile/profile_basis.jl:69: cost(dB) ~ 2 J cost(B))
+WORKLOADS["1d"] = Workload("1d", "SymmetricBasis evaluate_d (Jacobian dB), Invariant, ord=3, maxdeg=10, wL=1.5 SparseBasis, 30 neighbours (BASELINE config 1, evaluate_d)",
+                           lambda: sparse_basis(Invariant(), 3, 10), "dB", 1, 30, 100_000, seed=20248, cache_key="inv_3_10")
 
 _BASIS_CACHE: Dict[str, SymmetricBasis] = {}
 
@@ -91,6 +95,21 @@ def algorithmic_work(basis: SymmetricBasis, J: int, call: str, nprop: int = 1) -
     nsp = 4 if b1p.component(2) is not None else 0
     counts = {nu: int((orders == nu).sum()) for nu in range(1, int(orders.max()) + 1)}
     in_bytes = 24 * J + 8 + (4 * J if nsp else 0)
+    if call == "dB":
+        cs = 1 if basis.real else 2
+        nnz, maxo = basis.A2Bmap.nnz, int(orders.max())
+        pool = J * (28 + 5 * Nn + 15 * sizeP + 4 * nA)                            # A, as in the B call
+        dpool = J * (6 * Nn + 22 * sizeP + 12 * nA)                               # dA: 3 complex components per one-particle function
+        prod_B = float(sum(n * 6 * (nu - 1) for nu, n in counts.items()))
+        couple_B = float(nnz * ncomp * (2 if basis.pibasis.real else 4 if basis.real else 8))
+        # per neighbour and non-zero of A2Bmap: the local adjoints (2 (nu - 1) - 1 complex products) + nu complex x complex-3-vector
+        # multiply-adds + the coupling coefficient applied to the 3-vector
+        adj = float(J * sum(n * 6 * max(2 * (nu - 1) - 1, 0) for nu, n in counts.items()))
+        jac = float(J * sum(n * nu * 3 * (4 if basis.pibasis.real else 8) for nu, n in counts.items()) + J * nnz * ncomp * 3 * 2)
+        flops = {"pool": float(pool), "product_B": prod_B, "coupling_B": couple_B, "jacobian": float(dpool) + adj + jac}
+        out_bytes = J * len(basis) * ncomp * 3 * 8 * cs + len(basis) * ncomp * 8 * cs
+        return {"flops": flops, "flops_total": float(sum(flops.values())), "bytes": int(in_bytes + out_bytes),
+                "in_bytes": int(in_bytes), "out_bytes": int(out_bytes)}
     if call == "B":
         cs = 1 if basis.real else 2
         pool = J * (28 + 5 * Nn + 15 * sizeP + 4 * nA)

@@ -38,7 +38,8 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 UNIT = "env/s"
-METRICS = {"EF": "atom-environments/sec (energy+forces, FP64)",
+METRICS = {"dB": "atom-environments/sec (basis Jacobian dB, FP64)",
+           "EF": "atom-environments/sec (energy+forces, FP64)",
            "E": "atom-environments/sec (energies, FP64)",
            "B": "atom-environments/sec (basis values, FP64)"}
 
@@ -104,7 +105,7 @@ def cpu_reference_rate(w, basis, c, nenv_sample: int):
     o = orc.Oracle(basis_descriptor(basis, c))
     o.set_threads(len(os.sched_getaffinity(0)))   # all host cores (torchrun exports OMP_NUM_THREADS=1)
     R, off, sp = make_inputs(w, basis, nenv_sample, w.seed + 7)
-    fn = {"EF": o.energy_forces, "E": o.energy, "B": o.eval_B}[w.call]
+    fn = {"EF": o.energy_forces, "E": o.energy, "B": o.eval_B, "dB": o.eval_dB}[w.call]
     nw = min(64, nenv_sample)
     fn(R[: w.J * nw], off[: nw + 1], None if sp is None else sp[: w.J * nw])  # warm-up (thread pool, page faults)
     t0 = time.perf_counter()
@@ -155,7 +156,7 @@ def run_reference_arm(args, w):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="2", help="BASELINE configuration: 1, 2, 3, 4a, 4, 5, 5f")
+    ap.add_argument("--config", default="2", help="BASELINE configuration: 1, 1d (evaluate_d), 2, 3, 4a, 4, 5, 5f")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
@@ -203,6 +204,10 @@ def main():
     if w.call == "B":
         out = [torch.empty((nenv, nB, ncomp), dtype=torch.float64 if basis.real else torch.complex128, device=dev)]
         call = lambda b, o: h.eval_B(b, o[0])   # noqa: E731
+    elif w.call == "dB":
+        dt = torch.float64 if basis.real else torch.complex128
+        out = [torch.empty((nenv, nB, ncomp), dtype=dt, device=dev), torch.empty((nenv * J, nB, 3, ncomp), dtype=dt, device=dev)]
+        call = lambda b, o: h.eval_dB(b, o[0], o[1])   # noqa: E731
     elif w.call == "E":
         out = [torch.empty((nenv, w.nprop, ncomp), dtype=torch.float64, device=dev)]
         call = lambda b, o: h.energy(b, o[0])   # noqa: E731
@@ -214,7 +219,7 @@ def main():
 
     def step():
         call(batch, out)
-        if w.call != "B":
+        if w.call not in ("B", "dB"):
             tot.copy_(out[0].sum().reshape(1))
             if world > 1:
                 dist.all_reduce(tot)          # the one collective of the path: total energy over all shards
@@ -241,7 +246,8 @@ def main():
     for _ in range(args.steps):
         step()
         for k, v in h.last_stage_ms().items():
-            k = "basis" if (w.call == "B" and k == "adjoint") else k      # the second launch of a B call is the fused value kernel
+            k = "basis" if (w.call in ("B", "dB") and k == "adjoint") else k      # the second launch of a B call is the fused value kernel
+            k = "jacobian" if (w.call == "dB" and k == "forces") else k           # ... and what follows it in a dB call: k_dA + k_dB_fused
             stage[k] = stage.get(k, 0.0) + v
     e1.record()
     barrier()
@@ -270,6 +276,10 @@ def main():
         rel = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))   # noqa: E731
         if w.call == "B":
             errs = {"B": rel(out[0].cpu().numpy()[sel], o.eval_B(Rs, offs, sps))}
+        elif w.call == "dB":
+            Bo, dBo = o.eval_dB(Rs, offs, sps)
+            dBg = out[1].cpu().numpy().reshape(nenv, J, *out[1].shape[1:])[sel].reshape(ns * J, *out[1].shape[1:])
+            errs = {"B": rel(out[0].cpu().numpy()[sel], Bo), "dB": rel(dBg, dBo)}
         elif w.call == "E":
             errs = {"E": rel(out[0].cpu().numpy()[sel], o.energy(Rs, offs, sps))}
         else:
@@ -301,7 +311,7 @@ def main():
         e2e_env = {"value": world * nenv * e2e_steps / float(dt.item()), "unit": UNIT,
                    "h2d_bytes_per_step": int(R.nbytes + off.nbytes + (0 if sp is None else sp.nbytes)),
                    "d2h_bytes_per_step": int(sum(o_.numel() * o_.element_size() for o_ in outh)), "steps": e2e_steps,
-                   "call": {"EF": "aceb200_energy_forces", "E": "aceb200_energy", "B": "aceb200_eval_B"}[w.call],
+                   "call": {"EF": "aceb200_energy_forces", "E": "aceb200_energy", "B": "aceb200_eval_B", "dB": "aceb200_eval_dB"}[w.call],
                    "timer": "host wall clock around the C-ABI calls (they return after the D2H copy)"}
 
     # ---- end to end through the caller-side entry: a whole periodic structure with its neighbour
@@ -356,9 +366,13 @@ def main():
         hbm_ach = value / world * work["bytes"] / 1e9
         whole_tflops = work["flops_total"] * nenv / (step_ms * 1e-3) / 1e12
         stage_flops = dict(flops)
-        if "product" in stage_flops:                # the fused value kernel does products + coupling in one launch
+        if "coupling" in stage_flops:               # the fused value kernel does products + coupling in one launch
             stage_flops["basis"] = stage_flops.pop("product") + stage_flops.pop("coupling")
             kernel_names["basis"] = "k_basis_stream"
+        if "jacobian" in stage_flops:               # k_dB_fused recomputes the local adjoints and contracts with dA in one launch
+            stage_flops["basis"] = stage_flops.pop("product_B") + stage_flops.pop("coupling_B")
+            kernel_names["basis"] = "k_basis_stream"
+            kernel_names["jacobian"] = "k_dA + k_dB_fused"
         common = {k: v for k, v in per_launch_ms.items() if k in stage_flops}
         dom = max(common, key=common.get) if common else None
         fp64_roof = None
