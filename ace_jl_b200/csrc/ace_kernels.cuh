@@ -1892,7 +1892,8 @@ struct dAParams {
     BatchDev B;
     const int* slot_pos; const int* slot_neg;
     int nA;
-    c2* dA;                  // [neighbour][nA][3], chunk-relative; canon: [neighbour][nS][3] over the canonical slots (m >= 0)
+    c2* dA;                  // [neighbour][nA][3], chunk-relative; canon: [neighbour / 32][nS][3][neighbour % 32] over the canonical
+                             // slots (m >= 0) -- the plane layout of k_dB_env, written and read with full 512 B transactions
     long long nJ;
     int canon;
 };
@@ -1912,10 +1913,11 @@ __global__ void __launch_bounds__(128) k_dA(const dAParams p)
     const Spher sp = cart2spher(x, y, z);
     double Rn[NMAX], dRn[NMAX];
     radial_ed<NMAX>(p.rp, sp.r, Rn, dRn);
-    const int width = p.canon ? p.C.nS : p.nA;
-    c2* out = p.dA + (size_t)jl * width * 3;
+    // canon: element (slot, xyz) of neighbour jl is out[(slot * 3 + xyz) * 32]
+    c2* out = p.canon ? p.dA + (size_t)(jl >> 5) * p.C.nS * 3 * 32 + (jl & 31) : p.dA + (size_t)jl * p.nA * 3;
     // functions of other species are identically zero for this neighbour (one species: every canonical slot is written below)
-    if (!p.canon || p.C.nQ > 1) for (int a = 0; a < width * 3; ++a) out[a] = c2{0.0, 0.0};
+    if (!p.canon) for (int a = 0; a < p.nA * 3; ++a) out[a] = c2{0.0, 0.0};
+    else if (p.C.nQ > 1) for (int a = 0; a < p.C.nS * 3; ++a) out[(size_t)a * 32] = c2{0.0, 0.0};
     const int* cmap = p.C.colmap + (size_t)q * p.C.nPused;
     const double rx = x * sp.rinv, ry = y * sp.rinv, rz = z * sp.rinv;
     for_each_lm_ed(p.ap, sp, [&](int l, int m, double Pt, double dP, double epr, double epi) {
@@ -1940,7 +1942,7 @@ __global__ void __launch_bounds__(128) k_dA(const dAParams p)
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
                     g[k] = c2{dRn[n] * rh[k] * Y.x + Rn[n] * gY[k].x, dRn[n] * rh[k] * Y.y + Rn[n] * gY[k].y};
-                if (p.canon) { for (int k = 0; k < 3; ++k) out[(size_t)(base + n) * 3 + k] = g[k]; continue; }
+                if (p.canon) { for (int k = 0; k < 3; ++k) out[((size_t)(base + n) * 3 + k) * 32] = g[k]; continue; }
                 if (apos >= 0) for (int k = 0; k < 3; ++k) out[(size_t)apos * 3 + k] = g[k];
                 if (aneg >= 0) {
                     const double sg = (m & 1) ? -1.0 : 1.0;
@@ -2021,8 +2023,7 @@ static __global__ void k_dB(long long nJ, int nB, int nAA, int ncomp, const int*
 // its values depend on the environment only, not on the neighbour, so they are computed once per environment and row tile
 // (phase W, one thread per entry) and then applied to all neighbours (phase D): one CTA per environment, lane = neighbour,
 // warp = group of RW consecutive rows.  dA of the <= 32 neighbours of a pass lives in shared memory as planes [slot][xyz][lane]
-// over the canonical slots (pitch 33: the transposing store and the lane-contiguous LDS.128 of phase D are both
-// conflict-free); the weight of an entry is one broadcast LDS.128.  A warp stages the results of its group in a private
+// over the canonical slots (k_dA writes that layout, in 32-neighbour tiles of the chunk); the weight of an entry is one broadcast LDS.128.  A warp stages the results of its group in a private
 // strip of shared memory and writes them out itself, several neighbours' contiguous (RW x 3 x NC) runs per instruction, so
 // phase D needs no CTA barrier: the warps of a tile run decoupled, groups dealt longest-first.
 // Bound: shared-memory bandwidth -- 48 B of dA per lane and entry for 6 NC DFMAs.
@@ -2031,23 +2032,23 @@ struct DbEnvParams {
     int nA, nS, nB, nT, maxf, pireal, ET;
     const int* tile_grp;      // [nT + 1] position of each row tile's first group in grp_list
     const int* tile_ent;      // [nT + 1] first entry of each row tile (<= ET entries per tile)
-    const int* grp_list;      // first row of each group, dealt longest-first within a tile (warp w takes w, w + nwarps, ...)
-    const int* row_ent;       // [nB + 1] entries of each row
+    const int4* grp_list;     // (first row, first entry, end of row 0, end of row 1) of each group, entries relative to the tile;
+                              // dealt longest-first within a tile (warp w takes positions w, w + nwarps, ...)
     const int* ent_a;         // [nE] canonical slot of the entry
     const int* ent_con;       // [nE + 1] contributions of each entry
     const int* con_k;         // [nC] 4 * (non-zero of A2Bmap) + the neg / odd bits of the A-code of the differentiated factor
     const int* con_f;         // [nC][maxf] the other factors of the product (index into A), -1 = none
     const c2* val; const c2* A; const c2* dA; double* dB;
 };
-constexpr int kDbPitch = 33;
+constexpr int kDbPitch = 32;
 ACE_HD constexpr int db_threads(int NC) { return NC == 1 ? 1024 : 512; }   // one CTA per SM (the dA planes fill shared memory): as many warps as the registers allow
 ACE_HD constexpr int db_rows(int NC) { return NC == 1 ? 2 : 1; }           // rows per group
 ACE_HD constexpr int db_strip(int NC) { return (db_rows(NC) * 3 * NC) | 1; }   // doubles per lane in a warp's staging strip
-inline size_t db_env_fixed_smem(int nA, int nS, int NC)
+inline size_t db_env_fixed_smem(int nA, int nS, int NC, int threads)
 {
-    return ((size_t)nS * 3 * kDbPitch + nA) * sizeof(c2) + (size_t)(db_threads(NC) / 32) * 32 * db_strip(NC) * sizeof(double);
+    return ((size_t)nS * 3 * kDbPitch + nA) * sizeof(c2) + (size_t)(threads / 32) * 32 * db_strip(NC) * sizeof(double);
 }
-inline size_t db_env_smem(int nA, int nS, int ET, int NC) { return db_env_fixed_smem(nA, nS, NC) + (size_t)ET * (NC * sizeof(c2) + sizeof(int)); }
+inline size_t db_env_smem(int nA, int nS, int ET, int NC, int threads) { return db_env_fixed_smem(nA, nS, NC, threads) + (size_t)ET * (NC * sizeof(c2) + sizeof(int)); }
 
 template <int NC>
 __global__ void __launch_bounds__(db_threads(NC), 1) k_dB_env(const DbEnvParams p)
@@ -2069,13 +2070,10 @@ __global__ void __launch_bounds__(db_threads(NC), 1) k_dB_env(const DbEnvParams 
     for (int jt = 0; jt < J; jt += 32) {
         const int nj = (J - jt < 32) ? (J - jt) : 32;
         __syncthreads();                                         // the planes of the previous pass are no longer read
-        for (int j = warp; j < 32; j += nwarps) {
-            if (j < nj) {
-                const c2* src = p.dA + (size_t)(j0 + jt + j) * nS3;
-                for (int x = lane; x < nS3; x += 32) planes[(size_t)x * kDbPitch + j] = src[x];
-            } else {
-                for (int x = lane; x < nS3; x += 32) planes[(size_t)x * kDbPitch + j] = c2{0.0, 0.0};
-            }
+        {   // k_dA wrote dA in 32-neighbour tiles of the chunk: a plane row is one or two contiguous runs
+            const long long gj = j0 + jt + lane;
+            const c2* src = p.dA + (size_t)(gj >> 5) * nS3 * 32 + (gj & 31);
+            for (int x = warp; x < nS3; x += nwarps) planes[x * kDbPitch + lane] = lane < nj ? src[(size_t)x * 32] : c2{0.0, 0.0};
         }
         for (int t = 0; t < p.nT; ++t) {
             const int g0 = __ldg(p.tile_grp + t), g1 = __ldg(p.tile_grp + t + 1);
@@ -2113,40 +2111,47 @@ __global__ void __launch_bounds__(db_threads(NC), 1) k_dB_env(const DbEnvParams 
             __syncthreads();
             // phase D: one warp per group of RW rows, one lane per neighbour; no CTA barrier inside
             for (int pos = g0 + warp; pos < g1; pos += nwarps) {
-                const int r0 = __ldg(p.grp_list + pos);
+                const int4 gd = __ldg(p.grp_list + pos);
+                const int r0 = gd.x;
                 const int nr = (p.nB - r0 < RW) ? (p.nB - r0) : RW;
-                for (int rr = 0; rr < nr; ++rr) {
-                    double acc[3][NC];
 #pragma unroll
-                    for (int d = 0; d < 3; ++d)
+                for (int rr = 0; rr < RW; ++rr) {
+                    if (rr < nr) {
+                        double acc[3][NC];
 #pragma unroll
-                        for (int c = 0; c < NC; ++c) acc[d][c] = 0.0;
-                    const int i1 = __ldg(p.row_ent + r0 + rr + 1) - e0;
+                        for (int d = 0; d < 3; ++d)
+#pragma unroll
+                            for (int c = 0; c < NC; ++c) acc[d][c] = 0.0;
+                        const int i1 = rr == 0 ? gd.z : gd.w;
 #pragma unroll 2
-                    for (int i = __ldg(p.row_ent + r0 + rr) - e0; i < i1; ++i) {
-                        const c2* pl = planes + Ea[i] + lane;
-                        const c2 x0 = pl[0], x1 = pl[kDbPitch], x2 = pl[2 * kDbPitch];
-                        const c2* wr = Ws + (size_t)i * NC;
+                        for (int i = rr == 0 ? gd.y : gd.z; i < i1; ++i) {
+                            const c2* pl = planes + Ea[i] + lane;
+                            const c2 x0 = pl[0], x1 = pl[kDbPitch], x2 = pl[2 * kDbPitch];
+                            const c2* wr = Ws + (size_t)i * NC;
 #pragma unroll
-                        for (int c = 0; c < NC; ++c) {
-                            const c2 w = wr[c];
-                            acc[0][c] = fma(w.x, x0.x, fma(w.y, x0.y, acc[0][c]));
-                            acc[1][c] = fma(w.x, x1.x, fma(w.y, x1.y, acc[1][c]));
-                            acc[2][c] = fma(w.x, x2.x, fma(w.y, x2.y, acc[2][c]));
+                            for (int c = 0; c < NC; ++c) {
+                                const c2 w = wr[c];
+                                acc[0][c] = fma(w.x, x0.x, fma(w.y, x0.y, acc[0][c]));
+                                acc[1][c] = fma(w.x, x1.x, fma(w.y, x1.y, acc[1][c]));
+                                acc[2][c] = fma(w.x, x2.x, fma(w.y, x2.y, acc[2][c]));
+                            }
                         }
+                        double* o = strip + lane * SP + rr * 3 * NC;
+#pragma unroll
+                        for (int d = 0; d < 3; ++d)
+#pragma unroll
+                            for (int c = 0; c < NC; ++c) o[d * NC + c] = acc[d][c];
                     }
-                    double* o = strip + lane * SP + rr * 3 * NC;
-#pragma unroll
-                    for (int d = 0; d < 3; ++d)
-#pragma unroll
-                        for (int c = 0; c < NC; ++c) o[d * NC + c] = acc[d][c];
                 }
                 __syncwarp();
                 // JPER neighbours' contiguous runs of (nr x 3 x NC) doubles per store instruction
                 const int len = nr * 3 * NC, jj = lane / L, x = lane - jj * L;
                 if (jj < JPER && x < len) {
-                    for (int jb = jj; jb < nj; jb += JPER)
-                        p.dB[((size_t)(j0 + jt + jb) * p.nB + r0) * 3 * NC + x] = strip[jb * SP + x];
+                    const size_t dstep = (size_t)JPER * p.nB * 3 * NC;
+                    double* dst = p.dB + ((size_t)(j0 + jt + jj) * p.nB + r0) * 3 * NC + x;
+                    const double* src = strip + jj * SP + x;
+#pragma unroll 4
+                    for (int jb = jj; jb < nj; jb += JPER, dst += dstep, src += JPER * SP) *dst = *src;
                 }
                 __syncwarp();
             }

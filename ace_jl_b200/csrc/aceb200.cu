@@ -154,8 +154,8 @@ struct aceb200_model {
     // k_basis_stream (fused B = A2Bmap . prod A): leaf stream per warp; depends on the tables only, not on c
     BStream bs;                                // B = A2Bmap . AA
     // k_dB_env (dB = W_e . dA): static sparsity pattern of W; depends on the tables only
-    struct DbPack { bool ok = false; int nT = 0, maxf = 0, ET = 0; size_t smem = 0;
-                    const int *tile_grp = nullptr, *tile_ent = nullptr, *grp_list = nullptr, *row_ent = nullptr, *ent_a = nullptr, *ent_con = nullptr, *con_k = nullptr, *con_f = nullptr; } db;
+    struct DbPack { bool ok = false; int nT = 0, maxf = 0, ET = 0, threads = 0; size_t smem = 0;
+                    const int *tile_grp = nullptr, *tile_ent = nullptr; const int4* grp_list = nullptr; const int *row_ent = nullptr, *ent_a = nullptr, *ent_con = nullptr, *con_k = nullptr, *con_f = nullptr; } db;
     const int *d_orders = nullptr, *d_spec = nullptr;
     const int *d_csr_ptr = nullptr, *d_csr_col = nullptr;
     const c2* d_csr_val = nullptr;
@@ -890,9 +890,6 @@ static void upload_db_pack(aceb200_model* m)
     m->db = aceb200_model::DbPack();
     if (!T.symreal || T.nB == 0 || T.maxord < 1 || !(T.ncomp == 1 || T.ncomp == 3 || T.ncomp == 9)) return;
     const int NC = T.ncomp, maxf = std::max(1, T.maxord - 1);
-    const size_t base = db_env_fixed_smem(T.nA, T.nS, NC);
-    const size_t limit = (size_t)m->smem_optin - 1024;
-    if (base + 8192 > limit) return;                         // the planes leave no room: the generic k_dAA + k_dB path runs
     std::vector<int> row_ent(1, 0), ent_a, ent_con(1, 0), con_k, con_f;
     int emax = 0;
     for (int r = 0; r < T.nB; ++r) {
@@ -915,30 +912,47 @@ static void upload_db_pack(aceb200_model* m)
         row_ent.push_back((int)ent_a.size());
         emax = std::max(emax, row_ent[r + 1] - row_ent[r]);
     }
-    const int RW = db_rows(NC), nw = db_threads(NC) / 32, ngrp = (T.nB + RW - 1) / RW;
-    const int ET = (int)std::min<size_t>((limit - base) / (NC * sizeof(c2) + sizeof(int)), std::max<size_t>(ent_a.size(), 1));
+    const int RW = db_rows(NC), ngrp = (T.nB + RW - 1) / RW;
     auto gent = [&](int g) { return row_ent[std::min(T.nB, (g + 1) * RW)] - row_ent[g * RW]; };
-    std::vector<int> tile_grp(1, 0), tile_ent(1, 0), grp_list;
-    for (int g = 0; g < ngrp;) {
-        int g1 = g;
-        while (g1 < ngrp && row_ent[std::min(T.nB, (g1 + 1) * RW)] - row_ent[g * RW] <= ET) ++g1;
-        if (g1 == g) return;                                  // one group's weights do not fit: generic path
-        // deal the groups of the tile to the warps longest-first, in snake order: position w + k nw belongs to warp w
-        std::vector<int> order(g1 - g);
-        for (int i = 0; i < g1 - g; ++i) order[i] = g + i;
-        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return gent(x) > gent(y); });
-        for (size_t i = 0; i < order.size(); ++i) {
-            const size_t round = i / nw, k = i % nw;
-            const size_t src = round * nw + ((round & 1) ? std::min<size_t>(order.size() - round * nw, nw) - 1 - k : k);
-            grp_list.push_back(order[src] * RW);
+    std::vector<int> tile_grp, tile_ent;
+    std::vector<int4> grp_list;
+    int threads = 0, ET = 0;
+    // cut the rows into tiles whose weights fit beside the planes and the warps' strips; false: a group does not fit
+    auto cut = [&](int thr, size_t limit) {
+        const size_t base = db_env_fixed_smem(T.nA, T.nS, NC, thr);
+        if (base + 4096 > limit) return false;
+        const int nw = thr / 32;
+        ET = (int)std::min<size_t>((limit - base) / (NC * sizeof(c2) + sizeof(int)), std::max<size_t>(ent_a.size(), 1));
+        tile_grp.assign(1, 0); tile_ent.assign(1, 0); grp_list.clear();
+        for (int g = 0; g < ngrp;) {
+            int g1 = g;
+            while (g1 < ngrp && row_ent[std::min(T.nB, (g1 + 1) * RW)] - row_ent[g * RW] <= ET) ++g1;
+            if (g1 == g) return false;
+            // deal the groups of the tile to the warps longest-first, in snake order: position w + k nw belongs to warp w
+            std::vector<int> order(g1 - g);
+            for (int i = 0; i < g1 - g; ++i) order[i] = g + i;
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return gent(x) > gent(y); });
+            for (size_t i = 0; i < order.size(); ++i) {
+                const size_t round = i / nw, k = i % nw;
+                const size_t src = round * nw + ((round & 1) ? std::min<size_t>(order.size() - round * nw, nw) - 1 - k : k);
+                const int r0 = order[src] * RW, eb = row_ent[g * RW];
+                grp_list.push_back(int4{r0, row_ent[r0] - eb, row_ent[std::min(T.nB, r0 + 1)] - eb, row_ent[std::min(T.nB, r0 + 2)] - eb});
+            }
+            tile_grp.push_back(g1);
+            tile_ent.push_back(row_ent[std::min(T.nB, g1 * RW)]);
+            g = g1;
         }
-        tile_grp.push_back(g1);
-        tile_ent.push_back(row_ent[std::min(T.nB, g1 * RW)]);
-        g = g1;
-    }
+        threads = thr;
+        return true;
+    };
+    // two CTAs of half the threads per SM when at most three tiles result (the phases of one environment then overlap with
+    // the other's), else one CTA with all the warps the registers allow; neither: the generic k_dAA + k_dB path runs
+    const bool two = !getenv("ACEB200_DB_ONE_CTA") && cut(db_threads(NC) / 2, ((size_t)m->smem_optin + 1024) / 2 - 1024 - 256) && tile_grp.size() <= 4;
+    if (!two && !cut(db_threads(NC), (size_t)m->smem_optin - 1024)) return;
     auto& D = m->db;
     D.nT = (int)tile_grp.size() - 1; D.maxf = maxf; D.ET = std::max(ET, 1);
-    D.smem = db_env_smem(T.nA, T.nS, D.ET, NC);
+    D.threads = threads;
+    D.smem = db_env_smem(T.nA, T.nS, D.ET, NC, threads);
     D.tile_grp = upload(m->pool, tile_grp); D.tile_ent = upload(m->pool, tile_ent); D.grp_list = upload(m->pool, grp_list);
     D.row_ent = upload(m->pool, row_ent);
     if (ent_a.empty()) ent_a.push_back(0);
@@ -1718,7 +1732,7 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
                 CU(cudaGetLastError()); m->launches++;
             }
             if (need_dA) {
-                L.ws_dA.reserve(std::max<long long>(nj, 1) * nA * 3 * sizeof(c2));
+                L.ws_dA.reserve(std::max<long long>((nj + 31) / 32 * 32, 1) * nA * 3 * sizeof(c2));
                 dA_dev = L.ws_dA.as<c2>();
                 launch_dA(m, B, nj, dA_dev, dB_fusable);          // k_dB_env reads the canonical slots only
             }
@@ -1731,12 +1745,12 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
                 DbEnvParams q;
                 q.nenv = ne; q.off = st.off; q.gate = t_ctx->ws_err.as<int>();
                 q.nA = nA; q.nS = T.nS; q.nB = nB; q.nT = m->db.nT; q.maxf = m->db.maxf; q.pireal = T.pireal; q.ET = m->db.ET;
-                q.tile_grp = m->db.tile_grp; q.tile_ent = m->db.tile_ent; q.grp_list = m->db.grp_list; q.row_ent = m->db.row_ent; q.ent_a = m->db.ent_a; q.ent_con = m->db.ent_con;
+                q.tile_grp = m->db.tile_grp; q.tile_ent = m->db.tile_ent; q.grp_list = m->db.grp_list; q.ent_a = m->db.ent_a; q.ent_con = m->db.ent_con;
                 q.con_k = m->db.con_k; q.con_f = m->db.con_f;
                 q.val = m->d_csr_val; q.A = L.ws_A.as<c2>(); q.dA = dA_dev; q.dB = dB_dev;
                 const size_t smem = m->db.smem;
 #define ACE_DBF(NCV) { auto kfn = k_dB_env<NCV>; CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-                ACE_LAUNCH(kfn, dim3((unsigned)ne), dim3(db_threads(NCV)), smem, L.stream, q); }
+                ACE_LAUNCH(kfn, dim3((unsigned)ne), dim3(m->db.threads), smem, L.stream, q); }
                 if (ncomp == 1) ACE_DBF(1) else if (ncomp == 3) ACE_DBF(3) else ACE_DBF(9)
 #undef ACE_DBF
                 CU(cudaGetLastError()); m->launches++;
