@@ -2041,7 +2041,7 @@ struct DbEnvParams {
     const c2* val; const c2* A; const c2* dA; double* dB;
 };
 constexpr int kDbPitch = 32;
-ACE_HD constexpr int db_threads(int NC) { return NC == 1 ? 1024 : 512; }   // one CTA per SM (the dA planes fill shared memory): as many warps as the registers allow
+ACE_HD constexpr int db_threads(int NC) { return NC == 1 ? 1024 : NC == 3 ? 512 : 256; }   // one CTA per SM (the dA planes fill shared memory): as many warps as the registers allow
 ACE_HD constexpr int db_rows(int NC) { return NC == 1 ? 2 : 1; }           // rows per group
 ACE_HD constexpr int db_strip(int NC) { return (db_rows(NC) * 3 * NC) | 1; }   // doubles per lane in a warp's staging strip
 inline size_t db_env_fixed_smem(int nA, int nS, int NC, int threads)

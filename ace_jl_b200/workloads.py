@@ -66,6 +66,11 @@ WORKLOADS["4b"] = WORKLOADS["4"]
 WORKLOADS["1d"] = Workload("1d", "SymmetricBasis evaluate_d (Jacobian dB), Invariant, ord=3, maxdeg=10, wL=1.5 SparseBasis, 30 neighbours (BASELINE config 1, evaluate_d)",
                            lambda: sparse_basis(Invariant(), 3, 10), "dB", 1, 30, 100_000, seed=20248, cache_key="inv_3_10")
 
+WORKLOADS["4ad"] = Workload("4ad", "SymmetricBasis evaluate_d (Jacobian dB), EuclideanVector, ord=3, maxdeg=10, wL=1.5 SparseBasis, 30 neighbours (BASELINE config 4, L=1, evaluate_d)",
+                            lambda: sparse_basis(EuclideanVector(), 3, 10), "dB", 1, 30, 40_000, seed=20249, cache_key="vec_3_10")
+WORKLOADS["4d"] = Workload("4d", "SymmetricBasis evaluate_d (Jacobian dB), EuclideanMatrix, ord=3, maxdeg=10, wL=1.5 SparseBasis, 30 neighbours (BASELINE config 4, L=2, evaluate_d)",
+                           lambda: sparse_basis(EuclideanMatrix(), 3, 10), "dB", 1, 30, 5_000, seed=20250, cache_key="mat_3_10")
+
 _BASIS_CACHE: Dict[str, SymmetricBasis] = {}
 
 

@@ -122,7 +122,10 @@ def default_cpu_sample(w, basis) -> int:
     """About 10 s of CPU work on 16 cores for the call (measured rates: config 2 ~ 1e5 env/s)."""
     from ace_jl_b200.workloads import algorithmic_work
     fl = algorithmic_work(basis, w.J, w.call, w.nprop)["flops_total"] * (10.0 if w.call == "EF" else 3.0)   # the oracle materialises dA
-    return int(max(500, min(100_000, 2.0e11 / fl)))
+    n = max(500, min(100_000, 2.0e11 / fl))
+    if w.call == "dB":                              # the Jacobian of the sample must fit in host memory: <= 4 GB
+        n = max(50, min(n, 4.0e9 / algorithmic_work(basis, w.J, w.call, w.nprop)["out_bytes"]))
+    return int(n)
 
 
 def workload_config(w, nenv, ngpu):
@@ -160,7 +163,7 @@ def run_reference_arm(args, w):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="2", help="BASELINE configuration: 1, 1d (evaluate_d), 2, 3, 4a, 4, 5, 5f")
+    ap.add_argument("--config", default="2", help="BASELINE configuration: 1, 1d (evaluate_d), 2, 3, 4a, 4, 4ad / 4d (evaluate_d), 5, 5f")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
