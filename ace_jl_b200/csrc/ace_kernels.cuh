@@ -1916,8 +1916,9 @@ __global__ void __launch_bounds__(128) k_dA(const dAParams p)
     // canon: element (slot, xyz) of neighbour jl is out[(slot * 3 + xyz) * 32]
     c2* out = p.canon ? p.dA + (size_t)(jl >> 5) * p.C.nS * 3 * 32 + (jl & 31) : p.dA + (size_t)jl * p.nA * 3;
     // functions of other species are identically zero for this neighbour (one species: every canonical slot is written below)
-    if (!p.canon) for (int a = 0; a < p.nA * 3; ++a) out[a] = c2{0.0, 0.0};
-    else if (p.C.nQ > 1) for (int a = 0; a < p.C.nS * 3; ++a) out[(size_t)a * 32] = c2{0.0, 0.0};
+    if (p.C.nQ <= 1) {}
+    else if (!p.canon) for (int a = 0; a < p.nA * 3; ++a) out[a] = c2{0.0, 0.0};
+    else for (int a = 0; a < p.C.nS * 3; ++a) out[(size_t)a * 32] = c2{0.0, 0.0};
     const int* cmap = p.C.colmap + (size_t)q * p.C.nPused;
     const double rx = x * sp.rinv, ry = y * sp.rinv, rz = z * sp.rinv;
     for_each_lm_ed(p.ap, sp, [&](int l, int m, double Pt, double dP, double epr, double epi) {
