@@ -2030,15 +2030,14 @@ static __global__ void k_dB(long long nJ, int nB, int nAA, int ncomp, const int*
 // Bound: shared-memory bandwidth -- 48 B of dA per lane and entry for 6 NC DFMAs.
 struct DbEnvParams {
     long long nenv; const long long* off; const int* gate;
-    int nA, nS, nB, nT, maxf, pireal, ET;
+    int nA, nS, nB, nT, pireal, ET;
     const int* tile_grp;      // [nT + 1] position of each row tile's first group in grp_list
     const int* tile_ent;      // [nT + 1] first entry of each row tile (<= ET entries per tile)
     const int4* grp_list;     // (first row, first entry, end of row 0, end of row 1) of each group, entries relative to the tile;
                               // dealt longest-first within a tile (warp w takes positions w, w + nwarps, ...)
-    const int* ent_a;         // [nE] canonical slot of the entry
-    const int* ent_con;       // [nE + 1] contributions of each entry
-    const int* con_k;         // [nC] 4 * (non-zero of A2Bmap) + the neg / odd bits of the A-code of the differentiated factor
-    const int* con_f;         // [nC][maxf] the other factors of the product (index into A), -1 = none
+    const int4* ent_rec;      // [nE] (plane offset of the entry's canonical slot, first contribution, end of contributions, 0)
+    const int4* con_rec;      // [nC] (4 * (non-zero of A2Bmap) + the neg / odd bits of the A-code of the differentiated factor,
+                              //       the up to three other factors of the product (index into A), -1 = none)
     const c2* val; const c2* A; const c2* dA; double* dB;
 };
 constexpr int kDbPitch = 32;
@@ -2074,6 +2073,7 @@ __global__ void __launch_bounds__(db_threads(NC), 1) k_dB_env(const DbEnvParams 
         {   // k_dA wrote dA in 32-neighbour tiles of the chunk: a plane row is one or two contiguous runs
             const long long gj = j0 + jt + lane;
             const c2* src = p.dA + (size_t)(gj >> 5) * nS3 * 32 + (gj & 31);
+#pragma unroll 4
             for (int x = warp; x < nS3; x += nwarps) planes[x * kDbPitch + lane] = lane < nj ? src[(size_t)x * 32] : c2{0.0, 0.0};
         }
         for (int t = 0; t < p.nT; ++t) {
@@ -2085,17 +2085,16 @@ __global__ void __launch_bounds__(db_threads(NC), 1) k_dB_env(const DbEnvParams 
                 double m0[NC], m1[NC];
 #pragma unroll
                 for (int c = 0; c < NC; ++c) { m0[c] = 0.0; m1[c] = 0.0; }
-                const int q1 = __ldg(p.ent_con + i + 1);
-                for (int q = __ldg(p.ent_con + i); q < q1; ++q) {
+                const int4 er = __ldg(p.ent_rec + i);
+                for (int q = er.y; q < er.z; ++q) {
+                    const int4 cr = __ldg(p.con_rec + q);
+                    const c2* v = p.val + (size_t)(cr.x >> 2) * NC;
                     c2 g = c2{1.0, 0.0};
-                    for (int f = 0; f < p.maxf; ++f) {
-                        const int a = __ldg(p.con_f + (size_t)q * p.maxf + f);
-                        if (a >= 0) g = cmul(g, As[a]);
-                    }
-                    const int kc = __ldg(p.con_k + q);
+                    if (cr.y >= 0) g = As[cr.y];
+                    if (cr.z >= 0) g = cmul(g, As[cr.z]);
+                    if (cr.w >= 0) g = cmul(g, As[cr.w]);
                     // the differentiated factor is decode_A(slot value): Re flips for odd negative m, Im for even negative m
-                    const double sx = (kc & 2) ? -1.0 : 1.0, sy = ((kc & 1) && !(kc & 2)) ? -1.0 : 1.0;
-                    const c2* v = p.val + (size_t)(kc >> 2) * NC;
+                    const double sx = (cr.x & 2) ? -1.0 : 1.0, sy = ((cr.x & 1) && !(cr.x & 2)) ? -1.0 : 1.0;
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
                         const c2 vc = v[c];
@@ -2107,12 +2106,14 @@ __global__ void __launch_bounds__(db_threads(NC), 1) k_dB_env(const DbEnvParams 
                 }
 #pragma unroll
                 for (int c = 0; c < NC; ++c) Ws[(size_t)(i - e0) * NC + c] = c2{m0[c], m1[c]};
-                Ea[i - e0] = __ldg(p.ent_a + i) * 3 * kDbPitch;
+                Ea[i - e0] = er.x;
             }
             __syncthreads();
             // phase D: one warp per group of RW rows, one lane per neighbour; no CTA barrier inside
+            int4 gd_next = g0 + warp < g1 ? __ldg(p.grp_list + g0 + warp) : int4{0, 0, 0, 0};
             for (int pos = g0 + warp; pos < g1; pos += nwarps) {
-                const int4 gd = __ldg(p.grp_list + pos);
+                const int4 gd = gd_next;
+                if (pos + nwarps < g1) gd_next = __ldg(p.grp_list + pos + nwarps);     // the next descriptor arrives during this group
                 const int r0 = gd.x;
                 const int nr = (p.nB - r0 < RW) ? (p.nB - r0) : RW;
 #pragma unroll

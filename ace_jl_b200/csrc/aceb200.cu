@@ -154,8 +154,8 @@ struct aceb200_model {
     // k_basis_stream (fused B = A2Bmap . prod A): leaf stream per warp; depends on the tables only, not on c
     BStream bs;                                // B = A2Bmap . AA
     // k_dB_env (dB = W_e . dA): static sparsity pattern of W; depends on the tables only
-    struct DbPack { bool ok = false; int nT = 0, maxf = 0, ET = 0, threads = 0; size_t smem = 0;
-                    const int *tile_grp = nullptr, *tile_ent = nullptr; const int4* grp_list = nullptr; const int *row_ent = nullptr, *ent_a = nullptr, *ent_con = nullptr, *con_k = nullptr, *con_f = nullptr; } db;
+    struct DbPack { bool ok = false; int nT = 0, ET = 0, threads = 0; size_t smem = 0;
+                    const int *tile_grp = nullptr, *tile_ent = nullptr; const int4 *grp_list = nullptr, *ent_rec = nullptr, *con_rec = nullptr; } db;
     const int *d_orders = nullptr, *d_spec = nullptr;
     const int *d_csr_ptr = nullptr, *d_csr_col = nullptr;
     const c2* d_csr_val = nullptr;
@@ -888,9 +888,11 @@ static void upload_db_pack(aceb200_model* m)
 {
     const auto& T = m->T;
     m->db = aceb200_model::DbPack();
-    if (!T.symreal || T.nB == 0 || T.maxord < 1 || !(T.ncomp == 1 || T.ncomp == 3 || T.ncomp == 9)) return;
-    const int NC = T.ncomp, maxf = std::max(1, T.maxord - 1);
-    std::vector<int> row_ent(1, 0), ent_a, ent_con(1, 0), con_k, con_f;
+    // (a contribution record holds up to three other factors: correlation order <= 4)
+    if (!T.symreal || T.nB == 0 || T.maxord < 1 || T.maxord > 4 || !(T.ncomp == 1 || T.ncomp == 3 || T.ncomp == 9)) return;
+    const int NC = T.ncomp;
+    std::vector<int> row_ent(1, 0), ent_a;
+    std::vector<int4> ent_rec, con_rec;
     int emax = 0;
     for (int r = 0; r < T.nB; ++r) {
         std::map<int, std::vector<std::pair<int, int>>> by_a;            // canonical slot -> (k, t), ascending, contributions in (k, t) order
@@ -900,14 +902,14 @@ static void upload_db_pack(aceb200_model* m)
         }
         for (auto& kv : by_a) {
             ent_a.push_back(kv.first);
+            const int q0 = (int)con_rec.size();
             for (auto& kt : kv.second) {
                 const int i = T.csr_col[kt.first];
-                con_k.push_back(kt.first * 4 + (T.iA_code[T.spec[(size_t)i * T.maxord + kt.second]] & 3));
-                int nf = 0;
-                for (int s2 = 0; s2 < T.orders[i]; ++s2) if (s2 != kt.second) { con_f.push_back(T.spec[(size_t)i * T.maxord + s2]); ++nf; }
-                for (; nf < maxf; ++nf) con_f.push_back(-1);
+                int f[3] = {-1, -1, -1}, nf = 0;
+                for (int s2 = 0; s2 < T.orders[i]; ++s2) if (s2 != kt.second) f[nf++] = T.spec[(size_t)i * T.maxord + s2];
+                con_rec.push_back(int4{kt.first * 4 + (T.iA_code[T.spec[(size_t)i * T.maxord + kt.second]] & 3), f[0], f[1], f[2]});
             }
-            ent_con.push_back((int)con_k.size());
+            ent_rec.push_back(int4{kv.first * 3 * kDbPitch, q0, (int)con_rec.size(), 0});
         }
         row_ent.push_back((int)ent_a.size());
         emax = std::max(emax, row_ent[r + 1] - row_ent[r]);
@@ -950,15 +952,13 @@ static void upload_db_pack(aceb200_model* m)
     const bool two = !getenv("ACEB200_DB_ONE_CTA") && cut(db_threads(NC) / 2, ((size_t)m->smem_optin + 1024) / 2 - 1024 - 256) && tile_grp.size() <= 4;
     if (!two && !cut(db_threads(NC), (size_t)m->smem_optin - 1024)) return;
     auto& D = m->db;
-    D.nT = (int)tile_grp.size() - 1; D.maxf = maxf; D.ET = std::max(ET, 1);
+    D.nT = (int)tile_grp.size() - 1; D.ET = std::max(ET, 1);
     D.threads = threads;
     D.smem = db_env_smem(T.nA, T.nS, D.ET, NC, threads);
     D.tile_grp = upload(m->pool, tile_grp); D.tile_ent = upload(m->pool, tile_ent); D.grp_list = upload(m->pool, grp_list);
-    D.row_ent = upload(m->pool, row_ent);
-    if (ent_a.empty()) ent_a.push_back(0);
-    if (con_k.empty()) { con_k.push_back(0); con_f.assign(maxf, -1); }
-    D.ent_a = upload(m->pool, ent_a); D.ent_con = upload(m->pool, ent_con);
-    D.con_k = upload(m->pool, con_k); D.con_f = upload(m->pool, con_f);
+    if (ent_rec.empty()) ent_rec.push_back(int4{0, 0, 0, 0});
+    if (con_rec.empty()) con_rec.push_back(int4{0, -1, -1, -1});
+    D.ent_rec = upload(m->pool, ent_rec); D.con_rec = upload(m->pool, con_rec);
     D.ok = true;
 }
 
@@ -1744,9 +1744,8 @@ static void run(aceb200_model* m, const aceb200_batch* b, int want, const Output
                 else { L.ws_G.reserve((size_t)nj * nB * 24 * ncomp * cs); dB_dev = L.ws_G.as<double>(); }
                 DbEnvParams q;
                 q.nenv = ne; q.off = st.off; q.gate = t_ctx->ws_err.as<int>();
-                q.nA = nA; q.nS = T.nS; q.nB = nB; q.nT = m->db.nT; q.maxf = m->db.maxf; q.pireal = T.pireal; q.ET = m->db.ET;
-                q.tile_grp = m->db.tile_grp; q.tile_ent = m->db.tile_ent; q.grp_list = m->db.grp_list; q.ent_a = m->db.ent_a; q.ent_con = m->db.ent_con;
-                q.con_k = m->db.con_k; q.con_f = m->db.con_f;
+                q.nA = nA; q.nS = T.nS; q.nB = nB; q.nT = m->db.nT; q.pireal = T.pireal; q.ET = m->db.ET;
+                q.tile_grp = m->db.tile_grp; q.tile_ent = m->db.tile_ent; q.grp_list = m->db.grp_list; q.ent_rec = m->db.ent_rec; q.con_rec = m->db.con_rec;
                 q.val = m->d_csr_val; q.A = L.ws_A.as<c2>(); q.dA = dA_dev; q.dB = dB_dev;
                 const size_t smem = m->db.smem;
 #define ACE_DBF(NCV) { auto kfn = k_dB_env<NCV>; CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
