@@ -736,10 +736,11 @@ static bool pack_bstream(aceb200_model* m, std::vector<std::vector<BLeaf>>& rows
     if (!basis_geom(nfac, nch, cw, QB, KB, W)) return false;
     const int cs = cw ? 2 : 1, nrows = (int)rows.size();
     const unsigned ONE = (unsigned)T.nS;
+    const bool masked = (nfac == 3 && nch >= 3 && nch <= 9);     // BasisGeom::MASKED: channel mask in bits 16.. of the second code word
     size_t nleaves = 0;
     for (auto& r : rows) {
         if (r.empty()) {      // a structurally empty row still produces its zeros
-            BLeaf L; L.c0 = ONE | (ONE << 16); L.c1 = ONE | (ONE << 16); L.w.assign((size_t)nch * cs, 0.0);
+            BLeaf L; L.c0 = ONE | (ONE << 16); L.c1 = masked ? ONE : (ONE | (ONE << 16)); L.w.assign((size_t)nch * cs, 0.0);
             r.push_back(L);
         }
         r.back().c0 |= kRowEnd;
@@ -763,12 +764,17 @@ static bool pack_bstream(aceb200_model* m, std::vector<std::vector<BLeaf>>& rows
     // contiguous row ranges balanced by cost: a leaf costs its product + nch channel updates, a row its share of a flush
     std::vector<int> cut(nw + 1, nrows);
     cut[0] = 0;
-    { const double cleaf = 14.0 + 6.0 * (nfac - 1) + (cw ? 3.0 : 2.0) * nch, crow = 8.0 + 14.0 * nch;
+    { const double cfix = 14.0 + 6.0 * (nfac - 1) + (masked ? 2.0 * nch : 0.0), cchn = cw ? 3.0 : 2.0, crow = 8.0 + 14.0 * nch;
+      auto rcost = [&](int r) {
+          double c = crow;
+          for (const BLeaf& L : rows[r]) c += cfix + cchn * (masked ? __builtin_popcount(L.c1 >> 16) : nch);
+          return c;
+      };
       double tot = 0.0, acc = 0.0;
-      for (int r = 0; r < nrows; ++r) tot += cleaf * rows[r].size() + crow;
+      for (int r = 0; r < nrows; ++r) tot += rcost(r);
       int w = 1;
       for (int r = 0; r < nrows && w < nw; ++r) {
-          acc += cleaf * rows[r].size() + crow;
+          acc += rcost(r);
           while (w < nw && acc * nw >= tot * w) cut[w++] = r + 1;
       } }
     size_t longest = 1;
@@ -782,7 +788,7 @@ static bool pack_bstream(aceb200_model* m, std::vector<std::vector<BLeaf>>& rows
             uint32_t* blk = &blocks[(((size_t)w * nchunks * KB) + il / 4) * QB * 4];
             const int k = (int)(il % 4);
             blk[k] = L ? L->c0 : (ONE | (ONE << 16));
-            if (cwords == 2) blk[4 + k] = L ? L->c1 : (ONE | (ONE << 16));
+            if (cwords == 2) blk[4 + k] = L ? L->c1 : (masked ? ONE : (ONE | (ONE << 16)));
             double* wd = reinterpret_cast<double*>(blk + 4 * cwords) + (size_t)k * nch * cs;
             for (int i = 0; i < nch * cs; ++i) wd[i] = L ? L->w[i] : 0.0;
             ++il;
@@ -796,9 +802,12 @@ static bool pack_bstream(aceb200_model* m, std::vector<std::vector<BLeaf>>& rows
     CU(cudaMemcpy(out.buf.p, blocks.data(), blocks.size() * 4, cudaMemcpyHostToDevice));
     out.nw = nw; out.nchunks = (int)nchunks; out.nfac = nfac; out.nch = nch; out.cw = cw; out.QB = QB; out.KB = KB; out.W = W; out.epl = epl;
     out.nrows = nrows; out.smem = smem_of(nw, epl);
-    if (getenv("ACEB200_VERBOSE"))
-        fprintf(stderr, "[aceb200] %s stream: NFAC=%d NCH=%d CW=%d EPL=%d, %d warps x %zu chunks of %d blocks, %zu leaves in %d rows, smem %zu B\n",
-                what, nfac, nch, (int)cw, epl, nw, nchunks, KB, nleaves, nrows, out.smem);
+    if (getenv("ACEB200_VERBOSE")) {
+        size_t active = 0;
+        for (auto& r : rows) for (const BLeaf& L : r) active += masked ? __builtin_popcount(L.c1 >> 16) : nch;
+        fprintf(stderr, "[aceb200] %s stream: NFAC=%d NCH=%d CW=%d EPL=%d, %d warps x %zu chunks of %d blocks, %zu leaves in %d rows (%.2f active channels per leaf), smem %zu B\n",
+                what, nfac, nch, (int)cw, epl, nw, nchunks, KB, nleaves, nrows, (double)active / std::max<size_t>(nleaves, 1), out.smem);
+    }
     return true;
 }
 
@@ -851,6 +860,10 @@ static void upload_basis_stream(aceb200_model* m)
                 if (T.symreal) put(c, pr, qr);
                 else { put(2 * c, pr, qr); put(2 * c + 1, pi, qi); }
             }
+            unsigned mask = 0u;
+            for (int q = 0; q < nch; ++q) for (int i = 0; i < cs; ++i) if (L.w[(size_t)q * cs + i] != 0.0) mask |= 1u << q;
+            if (mask == 0u) continue;                            // a non-zero of A2Bmap whose value is exactly zero in every component
+            if (nfac == 3 && nch >= 3 && nch <= 9) L.c1 = (L.c1 & 0xffffu) | (mask << 16);   // BasisGeom::MASKED
             rows[r].push_back(L);
         }
     }
