@@ -1076,10 +1076,14 @@ template <int NFAC, int NCH, bool CW>
 struct BasisGeom {
     static constexpr int CS = CW ? 2 : 1;
     static constexpr bool MASKED = (NFAC == 3 && NCH >= 3 && NCH <= 9);  // bits 16.. of the second code word: channel mask of the leaf
-    static constexpr int CWORDS = (NFAC <= 2) ? 1 : 2;                   // code words per leaf
-    static constexpr int QB = CWORDS + 2 * NCH * CS;                     // uint4 per block (4 leaves)
-    static constexpr int KB = (QB * 16 >= 1024) ? 1 : (QB * 16 >= 512) ? 2 : ((QB * 16 >= 256) ? 4 : ((QB * 16 >= 128) ? 8 : 16));   // blocks per ring chunk (~1 KB)
-    static constexpr int CH = KB * QB;                                   // uint4 per chunk
+    // a leaf is one contiguous record: header (the two code words; padded to 16 bytes when the weights are read with LDS.128),
+    // then NCH x CS weights.  The walk is a running pointer with compile-time offsets (the earlier block-of-four layout cost
+    // ~8 index instructions per leaf).
+    static constexpr int NWD = NCH * CS;                                 // weights (doubles) per leaf
+    static constexpr int HDR = (NWD == 1) ? 8 : 16;
+    static constexpr int LB = (HDR + 8 * NWD + 15) / 16 * 16;            // bytes per leaf
+    static constexpr int LPC = (1024 / LB > 0) ? 1024 / LB : 1;          // leaves per ring chunk (~1 KB; 2 KB chunks measured the same at 4b)
+    static constexpr int CH = LPC * LB / 16;                             // uint4 per chunk
     static constexpr int NSLOT = 4;                                      // ring slots: three chunks in flight ahead of the one being read (a
                                                                          // two-slot ring left the L2 latency of the ~1 KB chunks exposed: the
                                                                          // mbarrier wait was the top stall of the 9- and 16-channel streams)
@@ -1090,7 +1094,7 @@ struct BasisGeom {
 
 struct BasisParams {
     int nS, nw, nchunks;
-    int nblk[kBasisMaxWarps];                // blocks of each warp's sub-stream
+    int nleaf[kBasisMaxWarps];               // leaves of each warp's sub-stream
     int row0[kBasisMaxWarps];                // first B row of each warp
     const uint4* stream;                     // [nw][nchunks][CH]
     const c2* Ac; long long ldA;
@@ -1105,7 +1109,7 @@ template <int NFAC, int NCH, bool CW, int EPL>
 __global__ void __launch_bounds__((EPL == 2 && NCH >= 9) ? 384 : 32 * kBasisMaxWarps, 1) k_basis_stream(const BasisParams p)
 {
     typedef BasisGeom<NFAC, NCH, CW> G;
-    constexpr int CS = G::CS, CH = G::CH, QB = G::QB, KB = G::KB, W = G::W, WP = G::WP, NSLOT = G::NSLOT;
+    constexpr int CS = G::CS, CH = G::CH, LPC = G::LPC, W = G::W, WP = G::WP, NSLOT = G::NSLOT;
     constexpr int TW = 32 * EPL;                                        // environments per tile
     constexpr int RSH = (EPL == 1) ? 9 : 10;                            // log2 of the tile row pitch in bytes
     const int NW = p.nw;
@@ -1130,8 +1134,8 @@ __global__ void __launch_bounds__((EPL == 2 && NCH >= 9) ? 384 : 32 * kBasisMaxW
         for (int j = 0; j < EPL; ++j) As[p.nS * TW + lane + 32 * j] = c2{1.0, 0.0};
     }
     __syncthreads();
-    const int nblkw = p.nblk[warp];
-    const int nchw = (nblkw + KB - 1) / KB;
+    const int nlw = p.nleaf[warp];
+    const int nchw = (nlw + LPC - 1) / LPC;
     const uint4* stream = p.stream + (size_t)warp * p.nchunks * CH;
     const unsigned char* Ab = reinterpret_cast<const unsigned char*>(As) + lane * 16;
     const long long ntiles = (p.nenv + TW - 1) / TW;
@@ -1206,19 +1210,17 @@ __global__ void __launch_bounds__((EPL == 2 && NCH >= 9) ? 384 : 32 * kBasisMaxW
             if (pre < nchw) for (int k = lane; k < CH; k += 32) ring[pslot * CH + k] = __ldg(stream + (size_t)pre * CH + k);
             __syncwarp();
 #endif
-            const uint4* rb = ring + slot * CH;
-            const int nb = (nblkw - ch * KB < KB) ? nblkw - ch * KB : KB;
+            const unsigned char* lp = reinterpret_cast<const unsigned char*>(ring + slot * CH);
+            const int nl = (nlw - ch * LPC < LPC) ? nlw - ch * LPC : LPC;
             // One leaf per trip and NOT unrolled: the body (product + NCH channel updates for EPL environments + the
             // row-end path with its flush) is ~100-250 instructions; unrolled four times it overflowed the instruction
             // cache with a dozen warps at different places in it (ncu: "no instruction" became the top stall).
 #pragma unroll 1
-            for (int lf = 0; lf < 4 * nb; ++lf) {
+            for (int lf = 0; lf < nl; ++lf, lp += G::LB) {
                 {
-                    const int b = lf >> 2, k = lf & 3;
-                    const unsigned* blk = reinterpret_cast<const unsigned*>(rb + b * QB);
-                    const unsigned c = blk[k];
-                    const unsigned cc2 = (NFAC > 2) ? blk[4 + k] : 0u;
-                    const double* wl = reinterpret_cast<const double*>(blk + 4 * G::CWORDS) + k * NCH * CS;     // [NCH][CS]
+                    const uint2 cw2 = *reinterpret_cast<const uint2*>(lp);
+                    const unsigned c = cw2.x, cc2 = cw2.y;
+                    const double* wl = reinterpret_cast<const double*>(lp + G::HDR);                            // [NCH][CS]
                     c2 X[EPL];
 #pragma unroll
                     for (int j = 0; j < EPL; ++j) X[j] = lds_c2(Ab + 512 * j, (c & 0x3fffu) << RSH);

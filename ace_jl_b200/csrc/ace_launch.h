@@ -33,7 +33,7 @@ void stream_inst_nf3(int pb, bool cw, int epl, const StreamParams& p, int grid, 
 void stream_inst_nf4(int pb, bool cw, int epl, const StreamParams& p, int grid, size_t smem, cudaStream_t st);
 
 bool launch_basis_inst(int nfac, int nch, bool cw, int epl, const BasisParams& p, int grid, size_t smem, cudaStream_t st);
-bool basis_geom(int nfac, int nch, bool cw, int& QB, int& KB, int& W);
+bool basis_geom(int nfac, int nch, bool cw, int& LB, int& LPC, int& HDR, int& W);
 bool basis_epl2(int nch, bool cw);
 
 inline void launch_stream_inst(int nf, int pb, bool cw, int epl, const StreamParams& p, int grid, size_t smem, cudaStream_t st)

@@ -127,9 +127,9 @@ struct StreamPass { DevBuf blocks, tinfo, w0; int pb0 = 0; };
 // A packed leaf stream for k_basis_stream and its geometry
 struct BStream {
     DevBuf buf;
-    int nw = 0, nchunks = 0, nfac = 0, nch = 0, QB = 0, KB = 0, W = 0, epl = 1, nrows = 0;
+    int nw = 0, nchunks = 0, nfac = 0, nch = 0, LB = 0, LPC = 0, W = 0, epl = 1, nrows = 0;
     bool cw = false;
-    int nblk[kBasisMaxWarps] = {0}, row0[kBasisMaxWarps] = {0};
+    int nleaf[kBasisMaxWarps] = {0}, row0[kBasisMaxWarps] = {0};
     size_t smem = 0;
 };
 struct BLeaf { unsigned c0, c1; std::vector<double> w; };     // slot codes; w: [nch][cs] = (p, -q) pairs
@@ -732,8 +732,8 @@ static bool pack_bstream(aceb200_model* m, std::vector<std::vector<BLeaf>>& rows
 {
     HostTables& T = m->T;
     out.nw = 0;
-    int QB, KB, W;
-    if (!basis_geom(nfac, nch, cw, QB, KB, W)) return false;
+    int LB, LPC, HDR, W;
+    if (!basis_geom(nfac, nch, cw, LB, LPC, HDR, W)) return false;
     const int cs = cw ? 2 : 1, nrows = (int)rows.size();
     const unsigned ONE = (unsigned)T.nS;
     const bool masked = (nfac == 3 && nch >= 3 && nch <= 9);     // BasisGeom::MASKED: channel mask in bits 16.. of the second code word
@@ -747,7 +747,7 @@ static bool pack_bstream(aceb200_model* m, std::vector<std::vector<BLeaf>>& rows
         nleaves += r.size();
     }
     auto smem_of = [&](int nw, int epl) {
-        return (size_t)(T.nS + 1) * 32 * epl * sizeof(c2) + (size_t)nw * 4 * KB * QB * 16 + (size_t)nw * 32 * epl * (W | 1) * sizeof(double)
+        return (size_t)(T.nS + 1) * 32 * epl * sizeof(c2) + (size_t)nw * 4 * LPC * LB + (size_t)nw * 32 * epl * (W | 1) * sizeof(double)
              + (size_t)(1 + 4 * nw) * 8;
     };
     // The kernel is latency-bound (dependent FP64 chains): what counts is warps per SM, so take as many as fit in shared
@@ -778,35 +778,32 @@ static bool pack_bstream(aceb200_model* m, std::vector<std::vector<BLeaf>>& rows
           while (w < nw && acc * nw >= tot * w) cut[w++] = r + 1;
       } }
     size_t longest = 1;
-    for (int w = 0; w < nw; ++w) { size_t nl = 0; for (int r = cut[w]; r < cut[w + 1]; ++r) nl += rows[r].size(); longest = std::max(longest, (nl + 3) / 4); }
-    const size_t nchunks = (longest + KB - 1) / KB;
-    std::vector<uint32_t> blocks((size_t)nw * nchunks * KB * QB * 4, 0u);
-    const int cwords = nfac <= 2 ? 1 : 2;
+    for (int w = 0; w < nw; ++w) { size_t nl = 0; for (int r = cut[w]; r < cut[w + 1]; ++r) nl += rows[r].size(); longest = std::max(longest, nl); }
+    const size_t nchunks = (longest + LPC - 1) / LPC;
+    const size_t chunk_bytes = (size_t)LPC * LB;
+    std::vector<uint32_t> blocks((size_t)nw * nchunks * chunk_bytes / 4, 0u);
     for (int w = 0; w < nw; ++w) {
         size_t il = 0;
-        auto emit = [&](const BLeaf* L) {
-            uint32_t* blk = &blocks[(((size_t)w * nchunks * KB) + il / 4) * QB * 4];
-            const int k = (int)(il % 4);
-            blk[k] = L ? L->c0 : (ONE | (ONE << 16));
-            if (cwords == 2) blk[4 + k] = L ? L->c1 : (masked ? ONE : (ONE | (ONE << 16)));
-            double* wd = reinterpret_cast<double*>(blk + 4 * cwords) + (size_t)k * nch * cs;
-            for (int i = 0; i < nch * cs; ++i) wd[i] = L ? L->w[i] : 0.0;
-            ++il;
-        };
-        for (int r = cut[w]; r < cut[w + 1]; ++r) for (const BLeaf& L : rows[r]) emit(&L);
-        out.nblk[w] = (int)((il + 3) / 4);
-        while (il % 4) emit(nullptr);                  // inert leaves: zero weights, no row end
+        for (int r = cut[w]; r < cut[w + 1]; ++r)
+            for (const BLeaf& L : rows[r]) {
+                unsigned char* rec = reinterpret_cast<unsigned char*>(blocks.data()) + ((size_t)w * nchunks + il / LPC) * chunk_bytes + (il % LPC) * LB;
+                uint32_t hdr[2] = {L.c0, L.c1};
+                memcpy(rec, hdr, 8);
+                memcpy(rec + HDR, L.w.data(), (size_t)nch * cs * sizeof(double));
+                ++il;
+            }
+        out.nleaf[w] = (int)il;
         out.row0[w] = cut[w];
     }
     out.buf.reserve(blocks.size() * 4 + 4096);
     CU(cudaMemcpy(out.buf.p, blocks.data(), blocks.size() * 4, cudaMemcpyHostToDevice));
-    out.nw = nw; out.nchunks = (int)nchunks; out.nfac = nfac; out.nch = nch; out.cw = cw; out.QB = QB; out.KB = KB; out.W = W; out.epl = epl;
+    out.nw = nw; out.nchunks = (int)nchunks; out.nfac = nfac; out.nch = nch; out.cw = cw; out.LB = LB; out.LPC = LPC; out.W = W; out.epl = epl;
     out.nrows = nrows; out.smem = smem_of(nw, epl);
     if (getenv("ACEB200_VERBOSE")) {
         size_t active = 0;
         for (auto& r : rows) for (const BLeaf& L : r) active += masked ? __builtin_popcount(L.c1 >> 16) : nch;
-        fprintf(stderr, "[aceb200] %s stream: NFAC=%d NCH=%d CW=%d EPL=%d, %d warps x %zu chunks of %d blocks, %zu leaves in %d rows (%.2f active channels per leaf), smem %zu B\n",
-                what, nfac, nch, (int)cw, epl, nw, nchunks, KB, nleaves, nrows, (double)active / std::max<size_t>(nleaves, 1), out.smem);
+        fprintf(stderr, "[aceb200] %s stream: NFAC=%d NCH=%d CW=%d EPL=%d, %d warps x %zu chunks of %d leaves, %zu leaves in %d rows (%.2f active channels per leaf), smem %zu B\n",
+                what, nfac, nch, (int)cw, epl, nw, nchunks, LPC, nleaves, nrows, (double)active / std::max<size_t>(nleaves, 1), out.smem);
     }
     return true;
 }
@@ -878,7 +875,7 @@ static bool launch_bstream(aceb200_model* m, const BStream& S, long long ne, lon
     BasisParams p;
     memset(&p, 0, sizeof(p));
     p.nS = T.nS; p.nw = S.nw; p.nchunks = S.nchunks;
-    for (int w = 0; w < S.nw; ++w) { p.nblk[w] = S.nblk[w]; p.row0[w] = S.row0[w]; }
+    for (int w = 0; w < S.nw; ++w) { p.nleaf[w] = S.nleaf[w]; p.row0[w] = S.row0[w]; }
     p.stream = S.buf.as<uint4>();
     p.Ac = t_cur->ws_Ac.as<c2>(); p.ldA = ldA; p.out = out; p.rowlen = (long long)S.nrows * S.nch; p.nenv = ne;
     const long long ntiles = (ne + 32 * S.epl - 1) / (32 * S.epl);

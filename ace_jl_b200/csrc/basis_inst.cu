@@ -36,13 +36,14 @@ bool launch_basis_inst(int nfac, int nch, bool cw, int epl, const BasisParams& p
 }
 
 // host mirror of BasisGeom for the supported combinations
-bool basis_geom(int nfac, int nch, bool cw, int& QB, int& KB, int& W)
+bool basis_geom(int nfac, int nch, bool cw, int& LB, int& LPC, int& HDR, int& W)
 {
-    const int cs = cw ? 2 : 1, cwords = nfac <= 2 ? 1 : 2;
+    const int cs = cw ? 2 : 1, nwd = nch * cs;
     if (!((nch == 1 || nch == 2) || (cw && (nch == 3 || nch == 6 || nch == 9 || nch == 18)))) return false;
     if (nfac < 1 || nfac > 4) return false;
-    QB = cwords + 2 * nch * cs;
-    KB = (QB * 16 >= 1024) ? 1 : (QB * 16 >= 512) ? 2 : ((QB * 16 >= 256) ? 4 : ((QB * 16 >= 128) ? 8 : 16));
+    HDR = (nwd == 1) ? 8 : 16;
+    LB = (HDR + 8 * nwd + 15) / 16 * 16;
+    LPC = std::max(1, 1024 / LB);
     W = (nch >= 9 ? 1 : (16 + nch - 1) / nch) * nch;
     return true;
 }
