@@ -424,7 +424,7 @@ def main():
             line["e2e"] = primary
         if e2e_struct and e2e_env:
             line["e2e_per_environment"] = e2e_env
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:          # the CPU baseline is a rank-0, N = 1 leg
             sample = args.cpu_envs or default_cpu_sample(w, basis)
             rate, cores, dtc, passes = cpu_reference_rate(w, basis, c, sample)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
