@@ -1082,12 +1082,15 @@ struct BasisGeom {
     static constexpr int NWD = NCH * CS;                                 // weights (doubles) per leaf
     static constexpr int HDR = (NWD == 1) ? 8 : 16;
     static constexpr int LB = (HDR + 8 * NWD + 15) / 16 * 16;            // bytes per leaf
-    static constexpr int LPC = (1024 / LB > 0) ? 1024 / LB : 1;          // leaves per ring chunk (~1 KB; 2 KB chunks measured the same at 4b)
+    static constexpr int LPC = (LB <= 32) ? 512 / LB : ((1024 / LB > 0) ? 1024 / LB : 1);   // leaves per ring chunk (~1 KB; 2 KB chunks measured the
+                                                                         // same at 4b; 512 B for the 16-byte leaves keeps the rings small)
     static constexpr int CH = LPC * LB / 16;                             // uint4 per chunk
     static constexpr int NSLOT = 4;                                      // ring slots: three chunks in flight ahead of the one being read (a
                                                                          // two-slot ring left the L2 latency of the ~1 KB chunks exposed: the
                                                                          // mbarrier wait was the top stall of the 9- and 16-channel streams)
-    static constexpr int ROWS = (NCH >= 9) ? 1 : (16 + NCH - 1) / NCH;   // rows staged per flush (>= 72 contiguous bytes per environment)
+    static constexpr int ROWS = (NCH >= 9) ? 1 : (NCH <= 2) ? 4 / NCH : (16 + NCH - 1) / NCH;   // rows staged per flush: >= 72 contiguous bytes per
+                                                                         // environment; one 32-byte sector for 1 / 2 channels, where a small
+                                                                         // staging area lets two CTAs share an SM (the tile loads then overlap)
     static constexpr int W = ROWS * NCH;                                 // doubles staged per environment
     static constexpr int WP = W | 1;                                     // odd pitch: conflict-free staging
 };

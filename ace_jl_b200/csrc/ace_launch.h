@@ -34,6 +34,7 @@ void stream_inst_nf4(int pb, bool cw, int epl, const StreamParams& p, int grid, 
 
 bool launch_basis_inst(int nfac, int nch, bool cw, int epl, const BasisParams& p, int grid, size_t smem, cudaStream_t st);
 bool basis_geom(int nfac, int nch, bool cw, int& LB, int& LPC, int& HDR, int& W);
+int basis_blocks_per_sm(int nfac, int nch, bool cw, int epl, int threads, size_t smem);
 bool basis_epl2(int nch, bool cw);
 
 inline void launch_stream_inst(int nf, int pb, bool cw, int epl, const StreamParams& p, int grid, size_t smem, cudaStream_t st)

@@ -758,6 +758,12 @@ static bool pack_bstream(aceb200_model* m, std::vector<std::vector<BLeaf>>& rows
     if (epl == 2 && smem_of(8, 2) > (size_t)m->smem_optin) epl = 1;
     int nw = (epl == 2 && nch >= 9) ? 12 : kBasisMaxWarps;
     while (nw > 1 && smem_of(nw, epl) > (size_t)m->smem_optin) --nw;
+    // two CTAs of 12 (10, 8) warps per SM when they fit: the TMA load of one CTA's next A tile then overlaps the other's walk
+    // (config 1: 39 leaves per warp and tile -- with one CTA per SM the tile load was exposed, issue slots 32 % busy)
+    if (!getenv("ACEB200_BASIS_ONE_CTA"))
+        for (int w2 : {12, 10, 8})
+            if (2 * (smem_of(w2, epl) + 1024) <= (size_t)m->smem_optin + 1024
+                && basis_blocks_per_sm(nfac, nch, cw, epl, 32 * w2, smem_of(w2, epl)) >= 2) { nw = w2; break; }   // (the register file must hold both)
     if (const char* ov = getenv("ACEB200_BASIS_WARPS")) nw = std::max(1, std::min(nw, atoi(ov)));
     if (smem_of(nw, epl) > (size_t)m->smem_optin) return false;
     nw = std::min(nw, std::max(1, nrows));

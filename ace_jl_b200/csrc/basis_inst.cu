@@ -35,6 +35,44 @@ bool launch_basis_inst(int nfac, int nch, bool cw, int epl, const BasisParams& p
     }
 }
 
+// resident CTAs per SM of an instantiation at a given geometry (registers and shared memory both count)
+template <int NFAC, int NCH, bool CW, int EPL>
+static int basis_occ(int threads, size_t smem)
+{
+#ifdef ACEB200_EMU
+    (void)threads; (void)smem;
+    return 2;
+#else
+    auto kfn = k_basis_stream<NFAC, NCH, CW, EPL>;
+    int nb = 0;
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kfn, threads, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return nb;
+#endif
+}
+
+template <int NFAC>
+static int basis_occ_nfac(int nch, bool cw, int epl, int threads, size_t smem)
+{
+#define ACE_B(N, C) if (nch == N && cw == C) { constexpr bool E2 = (N <= 9);                                   \
+                                               if (epl == 2 && E2) return basis_occ<NFAC, N, C, (E2 ? 2 : 1)>(threads, smem);  \
+                                               return basis_occ<NFAC, N, C, 1>(threads, smem); }
+    ACE_B(1, false) ACE_B(2, false)
+    ACE_B(1, true) ACE_B(2, true) ACE_B(3, true) ACE_B(6, true) ACE_B(9, true) ACE_B(18, true)
+#undef ACE_B
+    return 0;
+}
+
+int basis_blocks_per_sm(int nfac, int nch, bool cw, int epl, int threads, size_t smem)
+{
+    switch (nfac) {
+    case 1: case 2: return basis_occ_nfac<2>(nch, cw, epl, threads, smem);
+    case 3: return basis_occ_nfac<3>(nch, cw, epl, threads, smem);
+    case 4: return basis_occ_nfac<4>(nch, cw, epl, threads, smem);
+    default: return 0;
+    }
+}
+
 // host mirror of BasisGeom for the supported combinations
 bool basis_geom(int nfac, int nch, bool cw, int& LB, int& LPC, int& HDR, int& W)
 {
@@ -43,8 +81,8 @@ bool basis_geom(int nfac, int nch, bool cw, int& LB, int& LPC, int& HDR, int& W)
     if (nfac < 1 || nfac > 4) return false;
     HDR = (nwd == 1) ? 8 : 16;
     LB = (HDR + 8 * nwd + 15) / 16 * 16;
-    LPC = std::max(1, 1024 / LB);
-    W = (nch >= 9 ? 1 : (16 + nch - 1) / nch) * nch;
+    LPC = (LB <= 32) ? 512 / LB : std::max(1, 1024 / LB);
+    W = (nch >= 9 ? 1 : nch <= 2 ? 4 / nch : (16 + nch - 1) / nch) * nch;
     return true;
 }
 
