@@ -1912,7 +1912,7 @@ struct dAParams {
 
 // dA[j][iA][:] = grad phi_iA(r_j) (src/product_1pbasis.jl:169-221), one thread per neighbour
 template <int NMAX>
-__global__ void __launch_bounds__(128) k_dA(const dAParams p)
+__global__ void __launch_bounds__(128, 4) k_dA(const dAParams p)   // 4 CTAs per SM (128 registers, 168 B of spills at NMAX = 12): 0.38 -> 0.26 ms per 6 x 10^5 neighbours; 6 CTAs (80 registers) 0.50 ms
 {
     const long long jl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (jl >= p.nJ) return;
